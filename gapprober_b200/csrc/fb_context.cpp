@@ -1,0 +1,852 @@
+// fb_context.cpp — host side of libfigbird_cuda.so: the C ABI of include/figbird_cuda.h.
+//
+// Orchestrates GapFiller::fillGap (figbird.cpp:2436-2510) for a whole gap set on one GPU:
+//   pack records once (the reference re-parses the gap file 5*E times, figbird.cpp:1680-1812)
+//   -> EM scan of every (gap, estimate) unit on the device (fb_kernels.cu)
+//   -> per-unit likelihood = sum of glibc log() over per-record maxima, in record order, on the host
+//      (figbird.cpp:1951-1955; the host libm is the reference's libm, so the '>=' selection of
+//      figbird.cpp:2479 sees the same bits)
+//   -> finalize scoring on the device, cut-off test / counting / computeSequence(1) on the host.
+// There is no CPU implementation of the EM in here: without a CUDA device fb_create fails.
+
+#include "../../include/figbird_cuda.h"
+#include "fb_device.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+inline int base_code(char ch) {   // charCodes, figbird.cpp:2753-2776
+    switch (ch) {
+        case 'A': return 0;
+        case 'C': return 1;
+        case 'G': return 2;
+        case 'T': return 3;
+        default: return 4;
+    }
+}
+
+inline int revcomp_code(char ch) {   // reverse(), figbird.cpp:1382-1403, then charCodes
+    switch (ch) {
+        case 'A': case 'a': return 3;
+        case 'C': case 'c': return 2;
+        case 'G': case 'g': return 1;
+        case 'T': case 't': return 0;
+        default: return 4;
+    }
+}
+
+struct HostGap {
+    int contig_no;
+    long gap_start;
+    int orig, gmin, gmax;
+    int rec_off, nrec, lmax;
+    bool owned = true;
+    double cost = 0;
+    // results
+    bool done = false;
+    int best_est = 0;
+    double best_lik = 0;
+    int total_reads = 0, discarded = 0;
+    long likelihoods = 0;
+    std::string filled, best_string;
+    std::vector<double> liks;
+    int unit_first = -1;   // index of the gmin unit in ctx->unit_of (by estimate order)
+};
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t ensure(size_t want) {
+        if (want <= n && p) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+        if (want == 0) want = 1;
+        cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+        if (e == cudaSuccess) n = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+template <typename T>
+struct PinBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t ensure(size_t want) {
+        if (want <= n && p) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        n = 0;
+        if (want == 0) want = 1;
+        cudaError_t e = cudaMallocHost((void**)&p, want * sizeof(T));
+        if (e == cudaSuccess) n = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+struct Bin {
+    int first_unit, n_units;      // range in the sorted unit array
+    int gpmax, lmax;
+    int nr_stride, gp_stride, p_stride, chunk;
+    bool global_tables;
+    size_t smem;
+    int grid;
+};
+
+}  // namespace
+
+struct fb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    int max_smem = 0, sm_count = 0;
+    std::string err;
+
+    // model (host copies)
+    int max_read_len = 0, thr_min = 0, thr_max = 0, cutoff = 0, D = 200, num_iter = 5;
+    double T[25];
+    std::vector<double> epos, match;
+    // model (device)
+    DevBuf<double2> d_eo;
+    DevBuf<double> d_ild, d_epos, d_match;
+
+    // gaps + records (host staging)
+    std::vector<HostGap> gaps;
+    std::vector<FbGapMeta> h_gapmeta;
+    std::vector<uint8_t> h_flank;
+    std::vector<uint4> h_codes, h_nmask;
+    std::vector<FbRecMeta> h_rmeta;
+    std::vector<uint8_t> h_bytes;     // per record FB_MAX_READ scoring-orientation codes (host finalize)
+    int part_rank = 0, part_world = 1;
+
+    // units
+    std::vector<FbUnit> h_units;
+    std::vector<int> unit_nrec;
+    std::vector<Bin> bins;
+    bool uploaded = false, ran = false;
+
+    // device
+    DevBuf<FbGapMeta> d_gapmeta;
+    DevBuf<uint8_t> d_flank;
+    DevBuf<uint4> d_codes, d_nmask;
+    DevBuf<FbRecMeta> d_rmeta;
+    DevBuf<FbUnit> d_units;
+    DevBuf<int> d_counters;
+    DevBuf<double> d_maxprob, d_gws, d_finprob, d_dump;
+    DevBuf<char> d_cons;
+    DevBuf<int> d_finpos, d_gaplist, d_bestgp;
+    DevBuf<long long> d_bestoff;
+    PinBuf<double> h_maxprob, h_finprob;
+    PinBuf<int> h_finpos;
+
+    fb_stats stats;
+
+    int fail(int code, const char* fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+};
+
+#define FB_CUDA(ctx, call)                                                                             \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess) return (ctx)->fail(FB_ECUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+extern "C" {
+
+int fb_abi_version(void) { return FB_ABI_VERSION; }
+
+const char* fb_status_str(int s) {
+    switch (s) {
+        case FB_OK: return "ok";
+        case FB_EINVAL: return "invalid argument";
+        case FB_EDOMAIN: return "input outside the reference's defined territory";
+        case FB_ECUDA: return "CUDA error";
+        case FB_ENOMEM: return "out of memory";
+        case FB_ESTATE: return "call out of order";
+        case FB_EUNSUPPORTED: return "unsupported mode";
+        default: return "unknown status";
+    }
+}
+
+const char* fb_last_error(fb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+void fb_gap_range(int orig_gap, int* gap_min, int* gap_max) {
+    // figbird.cpp:2438-2453: float fractions, int*float evaluated in float, truncation on assignment.
+    float lo, hi;
+    if (orig_gap > 300) lo = .95;
+    else if (orig_gap < 100) lo = 0.1;
+    else lo = 0.85;
+    if (orig_gap > 200) hi = 1.05;
+    else hi = 1.5;
+    *gap_min = orig_gap * lo < 10 ? 1 : orig_gap * lo;
+    *gap_max = orig_gap * hi;
+}
+
+int fb_create(const fb_model* m, int device, fb_ctx** out) {
+    if (!m || !out) return FB_EINVAL;
+    *out = nullptr;
+    if (m->f_mode != 0) return FB_EUNSUPPORTED;
+    if (m->max_read_len < 1 || m->max_distance < 1 || m->num_iter < 1 || !m->error_pos || !m->in_pos || !m->del_pos || !m->ild)
+        return FB_EINVAL;
+    if (m->thr_min < 0 || m->thr_max < m->thr_min || m->thr_max >= m->ild_len) return FB_EINVAL;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || device < 0 || device >= ndev) return FB_ECUDA;
+    fb_ctx* c = new fb_ctx();
+    c->device = device;
+    memset(&c->stats, 0, sizeof c->stats);
+    auto bail = [&](int code) {
+        fb_destroy(c);
+        return code;
+    };
+    if (cudaSetDevice(device) != cudaSuccess) return bail(FB_ECUDA);
+    if (fb_kernels_init(&c->max_smem, &c->sm_count) != cudaSuccess) return bail(FB_ECUDA);
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FB_ECUDA);
+    cudaEventCreate(&c->ev0);
+    cudaEventCreate(&c->ev1);
+    cudaEventCreate(&c->ev2);
+    cudaEventCreate(&c->ev3);
+    c->max_read_len = m->max_read_len;
+    c->thr_min = m->thr_min;
+    c->thr_max = m->thr_max;
+    c->cutoff = m->gap_prob_cutoff;
+    c->D = m->max_distance;
+    c->num_iter = m->num_iter;
+    for (int i = 0; i < 5; i++)
+        for (int j = 0; j < 5; j++) c->T[i * 5 + j] = m->error_type[i][j];
+    const int n = std::min(m->max_read_len, FB_MAX_READ);
+    std::vector<double2> eo(FB_MAX_READ, make_double2(0, 0));
+    c->epos.assign(FB_MAX_READ, 0.0);
+    c->match.assign(FB_MAX_READ, 0.0);
+    for (int k = 0; k < n; k++) {
+        eo[k] = make_double2(1 - m->error_pos[k], m->error_pos[k]);                 // figbird.cpp:1855
+        c->epos[k] = m->error_pos[k];
+        c->match[k] = 1 - m->error_pos[k] - m->in_pos[k] - m->del_pos[k];           // figbird.cpp:2272
+    }
+    const int pwin = m->thr_max - m->thr_min + 1;
+    if (c->d_eo.ensure(FB_MAX_READ) || c->d_ild.ensure(pwin) || c->d_epos.ensure(FB_MAX_READ) || c->d_match.ensure(FB_MAX_READ))
+        return bail(FB_ECUDA);
+    cudaMemcpy(c->d_eo.p, eo.data(), sizeof(double2) * FB_MAX_READ, cudaMemcpyHostToDevice);
+    cudaMemcpy(c->d_ild.p, m->ild + m->thr_min, sizeof(double) * pwin, cudaMemcpyHostToDevice);
+    cudaMemcpy(c->d_epos.p, c->epos.data(), sizeof(double) * FB_MAX_READ, cudaMemcpyHostToDevice);
+    cudaMemcpy(c->d_match.p, c->match.data(), sizeof(double) * FB_MAX_READ, cudaMemcpyHostToDevice);
+    if (cudaDeviceSynchronize() != cudaSuccess) return bail(FB_ECUDA);
+    *out = c;
+    return FB_OK;
+}
+
+void fb_destroy(fb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    c->d_eo.release(); c->d_ild.release(); c->d_epos.release(); c->d_match.release();
+    c->d_gapmeta.release(); c->d_flank.release(); c->d_codes.release(); c->d_nmask.release(); c->d_rmeta.release();
+    c->d_units.release(); c->d_counters.release(); c->d_maxprob.release(); c->d_gws.release(); c->d_finprob.release();
+    c->d_dump.release(); c->d_cons.release(); c->d_finpos.release(); c->d_gaplist.release(); c->d_bestgp.release();
+    c->d_bestoff.release();
+    c->h_maxprob.release(); c->h_finprob.release(); c->h_finpos.release();
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev2) cudaEventDestroy(c->ev2);
+    if (c->ev3) cudaEventDestroy(c->ev3);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int fb_clear_gaps(fb_ctx* c) {
+    if (!c) return FB_EINVAL;
+    c->gaps.clear(); c->h_gapmeta.clear(); c->h_flank.clear(); c->h_codes.clear(); c->h_nmask.clear();
+    c->h_rmeta.clear(); c->h_bytes.clear(); c->h_units.clear(); c->unit_nrec.clear(); c->bins.clear();
+    c->uploaded = c->ran = false;
+    return FB_OK;
+}
+
+int fb_add_gap(fb_ctx* c, int contig_no, long gap_start, int orig_gap, const char* contig, long contig_len,
+               const fb_record* recs, int nrec) {
+    if (!c || !contig || nrec < 0 || (nrec > 0 && !recs)) return FB_EINVAL;
+    const int D = c->D;
+    // Outside these bounds the reference indexes past its arrays: refuse.
+    if (orig_gap < 1 || gap_start < D || gap_start + orig_gap + D > contig_len)
+        return c->fail(FB_EDOMAIN, "gap at %ld (+%d) is closer than %d to a scaffold end", gap_start, orig_gap, D);
+    for (int r = 0; r < nrec; r++) {
+        if (recs[r].len2 < 1 || recs[r].len2 > FB_MAX_READ || recs[r].len2 > c->max_read_len || recs[r].len2 > D || !recs[r].seq2)
+            return c->fail(FB_EDOMAIN, "record %d: mate length %d unsupported", r, recs[r].len2);
+    }
+    HostGap g;
+    g.contig_no = contig_no;
+    g.gap_start = gap_start;
+    g.orig = orig_gap;
+    fb_gap_range(orig_gap, &g.gmin, &g.gmax);
+    if (g.gmax < g.gmin) return c->fail(FB_EDOMAIN, "empty estimate range for gap length %d", orig_gap);
+    g.rec_off = (int)c->h_rmeta.size();
+    g.nrec = nrec;
+    g.lmax = 1;
+    // flanks: D bases before the gap, D bases after the ORIGINAL gap (figbird.cpp:1657-1670)
+    const size_t fo = c->h_flank.size();
+    c->h_flank.resize(fo + 2 * (size_t)D);
+    for (int i = 0; i < D; i++) {
+        c->h_flank[fo + i] = (uint8_t)base_code(contig[gap_start - D + i]);
+        c->h_flank[fo + D + i] = (uint8_t)base_code(contig[gap_start + orig_gap + i]);
+    }
+    const long sp = gap_start - D;
+    for (int r = 0; r < nrec; r++) {
+        const fb_record& rc = recs[r];
+        const int L2 = rc.len2;
+        g.lmax = std::max(g.lmax, L2);
+        const bool rev = rc.strand1 == 0;             // isReverse, figbird.cpp:1803-1812
+        const bool left = rc.pos1 < gap_start;        // figbird.cpp:1822
+        uint32_t cw[8] = {0, 0, 0, 0, 0, 0, 0, 0}, nm[4] = {0, 0, 0, 0};
+        const size_t bo = c->h_bytes.size();
+        c->h_bytes.resize(bo + FB_MAX_READ, 5);
+        for (int j = 0; j < L2; j++) {
+            int code = rev ? revcomp_code(rc.seq2[L2 - 1 - j]) : base_code(rc.seq2[j]);
+            c->h_bytes[bo + j] = (uint8_t)code;
+            if (code < 4) cw[j >> 4] |= (uint32_t)code << (2 * (j & 15));
+            else nm[j >> 5] |= 1u << (j & 31);
+        }
+        c->h_codes.push_back(make_uint4(cw[0], cw[1], cw[2], cw[3]));
+        c->h_codes.push_back(make_uint4(cw[4], cw[5], cw[6], cw[7]));
+        c->h_nmask.push_back(make_uint4(nm[0], nm[1], nm[2], nm[3]));
+        FbRecMeta m;
+        long tb, lo, hi;
+        if (left) {          // t = u + tb
+            tb = sp - rc.pos1 + L2;
+            lo = c->thr_min - tb;
+            hi = c->thr_max - tb;
+        } else {             // t = tb - u
+            tb = (long)rc.pos1 + rc.len1 - sp;
+            lo = tb - c->thr_max;
+            hi = tb - c->thr_min;
+        }
+        const long LIM = 1L << 30;
+        m.tb = (int)std::max(-LIM, std::min(LIM, tb));
+        m.a_lo = (int)std::max(-LIM, std::min(LIM, lo));
+        m.a_hi = (int)std::max(-LIM, std::min(LIM, hi));
+        m.flags = L2 | (rev ? 256 : 0) | (left ? 512 : 0);
+        c->h_rmeta.push_back(m);
+    }
+    FbGapMeta gm;
+    gm.rec_off = g.rec_off;
+    gm.nrec = nrec;
+    gm.orig = orig_gap;
+    gm.lmax = g.lmax;
+    c->h_gapmeta.push_back(gm);
+    c->gaps.push_back(g);
+    c->uploaded = c->ran = false;
+    return (int)c->gaps.size() - 1;
+}
+
+}  // extern "C"
+
+namespace {
+
+// placements of record m that pass the window test for estimate gp
+inline long placements(const FbRecMeta& m, int D, int gp) {
+    const int L2 = m.flags & 0xff;
+    long lo = std::max(m.a_lo, D - L2 + 1), hi = std::min(m.a_hi, D + gp - 1);
+    return hi >= lo ? hi - lo + 1 : 0;
+}
+
+void gap_cost(fb_ctx* c, HostGap& g) {
+    double cost = 0;
+    for (int gp = g.gmin; gp <= g.gmax; gp++)
+        for (int r = 0; r < g.nrec; r++) {
+            const FbRecMeta& m = c->h_rmeta[g.rec_off + r];
+            cost += (double)placements(m, c->D, gp) * (m.flags & 0xff);
+        }
+    g.cost = cost + 1000.0 * (g.gmax - g.gmin + 1);
+}
+
+}  // namespace
+
+extern "C" {
+
+int fb_set_partition(fb_ctx* c, int rank, int world) {
+    if (!c || world < 1 || rank < 0 || rank >= world) return FB_EINVAL;
+    c->part_rank = rank;
+    c->part_world = world;
+    // longest-processing-time first: gaps by descending cost, each to the least loaded rank
+    std::vector<int> order(c->gaps.size());
+    for (size_t i = 0; i < order.size(); i++) {
+        order[i] = (int)i;
+        gap_cost(c, c->gaps[i]);
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return c->gaps[a].cost > c->gaps[b].cost; });
+    std::vector<double> load(world, 0.0);
+    for (int gi : order) {
+        int best = 0;
+        for (int r = 1; r < world; r++)
+            if (load[r] < load[best]) best = r;
+        load[best] += c->gaps[gi].cost;
+        c->gaps[gi].owned = best == rank;
+    }
+    c->uploaded = c->ran = false;
+    return FB_OK;
+}
+
+int fb_owns_gap(fb_ctx* c, int gap) {
+    if (!c || gap < 0 || gap >= (int)c->gaps.size()) return 0;
+    return c->gaps[gap].owned ? 1 : 0;
+}
+
+int fb_upload(fb_ctx* c) {
+    if (!c) return FB_EINVAL;
+    FB_CUDA(c, cudaSetDevice(c->device));
+    const int D = c->D, pwin = c->thr_max - c->thr_min + 1;
+    // ---- units: every (owned gap, estimate); heaviest first so persistent CTAs balance (LPT)
+    struct U { int gap, gp; double cost; long liks; };
+    std::vector<U> us;
+    fb_stats& st = c->stats;
+    memset(&st, 0, sizeof st);
+    for (size_t gi = 0; gi < c->gaps.size(); gi++) {
+        HostGap& g = c->gaps[gi];
+        g.done = false;
+        g.likelihoods = 0;
+        if (!g.owned) continue;
+        st.n_gaps++;
+        st.n_records += g.nrec;
+        for (int gp = g.gmin; gp <= g.gmax; gp++) {
+            double cost = 0;
+            long liks = 0, terms = 0;
+            for (int r = 0; r < g.nrec; r++) {
+                const FbRecMeta& m = c->h_rmeta[g.rec_off + r];
+                long pl = placements(m, D, gp);
+                liks += pl;
+                terms += pl * (m.flags & 0xff);
+            }
+            cost = (double)terms + 2000.0;
+            us.push_back({(int)gi, gp, cost, liks});
+            g.likelihoods += liks * c->num_iter;
+            st.likelihoods += liks * c->num_iter;
+            st.base_terms += terms * c->num_iter;
+            // packed bases + mask + meta in, counts out / profile in, per-record maximum out
+            long bytes = 0;
+            for (int r = 0; r < g.nrec; r++) {
+                int L2 = c->h_rmeta[g.rec_off + r].flags & 0xff;
+                bytes += (L2 + 3) / 4 + (L2 + 7) / 8 + 8 + 8;
+            }
+            bytes += 2L * 40 * gp;
+            st.algorithmic_bytes += bytes * c->num_iter;
+        }
+    }
+    st.n_units = (long)us.size();
+    // bins by estimate size (shared-memory footprint decides occupancy), then cost-descending inside a bin
+    static const int edges[] = {96, 160, 256, 384, 544, 768, 1024, 1536, 2048, 3072, 4096, 6144, 8192, 1 << 30};
+    auto bin_of = [&](int gp) {
+        int b = 0;
+        while (gp > edges[b]) b++;
+        return b;
+    };
+    std::stable_sort(us.begin(), us.end(), [&](const U& a, const U& b) {
+        int ba = bin_of(a.gp), bb = bin_of(b.gp);
+        if (ba != bb) return ba > bb;       // big bins first: they have the longest units
+        return a.cost > b.cost;
+    });
+    c->h_units.resize(us.size());
+    c->unit_nrec.resize(us.size());
+    c->bins.clear();
+    long long mp = 0, co = 0;
+    for (size_t i = 0; i < us.size(); i++) {
+        FbUnit u;
+        u.gap = us[i].gap;
+        u.gp = us[i].gp;
+        u.mp_off = mp;
+        u.cons_off = co;
+        mp += c->gaps[u.gap].nrec;
+        co += u.gp;
+        c->h_units[i] = u;
+        c->unit_nrec[i] = c->gaps[u.gap].nrec;
+        int b = bin_of(u.gp);
+        if (c->bins.empty() || bin_of(c->h_units[c->bins.back().first_unit].gp) != b) {
+            Bin nb;
+            memset(&nb, 0, sizeof nb);
+            nb.first_unit = (int)i;
+            c->bins.push_back(nb);
+        }
+        Bin& bn = c->bins.back();
+        bn.n_units++;
+        bn.gpmax = std::max(bn.gpmax, u.gp);
+        bn.lmax = std::max(bn.lmax, c->gaps[u.gap].lmax);
+    }
+    // ---- shared-memory geometry per bin
+    size_t gws_need = 0;
+    for (Bin& b : c->bins) {
+        b.nr_stride = b.gpmax + 2 * b.lmax - 2;
+        b.gp_stride = (b.gpmax + 1) & ~1;
+        b.p_stride = std::max(1, std::min(pwin, b.gpmax + b.lmax - 1));
+        const size_t two_cta = (size_t)(c->max_smem + 1024) / 2 - 1024 - 512;   // two CTAs per SM incl. 1 KB system reserve each
+        const size_t one_cta = (size_t)c->max_smem - 1024;
+        b.global_tables = false;
+        b.chunk = 0;
+        int ctas = 2;
+        for (int want : {16, 8}) {
+            if (fb_em_smem_bytes(b.nr_stride, b.gp_stride, b.p_stride, want, pwin, false) <= two_cta) { b.chunk = want; break; }
+        }
+        if (!b.chunk) {
+            ctas = 1;
+            for (int want : {32, 16, 8, 4}) {
+                if (fb_em_smem_bytes(b.nr_stride, b.gp_stride, b.p_stride, want, pwin, false) <= one_cta) { b.chunk = want; break; }
+            }
+        }
+        if (!b.chunk) {
+            b.global_tables = true;
+            for (int want : {32, 16, 8, 4, 2, 1}) {
+                if (fb_em_smem_bytes(b.nr_stride, b.gp_stride, b.p_stride, want, pwin, true) <= one_cta) { b.chunk = want; break; }
+            }
+            if (!b.chunk) return c->fail(FB_EINVAL, "insert window of %d placements does not fit shared memory", pwin);
+        }
+        b.smem = fb_em_smem_bytes(b.nr_stride, b.gp_stride, b.p_stride, b.chunk, pwin, b.global_tables);
+        b.grid = std::min(b.n_units, c->sm_count * ctas);
+        if (b.global_tables) gws_need = std::max(gws_need, (size_t)b.grid * ((size_t)10 * b.nr_stride + 5 * (size_t)b.gp_stride + 16));
+    }
+    // ---- device buffers + host->device copies
+    const size_t ng = c->h_gapmeta.size(), nr = c->h_rmeta.size();
+    FB_CUDA(c, c->d_gapmeta.ensure(ng));
+    FB_CUDA(c, c->d_flank.ensure(c->h_flank.size()));
+    FB_CUDA(c, c->d_codes.ensure(c->h_codes.size()));
+    FB_CUDA(c, c->d_nmask.ensure(c->h_nmask.size()));
+    FB_CUDA(c, c->d_rmeta.ensure(nr));
+    FB_CUDA(c, c->d_units.ensure(c->h_units.size()));
+    FB_CUDA(c, c->d_counters.ensure(c->bins.size() + 1));
+    FB_CUDA(c, c->d_maxprob.ensure((size_t)mp));
+    FB_CUDA(c, c->d_cons.ensure((size_t)co));
+    FB_CUDA(c, c->d_finprob.ensure(nr));
+    FB_CUDA(c, c->d_finpos.ensure(nr));
+    FB_CUDA(c, c->d_gaplist.ensure(ng));
+    FB_CUDA(c, c->d_bestgp.ensure(ng));
+    FB_CUDA(c, c->d_bestoff.ensure(ng));
+    if (gws_need) FB_CUDA(c, c->d_gws.ensure(gws_need));
+    FB_CUDA(c, c->h_maxprob.ensure((size_t)mp));
+    FB_CUDA(c, c->h_finprob.ensure(nr));
+    FB_CUDA(c, c->h_finpos.ensure(nr));
+    long h2d = 0;
+    auto up = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
+        h2d += (long)bytes;
+        return bytes ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream) : cudaSuccess;
+    };
+    FB_CUDA(c, up(c->d_gapmeta.p, c->h_gapmeta.data(), ng * sizeof(FbGapMeta)));
+    FB_CUDA(c, up(c->d_flank.p, c->h_flank.data(), c->h_flank.size()));
+    FB_CUDA(c, up(c->d_codes.p, c->h_codes.data(), c->h_codes.size() * sizeof(uint4)));
+    FB_CUDA(c, up(c->d_nmask.p, c->h_nmask.data(), c->h_nmask.size() * sizeof(uint4)));
+    FB_CUDA(c, up(c->d_rmeta.p, c->h_rmeta.data(), nr * sizeof(FbRecMeta)));
+    FB_CUDA(c, up(c->d_units.p, c->h_units.data(), c->h_units.size() * sizeof(FbUnit)));
+    FB_CUDA(c, cudaStreamSynchronize(c->stream));
+    st.h2d_bytes = h2d;
+    c->uploaded = true;
+    c->ran = false;
+    return FB_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+void fill_em_params(fb_ctx* c, FbEmParams& p) {
+    memset(&p, 0, sizeof p);
+    p.eo = c->d_eo.p;
+    p.ild = c->d_ild.p;
+    memcpy(p.T, c->T, sizeof p.T);
+    p.thr_min = c->thr_min;
+    p.thr_max = c->thr_max;
+    p.D = c->D;
+    p.num_iter = c->num_iter;
+    p.max_read_len = c->max_read_len;
+    p.gaps = c->d_gapmeta.p;
+    p.flank = c->d_flank.p;
+    p.codes = c->d_codes.p;
+    p.nmask = c->d_nmask.p;
+    p.rmeta = c->d_rmeta.p;
+    p.unit_maxprob = c->d_maxprob.p;
+    p.unit_cons = c->d_cons.p;
+    p.dump_unit = -1;
+    p.gws = c->d_gws.p;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fb_run_device(fb_ctx* c) {
+    if (!c) return FB_EINVAL;
+    if (!c->uploaded) return c->fail(FB_ESTATE, "fb_run_device before fb_upload");
+    FB_CUDA(c, cudaSetDevice(c->device));
+    fb_stats& st = c->stats;
+    const int D = c->D;
+    long d2h = 0;
+    st.em_launches = st.finalize_launches = 0;
+    st.finalize_likelihoods = 0;
+
+    // ---- EM scan: one persistent launch per size bin
+    FB_CUDA(c, cudaMemsetAsync(c->d_counters.p, 0, sizeof(int) * (c->bins.size() + 1), c->stream));
+    FB_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    for (size_t bi = 0; bi < c->bins.size(); bi++) {
+        const Bin& b = c->bins[bi];
+        FbEmParams p;
+        fill_em_params(c, p);
+        p.units = c->d_units.p + b.first_unit;
+        p.n_units = b.n_units;
+        p.work_counter = c->d_counters.p + bi;
+        p.nr_stride = b.nr_stride;
+        p.gp_stride = b.gp_stride;
+        p.p_stride = b.p_stride;
+        p.chunk = b.chunk;
+        p.gws_stride = (size_t)10 * b.nr_stride + 5 * (size_t)b.gp_stride + 16;
+        FB_CUDA(c, fb_launch_em(p, b.grid, b.global_tables, b.smem, c->stream));
+        st.em_launches++;
+    }
+    FB_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    size_t mp_total = 0;
+    if (!c->h_units.empty()) mp_total = (size_t)c->h_units.back().mp_off + c->unit_nrec.back();
+    if (mp_total) {
+        FB_CUDA(c, cudaMemcpyAsync(c->h_maxprob.p, c->d_maxprob.p, mp_total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        d2h += (long)(mp_total * sizeof(double));
+    }
+    FB_CUDA(c, cudaStreamSynchronize(c->stream));
+
+    // ---- likelihood per unit (figbird.cpp:1951-1955) and best estimate per gap (figbird.cpp:2479-2490)
+    for (HostGap& g : c->gaps) {
+        if (!g.owned) continue;
+        g.liks.assign(g.gmax - g.gmin + 1, 0.0);
+    }
+    std::vector<long long> cons_off_of_best(c->gaps.size(), 0);
+    std::vector<std::vector<long long>> cons_off(c->gaps.size());
+    for (size_t gi = 0; gi < c->gaps.size(); gi++)
+        if (c->gaps[gi].owned) cons_off[gi].assign(c->gaps[gi].gmax - c->gaps[gi].gmin + 1, 0);
+    for (size_t ui = 0; ui < c->h_units.size(); ui++) {
+        const FbUnit& u = c->h_units[ui];
+        HostGap& g = c->gaps[u.gap];
+        const double* mp = c->h_maxprob.p + u.mp_off;
+        double lik = 0;
+        for (int r = 0; r < g.nrec; r++)
+            if (mp[r] > 0) lik += log(mp[r]);
+        g.liks[u.gp - g.gmin] = lik;
+        cons_off[u.gap][u.gp - g.gmin] = u.cons_off;
+    }
+    std::vector<int> gaplist, bestgp(c->gaps.size(), 0);
+    for (size_t gi = 0; gi < c->gaps.size(); gi++) {
+        HostGap& g = c->gaps[gi];
+        if (!g.owned) continue;
+        double best = -DBL_MAX;
+        int be = g.gmin;
+        for (int gp = g.gmin; gp <= g.gmax; gp++) {
+            if (g.liks[gp - g.gmin] >= best) {   // last estimate wins ties
+                best = g.liks[gp - g.gmin];
+                be = gp;
+            }
+        }
+        g.best_lik = best;
+        g.best_est = be;
+        bestgp[gi] = be;
+        cons_off_of_best[gi] = cons_off[gi][be - g.gmin];
+        gaplist.push_back((int)gi);
+    }
+
+    // ---- finalize scoring on the device
+    if (!gaplist.empty()) {
+        FB_CUDA(c, cudaMemcpyAsync(c->d_gaplist.p, gaplist.data(), gaplist.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        FB_CUDA(c, cudaMemcpyAsync(c->d_bestgp.p, bestgp.data(), bestgp.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        FB_CUDA(c, cudaMemcpyAsync(c->d_bestoff.p, cons_off_of_best.data(), cons_off_of_best.size() * sizeof(long long),
+                                   cudaMemcpyHostToDevice, c->stream));
+        FbFinParams f;
+        memset(&f, 0, sizeof f);
+        f.ild = c->d_ild.p;
+        f.epos = c->d_epos.p;
+        f.match = c->d_match.p;
+        memcpy(f.T, c->T, sizeof f.T);
+        f.thr_min = c->thr_min;
+        f.thr_max = c->thr_max;
+        f.D = D;
+        f.gaps = c->d_gapmeta.p;
+        f.flank = c->d_flank.p;
+        f.codes = c->d_codes.p;
+        f.nmask = c->d_nmask.p;
+        f.rmeta = c->d_rmeta.p;
+        f.gap_list = c->d_gaplist.p;
+        f.best_gp = c->d_bestgp.p;
+        f.best_cons_off = c->d_bestoff.p;
+        f.unit_cons = c->d_cons.p;
+        f.fin_maxprob = c->d_finprob.p;
+        f.fin_maxpos = c->d_finpos.p;
+        int rows = 0;
+        for (int gi : gaplist) rows = std::max(rows, c->gaps[gi].best_est + 2 * c->gaps[gi].lmax);
+        f.gmax_stride = rows;
+        if ((size_t)rows + 16 > (size_t)c->max_smem - 8192) return c->fail(FB_EINVAL, "gap estimate %d too long for finalize", rows);
+        FB_CUDA(c, cudaEventRecord(c->ev2, c->stream));
+        FB_CUDA(c, fb_launch_finalize(f, (int)gaplist.size(), (size_t)rows + 16, c->stream));
+        FB_CUDA(c, cudaEventRecord(c->ev3, c->stream));
+        st.finalize_launches = 1;
+        const size_t nr = c->h_rmeta.size();
+        FB_CUDA(c, cudaMemcpyAsync(c->h_finprob.p, c->d_finprob.p, nr * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        FB_CUDA(c, cudaMemcpyAsync(c->h_finpos.p, c->d_finpos.p, nr * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        d2h += (long)(nr * (sizeof(double) + sizeof(int)));
+        FB_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+
+    // ---- finalize on the host: cut-off, +1 counts, computeSequence(1), getConcensus
+    std::vector<int> cnt;
+    for (int gi : gaplist) {
+        HostGap& g = c->gaps[gi];
+        const int gb = g.best_est;
+        cnt.assign((size_t)gb * 5, 0);
+        int disc = 0;
+        for (int r = 0; r < g.nrec; r++) {
+            const int rec = g.rec_off + r;
+            const FbRecMeta& m = c->h_rmeta[rec];
+            const int L2 = m.flags & 0xff;
+            st.finalize_likelihoods += placements(m, D, gb);
+            const double mp = c->h_finprob.p[rec];
+            if (-log(mp) <= c->cutoff) {                       // figbird.cpp:2293
+                const int pos = c->h_finpos.p[rec];
+                const uint8_t* cs = &c->h_bytes[(size_t)rec * FB_MAX_READ];
+                for (int j = 0; j < L2; j++) {
+                    int x = pos + j;
+                    if (x >= D && x < D + gb) cnt[(size_t)(x - D) * 5 + cs[j]] += 1;
+                }
+            } else {
+                disc++;
+            }
+        }
+        g.total_reads = g.nrec;
+        g.discarded = disc;
+        g.filled.assign((size_t)gb, 'N');
+        for (int i = 0; i < gb; i++) {                          // computeSequence(1), figbird.cpp:1989-2045
+            int mx = 0, idx = -1;
+            for (int k = 0; k < 5; k++)
+                if (cnt[(size_t)i * 5 + k] > mx) { mx = cnt[(size_t)i * 5 + k]; idx = k; }
+            g.filled[i] = idx < 0 ? 'N' : "ACGTN"[idx];
+        }
+        g.done = true;
+    }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    st.em_kernel_ms = ms;
+    st.finalize_kernel_ms = 0;
+    if (!gaplist.empty()) {
+        cudaEventElapsedTime(&ms, c->ev2, c->ev3);
+        st.finalize_kernel_ms = ms;
+    }
+    st.d2h_bytes = d2h;
+    c->ran = true;
+    return FB_OK;
+}
+
+int fb_run(fb_ctx* c) {
+    int rc = fb_upload(c);
+    if (rc != FB_OK) return rc;
+    return fb_run_device(c);
+}
+
+int fb_result(fb_ctx* c, int gap, fb_gap_result* out, char* filled, int cap) {
+    if (!c || gap < 0 || gap >= (int)c->gaps.size()) return FB_EINVAL;
+    const HostGap& g = c->gaps[gap];
+    if (!c->ran || !g.done) return c->fail(FB_ESTATE, "gap %d has no result in this context", gap);
+    if (out) {
+        out->gap_min = g.gmin;
+        out->gap_max = g.gmax;
+        out->best_estimate = g.best_est;
+        out->best_lik = g.best_lik;
+        out->total_reads = g.total_reads;
+        out->discarded = g.discarded;
+        out->filled_len = (int)g.filled.size();
+        out->likelihoods = g.likelihoods;
+    }
+    if (filled) {
+        if (cap < (int)g.filled.size() + 1) return c->fail(FB_EINVAL, "filled buffer too small");
+        memcpy(filled, g.filled.data(), g.filled.size());
+        filled[g.filled.size()] = 0;
+    }
+    return FB_OK;
+}
+
+int fb_estimate_liks(fb_ctx* c, int gap, double* liks, int cap) {
+    if (!c || gap < 0 || gap >= (int)c->gaps.size() || !liks) return FB_EINVAL;
+    const HostGap& g = c->gaps[gap];
+    if (!c->ran || !g.done) return c->fail(FB_ESTATE, "gap %d has no result in this context", gap);
+    if (cap < (int)g.liks.size()) return FB_EINVAL;
+    memcpy(liks, g.liks.data(), g.liks.size() * sizeof(double));
+    return (int)g.liks.size();
+}
+
+int fb_best_string(fb_ctx* c, int gap, char* buf, int cap) {
+    if (!c || gap < 0 || gap >= (int)c->gaps.size() || !buf) return FB_EINVAL;
+    const HostGap& g = c->gaps[gap];
+    if (!c->ran || !g.done) return c->fail(FB_ESTATE, "gap %d has no result in this context", gap);
+    if (cap < g.best_est + 1) return FB_EINVAL;
+    FB_CUDA(c, cudaSetDevice(c->device));
+    for (size_t ui = 0; ui < c->h_units.size(); ui++) {
+        const FbUnit& u = c->h_units[ui];
+        if (u.gap == gap && u.gp == g.best_est) {
+            FB_CUDA(c, cudaMemcpy(buf, c->d_cons.p + u.cons_off, (size_t)u.gp, cudaMemcpyDeviceToHost));
+            buf[u.gp] = 0;
+            return FB_OK;
+        }
+    }
+    return FB_ESTATE;
+}
+
+int fb_dump_profile(fb_ctx* c, int gap, int estimate, double* probs, double* counts) {
+    if (!c || gap < 0 || gap >= (int)c->gaps.size() || !probs || !counts) return FB_EINVAL;
+    if (!c->uploaded) return c->fail(FB_ESTATE, "fb_dump_profile before fb_upload");
+    FB_CUDA(c, cudaSetDevice(c->device));
+    for (size_t bi = 0; bi < c->bins.size(); bi++) {
+        const Bin& b = c->bins[bi];
+        for (int k = 0; k < b.n_units; k++) {
+            const FbUnit& u = c->h_units[b.first_unit + k];
+            if (u.gap != gap || u.gp != estimate) continue;
+            const size_t n = (size_t)(estimate + 2 * c->D) * 5;
+            FB_CUDA(c, c->d_dump.ensure(2 * n));
+            FbEmParams p;
+            fill_em_params(c, p);
+            p.units = c->d_units.p + b.first_unit + k;
+            p.n_units = 1;
+            p.work_counter = c->d_counters.p + c->bins.size();
+            p.nr_stride = b.nr_stride;
+            p.gp_stride = b.gp_stride;
+            p.p_stride = b.p_stride;
+            p.chunk = b.chunk;
+            p.gws_stride = (size_t)10 * b.nr_stride + 5 * (size_t)b.gp_stride + 16;
+            p.dump_probs = c->d_dump.p;
+            p.dump_counts = c->d_dump.p + n;
+            p.dump_unit = 0;
+            FB_CUDA(c, cudaMemsetAsync(p.work_counter, 0, sizeof(int), c->stream));
+            FB_CUDA(c, fb_launch_em(p, 1, b.global_tables, b.smem, c->stream));
+            FB_CUDA(c, cudaMemcpyAsync(probs, c->d_dump.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            FB_CUDA(c, cudaMemcpyAsync(counts, c->d_dump.p + n, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            FB_CUDA(c, cudaStreamSynchronize(c->stream));
+            return FB_OK;
+        }
+    }
+    return c->fail(FB_EINVAL, "estimate %d is not in the scan range of gap %d (or the gap is not owned)", estimate, gap);
+}
+
+int fb_get_stats(fb_ctx* c, fb_stats* out) {
+    if (!c || !out) return FB_EINVAL;
+    *out = c->stats;
+    return FB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,91 @@
+// fb_device.h — device-side data layout and launch interface of the figbird EM kernels (sm_100a).
+// Shared between fb_kernels.cu (device code) and fb_context.cpp (host orchestration).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define FB_MAX_READ 128          // longest mate the packed layout holds (2-bit codes in 2 x uint4)
+#define FB_THREADS 512           // CTA size of the EM kernel
+#define FB_FIN_THREADS 256       // CTA size of the finalize kernel
+
+// Per-record metadata, relative to the gap's profile window (row 0 = scaffold position gapStart - D).
+// u = row of the mate's first base for a placement.  Insert size of a placement:
+//   anchor left of the gap  (figbird.cpp:1824-1828): t = u + tb
+//   anchor right of the gap (figbird.cpp:1887-1891): t = tb - u
+// [a_lo, a_hi] is the u-range that passes the insert-window test, before clamping to the estimate.
+struct FbRecMeta {
+    int a_lo, a_hi;
+    int tb;
+    int flags;   // bits 0-7 mate length, bit 8 isReverse (anchor forward), bit 9 anchor left of gap
+};
+
+struct FbGapMeta {
+    int rec_off, nrec;
+    int orig;    // original N-run length
+    int lmax;    // longest mate of this gap
+};
+
+struct FbUnit {
+    int gap;         // index into gap meta
+    int gp;          // gap-length estimate
+    long long mp_off;    // offset of this unit's per-record maxima in unit_maxprob
+    long long cons_off;  // offset of this unit's consensus string in unit_cons
+};
+
+struct FbEmParams {
+    // model
+    const double2* eo;      // [max_read_len] {1 - e[k], e[k]}
+    const double* ild;      // insertLengthDistSmoothed[thr_min .. thr_max]
+    double T[25];           // errorTypeProbs
+    int thr_min, thr_max, D, num_iter, max_read_len;
+    // gaps / records (struct of arrays in HBM)
+    const FbGapMeta* gaps;
+    const uint8_t* flank;   // [n_gaps][2*D] base codes: D left of the gap, D right of it
+    const uint4* codes;     // [n_records][2]  2-bit bases, 16 per 32-bit word, already in scoring orientation
+    const uint4* nmask;     // [n_records]     bit j set: base j is not ACGT
+    const FbRecMeta* rmeta; // [n_records]
+    // work list
+    const FbUnit* units;
+    int n_units;
+    int* work_counter;
+    // outputs
+    double* unit_maxprob;   // per (unit, record) max placement score of the last iteration
+    char* unit_cons;        // per unit consensus string (computeSequence(0))
+    double* dump_probs;     // optional: full profile of unit dump_unit, [(gp + 2D) * 5]
+    double* dump_counts;
+    int dump_unit;
+    // shared-memory geometry of this launch
+    int nr_stride;          // rows of the P/Q table
+    int gp_stride;          // rows of the counts table
+    int p_stride;           // placements per record slot in the score buffer
+    int chunk;              // records per E/M round
+    // global-memory tables for gaps too long for shared memory (one slice per CTA)
+    double* gws;
+    size_t gws_stride;      // doubles per CTA
+};
+
+struct FbFinParams {
+    const double* ild;
+    const double* epos;     // e[k]
+    const double* match;    // 1 - e[k] - in[k] - del[k]
+    double T[25];
+    int thr_min, thr_max, D;
+    const FbGapMeta* gaps;
+    const uint8_t* flank;
+    const uint4* codes;
+    const uint4* nmask;
+    const FbRecMeta* rmeta;
+    const int* gap_list;    // gaps to finalize in this launch
+    const int* best_gp;     // [n_gaps] winning estimate
+    const long long* best_cons_off;  // [n_gaps] offset of the winning consensus in unit_cons
+    const char* unit_cons;
+    double* fin_maxprob;    // [n_records]
+    int* fin_maxpos;        // [n_records]
+    int gmax_stride;        // smem rows for the gap string
+};
+
+size_t fb_em_smem_bytes(int nr_stride, int gp_stride, int p_stride, int chunk, int pwin, bool global_tables);
+cudaError_t fb_launch_em(const FbEmParams& p, int grid, bool global_tables, size_t smem, cudaStream_t s);
+cudaError_t fb_launch_finalize(const FbFinParams& p, int n, size_t smem, cudaStream_t s);
+cudaError_t fb_kernels_init(int* max_smem_optin, int* sm_count);

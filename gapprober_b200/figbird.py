@@ -1,0 +1,377 @@
+"""Host-side mirror of the reference's figbird interface over the C ABI (include/figbird_cuda.h).
+
+The reference exposes `class GapFiller` (figbird.cpp:1517-2532) driven by main()'s gap loop
+(figbird.cpp:2819-2855) and talks to the rest of GapProber through files in the working directory.
+This module keeps those names and meanings:
+
+    model = FigbirdModel.load("fb_model.bin")            # what the preamble leaves in globals
+    with FigbirdContext(model) as fb:
+        gf = fb.GapFiller()                               # allocate + initGapFiller
+        gf.initGapFiller(contigNo, gapStart, originalGap, "Gaps/gaps_0.sam", contig)
+        fb.fillGaps()                                     # fillGap() of every registered gap, on the GPU
+        n, s = gf.getConcensus()                          # figbird.cpp:2050-2063
+
+Everything numeric happens in libfigbird_cuda.so (hand-written sm_100a kernels).  There is no CPU
+fallback: importing works anywhere (so the ABI can be inspected), creating a context needs a GPU.
+"""
+import ctypes as C
+import os
+import struct
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfigbird_cuda.so")
+
+FB_OK = 0
+
+
+class FigbirdError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"figbird_cuda status {status}: {msg}")
+        self.status = status
+
+
+class _FbModel(C.Structure):
+    _fields_ = [
+        ("max_read_len", C.c_int),
+        ("error_pos", C.POINTER(C.c_double)),
+        ("in_pos", C.POINTER(C.c_double)),
+        ("del_pos", C.POINTER(C.c_double)),
+        ("error_type", (C.c_double * 5) * 5),
+        ("ild", C.POINTER(C.c_double)),
+        ("ild_len", C.c_int),
+        ("thr_min", C.c_int),
+        ("thr_max", C.c_int),
+        ("gap_prob_cutoff", C.c_int),
+        ("max_distance", C.c_int),
+        ("num_iter", C.c_int),
+        ("f_mode", C.c_int),
+    ]
+
+
+class _FbRecord(C.Structure):
+    _fields_ = [("pos1", C.c_int), ("len1", C.c_int), ("strand1", C.c_int), ("seq2", C.c_char_p), ("len2", C.c_int)]
+
+
+class _FbGapResult(C.Structure):
+    _fields_ = [
+        ("gap_min", C.c_int), ("gap_max", C.c_int), ("best_estimate", C.c_int), ("best_lik", C.c_double),
+        ("total_reads", C.c_int), ("discarded", C.c_int), ("filled_len", C.c_int), ("likelihoods", C.c_long),
+    ]
+
+
+class FbStats(C.Structure):
+    _fields_ = [
+        ("n_gaps", C.c_long), ("n_units", C.c_long), ("n_records", C.c_long),
+        ("likelihoods", C.c_long), ("finalize_likelihoods", C.c_long), ("base_terms", C.c_long),
+        ("em_kernel_ms", C.c_double), ("finalize_kernel_ms", C.c_double),
+        ("em_launches", C.c_int), ("finalize_launches", C.c_int),
+        ("h2d_bytes", C.c_long), ("d2h_bytes", C.c_long), ("algorithmic_bytes", C.c_long),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# Every symbol include/figbird_cuda.h declares; tests check the library exports all of them.
+ABI_SYMBOLS = [
+    "fb_create", "fb_destroy", "fb_add_gap", "fb_set_partition", "fb_owns_gap", "fb_run", "fb_upload",
+    "fb_run_device", "fb_result", "fb_estimate_liks", "fb_best_string", "fb_dump_profile", "fb_get_stats",
+    "fb_clear_gaps", "fb_gap_range", "fb_last_error", "fb_status_str", "fb_abi_version",
+]
+
+_lib = None
+
+
+def load_library():
+    """dlopen libfigbird_cuda.so and declare the prototypes.  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FigbirdError(-3, f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.fb_create.argtypes = [C.POINTER(_FbModel), C.c_int, C.POINTER(vp)]
+    L.fb_destroy.argtypes = [vp]
+    L.fb_destroy.restype = None
+    L.fb_add_gap.argtypes = [vp, C.c_int, C.c_long, C.c_int, C.c_char_p, C.c_long, C.POINTER(_FbRecord), C.c_int]
+    L.fb_set_partition.argtypes = [vp, C.c_int, C.c_int]
+    L.fb_owns_gap.argtypes = [vp, C.c_int]
+    L.fb_run.argtypes = [vp]
+    L.fb_upload.argtypes = [vp]
+    L.fb_run_device.argtypes = [vp]
+    L.fb_result.argtypes = [vp, C.c_int, C.POINTER(_FbGapResult), C.c_char_p, C.c_int]
+    L.fb_estimate_liks.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.c_int]
+    L.fb_best_string.argtypes = [vp, C.c_int, C.c_char_p, C.c_int]
+    L.fb_dump_profile.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.fb_get_stats.argtypes = [vp, C.POINTER(FbStats)]
+    L.fb_clear_gaps.argtypes = [vp]
+    L.fb_gap_range.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.fb_gap_range.restype = None
+    L.fb_last_error.argtypes = [vp]
+    L.fb_last_error.restype = C.c_char_p
+    L.fb_status_str.argtypes = [C.c_int]
+    L.fb_status_str.restype = C.c_char_p
+    L.fb_abi_version.restype = C.c_int
+    _lib = L
+    return L
+
+
+def gap_range(original_gap):
+    """Estimate range scanned by fillGap (figbird.cpp:2438-2453)."""
+    a, b = C.c_int(), C.c_int()
+    load_library().fb_gap_range(int(original_gap), C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+class FigbirdModel:
+    """Constant inputs of the hot path: the globals the reference's preamble fills (figbird.cpp:475-823, 2778-2794)."""
+
+    def __init__(self, max_read_len, ild, thr_min, thr_max, cutoff, error_type, error_pos, in_pos, del_pos,
+                 max_distance=200, num_iter=5, f_mode=0):
+        self.max_read_len = int(max_read_len)
+        self.ild = np.ascontiguousarray(ild, dtype=np.float64)
+        self.thr_min, self.thr_max, self.cutoff = int(thr_min), int(thr_max), int(cutoff)
+        self.error_type = np.ascontiguousarray(error_type, dtype=np.float64).reshape(5, 5)
+        self.error_pos = np.ascontiguousarray(error_pos, dtype=np.float64)
+        self.in_pos = np.ascontiguousarray(in_pos, dtype=np.float64)
+        self.del_pos = np.ascontiguousarray(del_pos, dtype=np.float64)
+        self.max_distance, self.num_iter, self.f_mode = int(max_distance), int(num_iter), int(f_mode)
+
+    @staticmethod
+    def load(path):
+        """Read a model file ("FBM1": 6 int32 + doubles; written by the host preamble or by the instrumented reference)."""
+        raw = open(path, "rb").read()
+        if raw[:4] != b"FBM1":
+            raise ValueError("not a figbird model file")
+        mrl, mis, tmin, tmax, cut, D = struct.unpack_from("<6i", raw, 4)
+        d = np.frombuffer(raw, dtype="<f8", offset=28)
+        et = d[:25].reshape(5, 5)
+        ep, ip, dp = d[25:25 + mrl], d[25 + mrl:25 + 2 * mrl], d[25 + 2 * mrl:25 + 3 * mrl]
+        ild = d[25 + 3 * mrl:25 + 3 * mrl + mis]
+        return FigbirdModel(mrl, ild, tmin, tmax, cut, et, ep, ip, dp, max_distance=D)
+
+    def save(self, path):
+        with open(path, "wb") as f:
+            f.write(b"FBM1")
+            f.write(struct.pack("<6i", self.max_read_len, self.ild.size, self.thr_min, self.thr_max, self.cutoff, self.max_distance))
+            for a in (self.error_type, self.error_pos, self.in_pos, self.del_pos, self.ild):
+                f.write(np.ascontiguousarray(a, dtype="<f8").tobytes())
+
+    def _as_c(self):
+        m = _FbModel()
+        dp = C.POINTER(C.c_double)
+        m.max_read_len = self.max_read_len
+        m.error_pos = self.error_pos.ctypes.data_as(dp)
+        m.in_pos = self.in_pos.ctypes.data_as(dp)
+        m.del_pos = self.del_pos.ctypes.data_as(dp)
+        for i in range(5):
+            for j in range(5):
+                m.error_type[i][j] = self.error_type[i, j]
+        m.ild = self.ild.ctypes.data_as(dp)
+        m.ild_len = self.ild.size
+        m.thr_min, m.thr_max, m.gap_prob_cutoff = self.thr_min, self.thr_max, self.cutoff
+        m.max_distance, m.num_iter, m.f_mode = self.max_distance, self.num_iter, self.f_mode
+        return m
+
+
+def read_gap_file(path):
+    """Line pairs of Gaps/gaps_<n>.sam as placeReads parses them (figbird.cpp:1718-1801):
+    (pos1, len1, strand1, seq2) per pair; '@' lines skipped, a trailing unpaired line dropped."""
+    recs = []
+    with open(path, "rb") as f:
+        lines = [ln for ln in f.read().split(b"\n") if ln and not ln.startswith(b"@")]
+    for a, b in zip(lines[0::2], lines[1::2]):
+        fa, fb = a.split(b"\t"), b.split(b"\t")
+        recs.append((int(fa[3]), len(fa[6]), (int(fa[1]) & 16) >> 4, fb[6]))
+    return recs
+
+
+def read_scaffolds(path):
+    """Scaffold FASTA as figbird's main() loads it (figbird.cpp:2586-2658): names up to the first blank, upper-cased bases."""
+    names, seqs, cur = [], [], []
+    with open(path, "rb") as f:
+        for ln in f:
+            if ln.startswith(b";"):
+                continue
+            if ln.startswith(b">"):
+                if cur:
+                    seqs.append(b"".join(cur).upper())
+                    cur = []
+                names.append(ln[1:].split()[0])
+            else:
+                cur.append(ln.rstrip(b"\n"))
+    seqs.append(b"".join(cur).upper())
+    return names, seqs
+
+
+def read_gap_info(path):
+    """gapInfo.txt rows (contigNo, gapStart, gapLength), main.cpp:965."""
+    out = []
+    with open(path) as f:
+        for ln in f:
+            if ln.strip():
+                c, s, l = ln.split()[:3]
+                out.append((int(c), int(s), int(l)))
+    return out
+
+
+class GapFiller:
+    """One gap.  Method names follow the reference class (figbird.cpp:1517-2532)."""
+
+    def __init__(self, ctx):
+        self._ctx = ctx
+        self.index = None
+        self.originalGap = None
+        self.gapStart = None
+        self.contigNo = None
+
+    def initGapFiller(self, contigNo, gapStart, originalGap, gapFile, contig):
+        """figbird.cpp:1610-1618 + the gap-file parse.  gapFile: path, or a list of (pos1, len1, strand1, seq2)."""
+        recs = read_gap_file(gapFile) if isinstance(gapFile, (str, bytes, os.PathLike)) else list(gapFile)
+        self.contigNo, self.gapStart, self.originalGap = int(contigNo), int(gapStart), int(originalGap)
+        self.index = self._ctx._add_gap(self.contigNo, self.gapStart, self.originalGap, contig, recs)
+        self.n_records = len(recs)
+        return self
+
+    def _result(self):
+        return self._ctx._result(self.index)
+
+    def getConcensus(self):
+        """(length, string) — figbird.cpp:2050-2063."""
+        r = self._result()
+        return r["filled_len"], r["filled"]
+
+    @property
+    def maxGapEstimate(self):
+        return self._result()["best_estimate"]
+
+    @property
+    def maxLikelihood(self):
+        return self._result()["best_lik"]
+
+    def result(self):
+        return self._result()
+
+    def estimateLikelihoods(self):
+        return self._ctx._liks(self.index)
+
+    def bestString(self):
+        return self._ctx._best_string(self.index)
+
+    def dumpProfile(self, estimate):
+        """(probsGap, countsGap) after the last EM iteration of one estimate, [(estimate+2D), 5] each."""
+        return self._ctx._dump(self.index, estimate)
+
+
+class FigbirdContext:
+    """A model bound to one GPU; owns the registered gaps.  fillGaps() = GapFiller::fillGap for all of them."""
+
+    def __init__(self, model, device=0):
+        self._L = load_library()
+        self.model = model
+        self._h = C.c_void_p()
+        self._cm = model._as_c()
+        rc = self._L.fb_create(C.byref(self._cm), int(device), C.byref(self._h))
+        if rc != FB_OK:
+            raise FigbirdError(rc, self._L.fb_status_str(rc).decode() + " (fb_create; is a CUDA device visible?)")
+        self._gaps = []
+
+    def close(self):
+        if self._h:
+            self._L.fb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc < 0:
+            raise FigbirdError(rc, self._L.fb_last_error(self._h).decode() or self._L.fb_status_str(rc).decode())
+        return rc
+
+    def GapFiller(self):
+        g = GapFiller(self)
+        self._gaps.append(g)
+        return g
+
+    def _add_gap(self, contig_no, gap_start, orig, contig, recs):
+        arr = (_FbRecord * max(1, len(recs)))()
+        for i, (p, l1, s1, seq) in enumerate(recs):
+            arr[i].pos1, arr[i].len1, arr[i].strand1 = int(p), int(l1), int(s1)
+            arr[i].seq2 = seq
+            arr[i].len2 = len(seq)
+        return self._check(self._L.fb_add_gap(self._h, contig_no, gap_start, orig, contig, len(contig), arr, len(recs)))
+
+    def add_workdir(self, wd, scaffolds="scaffolds.fa"):
+        """Register every gap of a GapProber working directory (gapInfo.txt + Gaps/), like figbird.cpp:2819-2842."""
+        _, seqs = read_scaffolds(os.path.join(wd, scaffolds))
+        out = []
+        for gi, (c, s, l) in enumerate(read_gap_info(os.path.join(wd, "gapInfo.txt"))):
+            out.append(self.GapFiller().initGapFiller(c, s, l, os.path.join(wd, "Gaps", f"gaps_{gi}.sam"), seqs[c]))
+        return out
+
+    def setPartition(self, rank, world):
+        self._check(self._L.fb_set_partition(self._h, rank, world))
+
+    def ownsGap(self, index):
+        return bool(self._L.fb_owns_gap(self._h, index))
+
+    def fillGaps(self):
+        """Upload + run: host buffers in, filled sequences out (the end-to-end call)."""
+        self._check(self._L.fb_run(self._h))
+
+    def upload(self):
+        self._check(self._L.fb_upload(self._h))
+
+    def runDevice(self):
+        """Everything after the upload (inputs resident in HBM)."""
+        self._check(self._L.fb_run_device(self._h))
+
+    def clearGaps(self):
+        self._check(self._L.fb_clear_gaps(self._h))
+        self._gaps = []
+
+    def stats(self):
+        s = FbStats()
+        self._check(self._L.fb_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def _result(self, idx):
+        r = _FbGapResult()
+        cap = 2 * self._gaps[idx].originalGap + 16
+        buf = C.create_string_buffer(cap)
+        self._check(self._L.fb_result(self._h, idx, C.byref(r), buf, cap))
+        return dict(gap_min=r.gap_min, gap_max=r.gap_max, best_estimate=r.best_estimate, best_lik=r.best_lik,
+                    total_reads=r.total_reads, discarded=r.discarded, filled_len=r.filled_len,
+                    filled=buf.value[:r.filled_len], likelihoods=r.likelihoods)
+
+    def _liks(self, idx):
+        a, b = gap_range(self._gaps[idx].originalGap)
+        out = np.zeros(b - a + 1)
+        n = self._check(self._L.fb_estimate_liks(self._h, idx, out.ctypes.data_as(C.POINTER(C.c_double)), out.size))
+        return out[:n]
+
+    def _best_string(self, idx):
+        cap = 2 * self._gaps[idx].originalGap + 16
+        buf = C.create_string_buffer(cap)
+        self._check(self._L.fb_best_string(self._h, idx, buf, cap))
+        return buf.value
+
+    def _dump(self, idx, estimate):
+        n = (estimate + 2 * self.model.max_distance) * 5
+        p, c = np.zeros(n), np.zeros(n)
+        dp = C.POINTER(C.c_double)
+        self._check(self._L.fb_dump_profile(self._h, idx, int(estimate), p.ctypes.data_as(dp), c.ctypes.data_as(dp)))
+        return p.reshape(-1, 5), c.reshape(-1, 5)

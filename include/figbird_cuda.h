@@ -1,0 +1,131 @@
+/* figbird_cuda.h — C ABI of libfigbird_cuda.so: the figbird EM hot path of GapProber on B200 (sm_100a).
+ *
+ * The reference has no library/FFI boundary: figbird.cpp is one translation unit whose main() drives
+ * `class GapFiller` (figbird.cpp:1517-2532) gap by gap (figbird.cpp:2819-2855).  This header is the
+ * boundary a maintainer would bind instead: each entry point replaces the GapFiller method(s) cited
+ * next to it.  Plain C types only; the caller owns every buffer it passes (inputs are copied before
+ * the call returns) and every buffer it receives results in.  No exceptions and no exit() cross the
+ * ABI: every function returns FB_OK (0) or a negative fb_status.  One host thread drives a context;
+ * a context owns one CUDA device, one stream and its device memory.  There is NO CPU fallback: with
+ * no usable CUDA device fb_create fails with FB_ECUDA.
+ */
+#ifndef FIGBIRD_CUDA_H
+#define FIGBIRD_CUDA_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB_ABI_VERSION 1
+
+typedef enum fb_status {
+    FB_OK = 0,
+    FB_EINVAL = -1,   /* bad argument / model outside supported bounds                               */
+    FB_EDOMAIN = -2,  /* gap or record outside the territory where the reference is defined: */
+                      /* gap closer than max_distance to a scaffold end, read longer than max_distance.  */
+    FB_ECUDA = -3,    /* CUDA runtime error or no device; fb_last_error() has the text                 */
+    FB_ENOMEM = -4,
+    FB_ESTATE = -5,   /* call out of order (e.g. fb_result before fb_run)                              */
+    FB_EUNSUPPORTED = -6 /* f_mode != 0: the log-domain variant (figbird.cpp:1814-1815) is not on the GPU yet */
+} fb_status;
+
+/* Constant inputs of the hot path = outputs of the reference's preamble (figbird.cpp:475-823,
+ * 2753-2794).  Defaults of the compile-time constants: max_distance 200 (figbird.cpp:103),
+ * num_iter 5 (figbird.cpp:2466), f_mode 0 (what GapProber.py:44 passes). */
+typedef struct fb_model {
+    int max_read_len;          /* maxReadLength                                   */
+    const double* error_pos;   /* errorPosDist[max_read_len]     figbird.cpp:511  */
+    const double* in_pos;      /* inPosDist[max_read_len]        figbird.cpp:518  */
+    const double* del_pos;     /* delPosDist[max_read_len]       figbird.cpp:539  */
+    double error_type[5][5];   /* errorTypeProbs                 figbird.cpp:480  */
+    const double* ild;         /* insertLengthDistSmoothed[ild_len]  figbird.cpp:624 */
+    int ild_len;               /* maxInsertSize                                   */
+    int thr_min, thr_max;      /* insertThresholdMin/Max         figbird.cpp:788  */
+    int gap_prob_cutoff;       /* gapProbCutOff                  figbird.cpp:2778 */
+    int max_distance;
+    int num_iter;
+    int f_mode;
+} fb_model;
+
+/* One (anchor, unmapped mate) line pair of Gaps/gaps_<n>.sam, as placeReads parses it
+ * (figbird.cpp:1726-1801). */
+typedef struct fb_record {
+    int pos1;          /* anchor POS column, unadjusted                         */
+    int len1;          /* strlen(anchor SEQ)                                    */
+    int strand1;       /* (anchor FLAG & 16) >> 4                               */
+    const char* seq2;  /* mate SEQ as stored in the file (not NUL-terminated ok) */
+    int len2;          /* strlen(mate SEQ)                                      */
+} fb_record;
+
+typedef struct fb_gap_result {
+    int gap_min, gap_max;     /* scanned estimate range           figbird.cpp:2452-2453 */
+    int best_estimate;        /* maxGapEstimate                   figbird.cpp:2485      */
+    double best_lik;          /* maxLikelihood                    figbird.cpp:2484      */
+    int total_reads;          /* finalize's Total_Reads           figbird.cpp:2382      */
+    int discarded;            /* finalize's Discard                                     */
+    int filled_len;           /* getConcensus() length            figbird.cpp:2050      */
+    long likelihoods;         /* (record, placement) scores evaluated by the EM scan of this gap */
+} fb_gap_result;
+
+typedef struct fb_stats {
+    long n_gaps, n_units, n_records;
+    long likelihoods;           /* EM scan: sum over units, iterations, records of in-window placements */
+    long finalize_likelihoods;  /* hard-assignment pass                                               */
+    long base_terms;            /* likelihoods x mate length                                          */
+    double em_kernel_ms;        /* CUDA-event time of the EM kernel launches of the last fb_run_device */
+    double finalize_kernel_ms;
+    int em_launches, finalize_launches;
+    long h2d_bytes, d2h_bytes;  /* of the last fb_upload + fb_run_device                               */
+    long algorithmic_bytes;     /* SURVEY §8(d) HBM byte model summed over (unit, iteration)            */
+} fb_stats;
+
+typedef struct fb_ctx fb_ctx;
+
+/* Create a context on CUDA device `device` and copy the model.  Replaces the globals the reference's
+ * main() leaves behind for GapFiller (figbird.cpp:2718-2794). */
+int fb_create(const fb_model* model, int device, fb_ctx** out);
+void fb_destroy(fb_ctx* ctx);
+
+/* Register one gap = GapFiller::allocate + initGapFiller (figbird.cpp:1543-1566, 1610-1618) plus the
+ * parse of its gap file (figbird.cpp:1718-1812, done by the caller).  `contig` is the upper-cased
+ * scaffold (figbird.cpp:2652-2658); only the max_distance bases either side of the gap are read.
+ * Returns the gap index (>= 0) or a negative fb_status. */
+int fb_add_gap(fb_ctx* ctx, int contig_no, long gap_start, int orig_gap, const char* contig, long contig_len,
+               const fb_record* recs, int nrec);
+
+/* Restrict this context to its share of the work when several processes (one per GPU) split one gap
+ * set: gaps are dealt to `world` ranks by descending cost (longest-processing-time first); this
+ * context runs those of `rank`.  Results of other ranks' gaps are absent (fb_result -> FB_ESTATE).
+ * Call after the last fb_add_gap and before fb_upload/fb_run.  No data-path collective is involved. */
+int fb_set_partition(fb_ctx* ctx, int rank, int world);
+/* 1 if gap `gap` is run by this context under the current partition. */
+int fb_owns_gap(fb_ctx* ctx, int gap);
+
+/* GapFiller::fillGap for every registered gap (figbird.cpp:2436-2510): estimate scan, num_iter EM
+ * iterations per estimate, best-estimate selection, finalize.  fb_run = fb_upload + fb_run_device. */
+int fb_run(fb_ctx* ctx);
+int fb_upload(fb_ctx* ctx);      /* pack + host->device copy of every registered gap */
+int fb_run_device(fb_ctx* ctx);  /* everything after the upload; may be called repeatedly (benchmark steps) */
+
+/* GapFiller::getConcensus (figbird.cpp:2050-2063) + the numbers fillGap/finalize print. */
+int fb_result(fb_ctx* ctx, int gap, fb_gap_result* out, char* filled, int filled_cap);
+
+/* Parity taps (the reference prints none of this; tests compare with oracle/ dumps). */
+int fb_estimate_liks(fb_ctx* ctx, int gap, double* liks, int cap);   /* final-iteration likelihood per estimate */
+int fb_best_string(fb_ctx* ctx, int gap, char* buf, int cap);         /* bestString handed to finalize        */
+/* Re-runs estimate `estimate` of gap `gap` alone and copies its final profile:
+ * probs/counts are [(estimate + 2*max_distance) * 5] doubles, row-major like probsGap/countsGap. */
+int fb_dump_profile(fb_ctx* ctx, int gap, int estimate, double* probs, double* counts);
+
+int fb_get_stats(fb_ctx* ctx, fb_stats* out);
+int fb_clear_gaps(fb_ctx* ctx);                 /* drop all gaps, keep the model */
+/* Estimate range of fillGap (figbird.cpp:2438-2453), float arithmetic included. */
+void fb_gap_range(int orig_gap, int* gap_min, int* gap_max);
+const char* fb_last_error(fb_ctx* ctx);
+const char* fb_status_str(int status);
+int fb_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
