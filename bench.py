@@ -1,0 +1,396 @@
+#!/usr/bin/env python3
+"""Benchmark of the figbird EM hot path (GapFiller::fillGap, figbird.cpp:2436-2510) on B200.
+
+Metric (BASELINE.json): read-placement likelihoods per second — one likelihood = one (record, placement) score
+that passes the insert-window test in one placeReads call; counted analytically, the same counter for
+the GPU and the CPU arm.  A "step" = fillGap for every gap of the workload (estimate scan x 5 EM iterations +
+finalize).  Workload at N=1: BASELINE.json configs[1] (R. sphaeroides scale, ~200 gaps, 1 % errors, 50x).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (one process per GPU under torchrun)
+  python bench.py --impl reference [--gpus N] [--steps K] ...    the unmodified reference (oracle/_ref/figbird.out)
+                                                                on the host cores, bounded sample per step
+
+`value`  : inputs resident in HBM (fb_run_device), whole job, max over ranks.
+`e2e`    : the same work through the public entry point from HOST data: gap files parsed and packed by the
+           library, pinned host->device copies, kernels, device->host copies (fb_add_gap_file + fb_run).
+`roofline`: the EM kernel against the measured HBM peak with SURVEY §8(d)'s algorithmic bytes — reported as asked,
+           but shared-memory bandwidth is the binding roof of this path (see `smem` and DESIGN.md).
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "read-placement likelihoods/sec"
+UNIT = "likelihoods/s"
+
+
+def workload_dir(cfg, seed):
+    return os.path.join(os.environ.get("FB_BENCH_CACHE", "/tmp"), f"fb_bench_{cfg}_s{seed}")
+
+
+def prepare_workload(cfg, seed):
+    """Generate (once) the synthetic working directory and learn its model with the host preamble."""
+    from gapprober_b200 import build, synth
+    wd = workload_dir(cfg, seed)
+    done = os.path.join(wd, ".ready")
+    if not os.path.exists(done):
+        if os.path.isdir(wd):
+            shutil.rmtree(wd)
+        args = list(synth.CONFIGS[cfg])
+        if "--model-pairs" not in args:
+            args += ["--model-pairs", "200000"]   # the model is learned from a 200k-pair sample of the proper pairs
+        synth.generate(wd, args, seed=seed)
+        build.learn_model(wd)
+        open(done, "w").write("ok")
+    return wd
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index, self.proc, self.rows = index, None, []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.rows.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def sample_gaps(wd, model, target_liks):
+    """Pick gaps (in file order) until the analytic likelihood count reaches target_liks."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    gaps = O.read_gap_info(os.path.join(wd, "gapInfo.txt"))
+    picked, total = [], 0
+    for gi, (c, s, l) in enumerate(gaps):
+        recs = O.read_gap_file(os.path.join(wd, "Gaps", f"gaps_{gi}.sam"))
+        a, b = O.gap_range(l)
+        n = sum(O.count_likelihoods(model, s, gp, recs) for gp in range(a, b + 1)) * model.num_iter
+        picked.append((gi, n))
+        total += n
+        if total >= target_liks:
+            break
+    return picked, total
+
+
+def make_sample_dir(wd, dst, gap_ids, empty=False):
+    """A working directory holding only the chosen gaps (renumbered), sharing the big inputs by symlink.
+    empty=True keeps the gaps but gives them no records: the run then costs the preamble only."""
+    if os.path.isdir(dst):
+        shutil.rmtree(dst)
+    os.makedirs(os.path.join(dst, "Gaps"))
+    for f in ("scaffolds.fa", "myout.sam", "stat.txt"):
+        os.symlink(os.path.join(wd, f), os.path.join(dst, f))
+    lines = open(os.path.join(wd, "gapInfo.txt")).read().splitlines()
+    with open(os.path.join(dst, "gapInfo.txt"), "w") as f:
+        for k, gi in enumerate(gap_ids):
+            f.write(lines[gi] + "\n")
+            if empty:
+                open(os.path.join(dst, "Gaps", f"gaps_{k}.sam"), "w").close()
+            else:
+                shutil.copy(os.path.join(wd, "Gaps", f"gaps_{gi}.sam"), os.path.join(dst, "Gaps", f"gaps_{k}.sam"))
+    return dst
+
+
+def time_reference(dirs):
+    """Run the unmodified reference figbird.out concurrently in every directory; wall seconds of the slowest."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "figbird.out")
+    t0 = time.perf_counter()
+    procs = [subprocess.Popen([exe, "scaffolds.fa", " 0", "250"], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for d in dirs]
+    for p in procs:
+        if p.wait() != 0:
+            raise RuntimeError("reference figbird.out failed")
+    return time.perf_counter() - t0
+
+
+def cpu_reference_rate(wd, target_liks, procs, tag, t_pre=None):
+    """likelihoods/s of the reference's own CPU EM on `procs` host cores over a bounded sample.
+    The reference's wall time includes its preamble (myout.sam scan); that part is measured with an empty
+    gapInfo.txt on the same number of concurrent processes and subtracted."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    model = O.Model.load(os.path.join(wd, "fb_model.bin"))
+    picked, _ = sample_gaps(wd, model, target_liks * procs)
+    # deal gaps to processes, heaviest first
+    loads = [[0, []] for _ in range(procs)]
+    for gi, n in sorted(picked, key=lambda x: -x[1]):
+        tgt = min(loads, key=lambda x: x[0])
+        tgt[0] += n
+        tgt[1].append(gi)
+    loads = [l for l in loads if l[1]]
+    base = os.path.join(os.environ.get("FB_BENCH_CACHE", "/tmp"), f"fb_cpu_{tag}_{os.getpid()}")
+    dirs = [make_sample_dir(wd, f"{base}_{k}", l[1]) for k, l in enumerate(loads)]
+    if t_pre is None:
+        empties = [make_sample_dir(wd, f"{base}_e{k}", l[1][:1], empty=True) for k, l in enumerate(loads)]
+        t_pre = time_reference(empties)
+        for d in empties:
+            shutil.rmtree(d, ignore_errors=True)
+    t_all = time_reference(dirs)
+    for d in dirs:
+        shutil.rmtree(d, ignore_errors=True)
+    liks = sum(l[0] for l in loads)
+    em_s = max(t_all - t_pre, 1e-6)
+    return liks / em_s, dict(liks=liks, gaps=sum(len(l[1]) for l in loads), procs=len(loads), em_s=em_s, preamble_s=t_pre)
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    exe = os.path.join(ROOT, "oracle", "_ref", "figbird.out")
+    if not os.path.exists(exe):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/figbird.out has not been built (needs /root/reference at build time)"}))
+        return
+    wd = prepare_workload(a.config, a.seed)
+    cores = os.cpu_count() or 1
+    # bounded sample per step: ~4 s of single-core EM per process
+    per_proc = int(a.ref_liks)
+    rates, info, t_pre = [], None, None
+    for step in range(a.warmup + a.steps):
+        r, info = cpu_reference_rate(wd, per_proc, cores, "ref", t_pre)
+        t_pre = info["preamble_s"]
+        if step >= a.warmup:
+            rates.append((r, info))
+    liks = sum(i["liks"] for _, i in rates)
+    secs = sum(i["em_s"] for _, i in rates)
+    value = liks / secs
+    sample = (f"{info['gaps']} gaps / {info['liks']} likelihoods per step on {info['procs']} processes; "
+              f"EM seconds = wall - preamble wall ({info['preamble_s']:.2f} s)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1e3 * secs / max(1, a.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": a.config, "seed": a.seed, "note": "unmodified reference figbird.out, host CPU only"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["procs"], "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the figbird hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from gapprober_b200 import FigbirdContext, FigbirdModel, read_gap_info, read_scaffolds
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    weak = a.scaling == "weak"
+    # weak: the gap set grows with N — rank r fills the gaps of its own copy of the workload (seed + r);
+    # strong: one gap set, dealt to the ranks by descending cost (fb_set_partition).  No data-path collective either way.
+    my_seed = a.seed + (rank if weak else 0)
+    if weak or rank == 0:
+        prepare_workload(a.config, my_seed)
+    barrier()
+    wd = prepare_workload(a.config, my_seed)
+    model = FigbirdModel.load(os.path.join(wd, "fb_model.bin"))
+    _, seqs = read_scaffolds(os.path.join(wd, "scaffolds.fa"))
+    gaps = read_gap_info(os.path.join(wd, "gapInfo.txt"))
+    gap_files = [os.path.join(wd, "Gaps", f"gaps_{gi}.sam") for gi in range(len(gaps))]
+
+    fb = FigbirdContext(model, device=local)
+
+    def register():
+        fb.clearGaps()
+        for (c, s, l), path in zip(gaps, gap_files):
+            fb.GapFiller().initGapFiller(c, s, l, path, seqs[c])
+        if world > 1 and not weak:
+            fb.setPartition(rank, world)
+
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    # ---- device-resident arm -------------------------------------------------------------------------
+    register()
+    fb.upload()
+    for _ in range(a.warmup):
+        fb.runDevice()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    em_ms, step_ms = 0.0, 0.0
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        flush.fill_(1)                      # evict L2 between steps
+        torch.cuda.synchronize()
+        fb.runDevice()                      # synchronous: returns after the last device->host copy
+        st = fb.stats()
+        em_ms += st["em_kernel_ms"]
+        step_ms += st["step_ms"]
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    st = fb.stats()
+    dev_seconds = allmax(step_ms / 1e3)     # CUDA-event time of the steps, max over ranks
+    liks_all = allsum(float(st["likelihoods"]))
+    value = liks_all * a.steps / dev_seconds
+    launches = (st["em_launches"] + st["finalize_launches"]) * a.steps
+
+    # ---- end-to-end arm: host gap files -> library parse/pack -> H2D -> kernels -> D2H ------------------
+    for _ in range(min(a.warmup, 2)):
+        register()
+        fb.fillGaps()
+    barrier()
+    t0 = time.perf_counter()
+    h2d = d2h = 0
+    for _ in range(a.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        register()
+        fb.fillGaps()
+        s2 = fb.stats()
+        h2d, d2h = s2["h2d_bytes"], s2["d2h_bytes"]
+    barrier()
+    e2e_seconds = allmax(time.perf_counter() - t0)
+    e2e_value = liks_all * a.steps / e2e_seconds
+
+    # a result checksum so the step cannot be optimised away: total filled length over owned gaps
+    filled_total = 0
+    for gi, gf in enumerate(fb._gaps):
+        if world == 1 or weak or fb.ownsGap(gi):
+            filled_total += gf.result()["filled_len"]
+    filled_total = int(allsum(float(filled_total)))
+
+    if rank == 0:
+        peaks, peak_kind = load_peaks()
+        em_s = em_ms / 1e3 / a.steps
+        alg_bytes = st["algorithmic_bytes"]
+        achieved = alg_bytes / em_s / 1e9
+        # shared-memory model: 16 B (P,Q) + 16 B broadcast (1-e,e) per base term in the E-step, 8 B per M-step add
+        smem_bytes = st["base_terms"] * (16 + 8)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * dev_seconds / a.steps, "higher_is_better": True, "scaling": a.scaling,
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": a.config, "seed": a.seed, "gaps": len(gaps), "units": st["n_units"], "records": st["n_records"],
+                       "likelihoods_per_step_this_rank": st["likelihoods"], "l2": "flushed between steps (256 MiB write)",
+                       "partition": ("rank r fills the gap set of seed+r (gap-partitioned, no data-path collective)" if weak else
+                                     "one gap set dealt to ranks by descending cost, no data-path collective"),
+                       "filled_bases_total": filled_total, "host_wall_s": wall},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                         "frac": achieved / peaks.get("hbm_gbs"), "traffic": None, "peak_source": peak_kind,
+                         "kernel": "fb_em_kernel", "kernel_ms_per_step": 1e3 * em_s,
+                         "note": "HBM is not the binding roof of this path (~3 algorithmic bytes per likelihood); see smem"},
+            "smem": {"model_bytes_per_step": smem_bytes, "achieved_gbs": smem_bytes / em_s / 1e9,
+                     "fp64_instr_per_step": st["base_terms"] * 5, "fp64_ginstr_s": st["base_terms"] * 5 / em_s / 1e9},
+        }
+        if world == 1 and not a.no_cpu:
+            try:
+                rate, info = cpu_reference_rate(wd, a.cpu_liks, 1, "cb") if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "figbird.out")) else (None, None)
+            except Exception as e:   # the checker must not take the bench down
+                rate, info = None, {"error": str(e)}
+            if rate:
+                line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "reference",
+                                        "sample": f"{info['gaps']} gaps, {info['liks']} likelihoods, unmodified figbird.out -O2, 1 thread; "
+                                                  f"EM {info['em_s']:.2f} s = wall - preamble {info['preamble_s']:.2f} s"}
+            else:
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": f"unavailable: {info}"}
+        print(json.dumps(line))
+    fb.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2_rhodobacter")
+    ap.add_argument("--seed", type=int, default=2)
+    ap.add_argument("--cpu-liks", type=float, default=2.0e7, help="likelihoods in the cpu_baseline sample (~15-25 s of one core)")
+    ap.add_argument("--ref-liks", type=float, default=4.0e6, help="likelihoods per process per step in the reference arm")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

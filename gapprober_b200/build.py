@@ -57,9 +57,30 @@ def build_tools(force=False):
     return out
 
 
+def build_host(force=False):
+    """The drop-in figbird binary (host preamble + file contract; dlopens libfigbird_cuda.so at run time)."""
+    os.makedirs(BIN, exist_ok=True)
+    host = os.path.join(CSRC, "host")
+    src = os.path.join(host, "figbird.cpp")
+    deps = [src, os.path.join(host, "fb_preamble.hpp"), os.path.join(host, "fb_io.hpp"), os.path.join(ROOT, "include", "figbird_cuda.h")]
+    exe = os.path.join(BIN, "figbird.out")
+    if force or _newer(exe, deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, src])
+    return exe
+
+
+def learn_model(workdir, scaffolds="scaffolds.fa", out="fb_model.bin"):
+    """Run the host preamble of the drop-in binary in a GapProber working directory; returns the model path."""
+    exe = build_host()
+    env = dict(os.environ, FIGBIRD_MODEL_OUT=out, FIGBIRD_PREAMBLE_ONLY="1")
+    subprocess.run([exe, scaffolds, " 0", "250"], cwd=workdir, env=env, check=True, stdout=subprocess.DEVNULL)
+    return os.path.join(workdir, out)
+
+
 def build_all(force=False, verbose=False):
     build_library(force, verbose)
     build_tools(force)
+    build_host(force)
 
 
 if __name__ == "__main__":

@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -117,7 +118,7 @@ struct Bin {
 struct fb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, evs = nullptr, eve = nullptr;
     int max_smem = 0, sm_count = 0;
     std::string err;
 
@@ -157,6 +158,7 @@ struct fb_ctx {
     DevBuf<long long> d_bestoff;
     PinBuf<double> h_maxprob, h_finprob;
     PinBuf<int> h_finpos;
+    PinBuf<unsigned char> h_stage;   // pinned staging for the host->device copies
 
     fb_stats stats;
 
@@ -231,6 +233,8 @@ int fb_create(const fb_model* m, int device, fb_ctx** out) {
     cudaEventCreate(&c->ev1);
     cudaEventCreate(&c->ev2);
     cudaEventCreate(&c->ev3);
+    cudaEventCreate(&c->evs);
+    cudaEventCreate(&c->eve);
     c->max_read_len = m->max_read_len;
     c->thr_min = m->thr_min;
     c->thr_max = m->thr_max;
@@ -268,11 +272,13 @@ void fb_destroy(fb_ctx* c) {
     c->d_units.release(); c->d_counters.release(); c->d_maxprob.release(); c->d_gws.release(); c->d_finprob.release();
     c->d_dump.release(); c->d_cons.release(); c->d_finpos.release(); c->d_gaplist.release(); c->d_bestgp.release();
     c->d_bestoff.release();
-    c->h_maxprob.release(); c->h_finprob.release(); c->h_finpos.release();
+    c->h_maxprob.release(); c->h_finprob.release(); c->h_finpos.release(); c->h_stage.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev2) cudaEventDestroy(c->ev2);
     if (c->ev3) cudaEventDestroy(c->ev3);
+    if (c->evs) cudaEventDestroy(c->evs);
+    if (c->eve) cudaEventDestroy(c->eve);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -358,6 +364,38 @@ int fb_add_gap(fb_ctx* c, int contig_no, long gap_start, int orig_gap, const cha
     c->gaps.push_back(g);
     c->uploaded = c->ran = false;
     return (int)c->gaps.size() - 1;
+}
+
+int fb_add_gap_file(fb_ctx* c, int contig_no, long gap_start, int orig_gap, const char* contig, long contig_len, const char* gap_file) {
+    if (!c || !gap_file) return FB_EINVAL;
+    FILE* fp = fopen(gap_file, "r");
+    if (!fp) return c->fail(FB_EINVAL, "cannot open %s", gap_file);
+    // placeReads' parse, figbird.cpp:1718-1801
+    std::vector<fb_record> recs;
+    std::vector<std::string> seqs;
+    char l1[1024], l2[1024];
+    while (fgets(l1, sizeof l1, fp)) {
+        if (l1[0] == '@') continue;
+        if (!fgets(l2, sizeof l2, fp)) break;
+        char *s1 = nullptr, *s2 = nullptr, *col[7];
+        bool ok = (col[0] = strtok_r(l1, "\t", &s1)) != nullptr;
+        for (int k = 1; k < 7 && ok; k++) ok = (col[k] = strtok_r(nullptr, "\t", &s1)) != nullptr;
+        if (!ok) continue;
+        char* m = strtok_r(l2, "\t", &s2);
+        for (int k = 1; k < 7 && m; k++) m = strtok_r(nullptr, "\t", &s2);
+        if (!m) continue;
+        fb_record r;
+        r.strand1 = (atoi(col[1]) & 16) >> 4;
+        r.pos1 = atoi(col[3]);
+        r.len1 = (int)strlen(col[6]);
+        seqs.emplace_back(m);
+        r.seq2 = nullptr;
+        r.len2 = (int)seqs.back().size();
+        recs.push_back(r);
+    }
+    fclose(fp);
+    for (size_t i = 0; i < recs.size(); i++) recs[i].seq2 = seqs[i].c_str();
+    return fb_add_gap(c, contig_no, gap_start, orig_gap, contig, contig_len, recs.data(), (int)recs.size());
 }
 
 }  // extern "C"
@@ -544,9 +582,17 @@ int fb_upload(fb_ctx* c) {
     FB_CUDA(c, c->h_finprob.ensure(nr));
     FB_CUDA(c, c->h_finpos.ensure(nr));
     long h2d = 0;
+    const size_t stage_need = ng * sizeof(FbGapMeta) + c->h_flank.size() + (c->h_codes.size() + c->h_nmask.size()) * sizeof(uint4) +
+                              nr * sizeof(FbRecMeta) + c->h_units.size() * sizeof(FbUnit) + 6 * 256;
+    FB_CUDA(c, c->h_stage.ensure(stage_need));
+    size_t stage_off = 0;
     auto up = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
+        if (!bytes) return cudaSuccess;
         h2d += (long)bytes;
-        return bytes ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream) : cudaSuccess;
+        unsigned char* pin = c->h_stage.p + stage_off;   // copies leave from pinned memory
+        memcpy(pin, src, bytes);
+        stage_off += (bytes + 255) & ~size_t(255);
+        return cudaMemcpyAsync(dst, pin, bytes, cudaMemcpyHostToDevice, c->stream);
     };
     FB_CUDA(c, up(c->d_gapmeta.p, c->h_gapmeta.data(), ng * sizeof(FbGapMeta)));
     FB_CUDA(c, up(c->d_flank.p, c->h_flank.data(), c->h_flank.size()));
@@ -601,6 +647,7 @@ int fb_run_device(fb_ctx* c) {
     st.finalize_likelihoods = 0;
 
     // ---- EM scan: one persistent launch per size bin
+    FB_CUDA(c, cudaEventRecord(c->evs, c->stream));
     FB_CUDA(c, cudaMemsetAsync(c->d_counters.p, 0, sizeof(int) * (c->bins.size() + 1), c->stream));
     FB_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     for (size_t bi = 0; bi < c->bins.size(); bi++) {
@@ -741,7 +788,11 @@ int fb_run_device(fb_ctx* c) {
         }
         g.done = true;
     }
+    FB_CUDA(c, cudaEventRecord(c->eve, c->stream));
+    FB_CUDA(c, cudaEventSynchronize(c->eve));
     float ms = 0;
+    cudaEventElapsedTime(&ms, c->evs, c->eve);
+    st.step_ms = ms;
     cudaEventElapsedTime(&ms, c->ev0, c->ev1);
     st.em_kernel_ms = ms;
     st.finalize_kernel_ms = 0;

@@ -1,0 +1,233 @@
+// figbird.cpp — drop-in replacement for the reference's figbird.cpp (the binary GapProber.py:41-44 builds
+// with a bare `g++ ../figbird.cpp -o figbird.out` and runs as `./figbird.out <scaffolds.fa> ' 0' 250`).
+//
+// Same argv, same input files in the working directory (stat.txt, myout.sam, gapInfo.txt, Gaps/gaps_<n>.sam),
+// same output files (gapout.txt, filledContigs.fa, mappedInserts.txt, out.txt) and the same stdout lines
+// (figbird.cpp:2744, 2503, 2382, 2852, 2863, 2877, 2947).  The preamble runs on the host (fb_preamble.hpp);
+// GapFiller::fillGap for ALL gaps runs on the GPU through the C ABI of libfigbird_cuda.so, loaded with
+// dlopen so this file still compiles with no flags (glibc >= 2.34 needs no -ldl / -lpthread).
+//
+// Library lookup: $FIGBIRD_CUDA_LIB, then next to the executable, then its parent directory, then the
+// dynamic loader's search path.  Optional environment:
+//   FIGBIRD_DEVICE=<n>       CUDA device (default 0)
+//   FIGBIRD_MODEL_OUT=<path> also write the learned model ("FBM1" file)
+//   FIGBIRD_PREAMBLE_ONLY=1  stop after the preamble (used by the benchmark to build its model)
+// There is no CPU fallback: if the library or a GPU is missing the program prints why and exits 1.
+
+#include <dlfcn.h>
+#include <unistd.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "../../../include/figbird_cuda.h"
+#include "fb_io.hpp"
+#include "fb_preamble.hpp"
+
+namespace {
+
+struct Api {
+    void* h = nullptr;
+    decltype(&fb_create) create = nullptr;
+    decltype(&fb_destroy) destroy = nullptr;
+    decltype(&fb_add_gap) add_gap = nullptr;
+    decltype(&fb_run) run = nullptr;
+    decltype(&fb_result) result = nullptr;
+    decltype(&fb_last_error) last_error = nullptr;
+    decltype(&fb_status_str) status_str = nullptr;
+    decltype(&fb_abi_version) abi_version = nullptr;
+};
+
+std::string exe_dir() {
+    char buf[4096];
+    ssize_t n = readlink("/proc/self/exe", buf, sizeof buf - 1);
+    if (n <= 0) return ".";
+    buf[n] = 0;
+    std::string p(buf);
+    size_t s = p.rfind('/');
+    return s == std::string::npos ? "." : p.substr(0, s);
+}
+
+bool load_api(Api& a, std::string& why) {
+    std::vector<std::string> cand;
+    if (const char* e = getenv("FIGBIRD_CUDA_LIB")) cand.push_back(e);
+    const std::string d = exe_dir();
+    cand.push_back(d + "/libfigbird_cuda.so");
+    cand.push_back(d + "/../libfigbird_cuda.so");
+    cand.push_back("libfigbird_cuda.so");
+    for (auto& c : cand) {
+        a.h = dlopen(c.c_str(), RTLD_NOW | RTLD_LOCAL);
+        if (a.h) break;
+        why = dlerror();
+    }
+    if (!a.h) return false;
+#define FB_SYM(field, name)                                      \
+    a.field = reinterpret_cast<decltype(a.field)>(dlsym(a.h, name)); \
+    if (!a.field) { why = std::string("missing symbol ") + name; return false; }
+    FB_SYM(create, "fb_create")
+    FB_SYM(destroy, "fb_destroy")
+    FB_SYM(add_gap, "fb_add_gap")
+    FB_SYM(run, "fb_run")
+    FB_SYM(result, "fb_result")
+    FB_SYM(last_error, "fb_last_error")
+    FB_SYM(status_str, "fb_status_str")
+    FB_SYM(abi_version, "fb_abi_version")
+#undef FB_SYM
+    if (a.abi_version() != FB_ABI_VERSION) { why = "ABI version mismatch"; return false; }
+    return true;
+}
+
+}  // namespace
+
+int main(int argc, char* argv[]) {
+    if (argc < 3) {
+        printf("usage: %s <scaffolds.fa> <f> [ignored]\n", argv[0]);
+        return 1;
+    }
+    const char* contig_path = argv[1];
+    const int f_mode = atoi(argv[2]);
+    FILE* out_txt = fopen("out.txt", "w");   // the reference creates it and never writes to it
+    fbhost::Scaffolds sc;
+    if (!fbhost::read_scaffolds(contig_path, sc)) {
+        printf("Can't open contig file\n");
+        return 1;
+    }
+    FILE* probe = fopen("myout.sam", "r");
+    if (!probe) {
+        printf("Can't open map file\n");
+        return 1;
+    }
+    fclose(probe);
+    long total_count = 0, un_count = 0;
+    int max_read_len = 0, max_insert = 0;
+    if (FILE* st = fopen("stat.txt", "r")) {
+        if (fscanf(st, "%ld %ld %d %d", &total_count, &un_count, &max_read_len, &max_insert) != 4) max_read_len = 0;
+        fclose(st);
+    }
+    if (max_read_len < 1) {
+        printf("Can't read stat.txt\n");
+        return 1;
+    }
+
+    // ---- preamble (host): model tables + gapProbCutOff
+    fbhost::Preamble pre(max_read_len, max_insert, sc.lengths());
+    fbhost::Model hm;
+    if (!pre.learn("myout.sam", hm)) {
+        printf("Can't open map file\n");
+        return 1;
+    }
+    if (FILE* mi = fopen("mappedInserts.txt", "w")) {
+        for (long i = 0; i < (long)hm.inserts_mapped.size(); i++)
+            if (hm.inserts_mapped[i] > 0) fprintf(mi, "%ld,%ld\n", i, hm.inserts_mapped[i]);
+        fclose(mi);
+    }
+    if (out_txt) fclose(out_txt);
+    std::cout << "insertThresholdMin = " << hm.thr_min << "...insertThresholdMax = " << hm.thr_max << std::endl;
+    if (const char* mo = getenv("FIGBIRD_MODEL_OUT")) hm.save(mo);
+    if (getenv("FIGBIRD_PREAMBLE_ONLY")) return 0;
+
+    // ---- the hot path, on the GPU
+    Api api;
+    std::string why;
+    if (!load_api(api, why)) {
+        printf("figbird: cannot load libfigbird_cuda.so (%s); there is no CPU fallback\n", why.c_str());
+        return 1;
+    }
+    fb_model m;
+    memset(&m, 0, sizeof m);
+    m.max_read_len = hm.max_read_len;
+    m.error_pos = hm.error_pos.data();
+    m.in_pos = hm.in_pos.data();
+    m.del_pos = hm.del_pos.data();
+    for (int i = 0; i < 5; i++)
+        for (int j = 0; j < 5; j++) m.error_type[i][j] = hm.error_type[i][j];
+    m.ild = hm.ild_smoothed.data();
+    m.ild_len = hm.max_insert;
+    m.thr_min = hm.thr_min;
+    m.thr_max = hm.thr_max;
+    m.gap_prob_cutoff = hm.cutoff;
+    m.max_distance = 200;   // maxDistance, figbird.cpp:103
+    m.num_iter = 5;         // num_itr, figbird.cpp:2466
+    m.f_mode = f_mode;
+    fb_ctx* ctx = nullptr;
+    const int device = getenv("FIGBIRD_DEVICE") ? atoi(getenv("FIGBIRD_DEVICE")) : 0;
+    int rc = api.create(&m, device, &ctx);
+    if (rc != FB_OK) {
+        printf("figbird: fb_create failed: %s%s\n", api.status_str(rc),
+               rc == FB_EUNSUPPORTED ? " (only f=0, the mode GapProber.py uses, runs on the GPU)" : "");
+        return 1;
+    }
+
+    time_t t0, t1;
+    time(&t0);
+    std::vector<fbhost::GapInfo> gaps;
+    if (!fbhost::read_gap_info("gapInfo.txt", gaps)) {
+        printf("Can't open gapInfo.txt\n");
+        return 1;
+    }
+    std::vector<int> handle(gaps.size(), -1);
+    for (size_t g = 0; g < gaps.size(); g++) {
+        char name[64];
+        snprintf(name, sizeof name, "Gaps/gaps_%zu.sam", g);
+        std::vector<fbhost::GapRecord> recs;
+        if (!fbhost::read_gap_file(name, recs)) {
+            printf("Can't open %s\n", name);
+            return 1;
+        }
+        std::vector<fb_record> rv(recs.size());
+        for (size_t r = 0; r < recs.size(); r++) {
+            rv[r].pos1 = recs[r].pos1;
+            rv[r].len1 = recs[r].len1;
+            rv[r].strand1 = recs[r].strand1;
+            rv[r].seq2 = recs[r].seq2.c_str();
+            rv[r].len2 = (int)recs[r].seq2.size();
+        }
+        const fbhost::GapInfo& gi = gaps[g];
+        if (gi.contig_no < 0 || gi.contig_no >= (int)sc.seqs.size()) continue;
+        const std::string& ctg = sc.seqs[gi.contig_no];
+        int h = api.add_gap(ctx, gi.contig_no, gi.start, gi.length, ctg.c_str(), (long)ctg.size(), rv.data(), (int)rv.size());
+        if (h < 0) fprintf(stderr, "figbird: gap %zu left unfilled: %s\n", g, api.last_error(ctx));
+        handle[g] = h;
+    }
+    rc = api.run(ctx);
+    if (rc != FB_OK) {
+        printf("figbird: fb_run failed: %s: %s\n", api.status_str(rc), api.last_error(ctx));
+        return 1;
+    }
+    FILE* gap_out = fopen("gapout.txt", "w");
+    std::vector<std::string> filled(gaps.size());
+    for (size_t g = 0; g < gaps.size(); g++) {
+        const fbhost::GapInfo& gi = gaps[g];
+        if (handle[g] >= 0) {
+            fb_gap_result res;
+            std::vector<char> buf((size_t)2 * gi.length + 16);
+            rc = api.result(ctx, handle[g], &res, buf.data(), (int)buf.size());
+            if (rc != FB_OK) {
+                printf("figbird: fb_result failed: %s\n", api.last_error(ctx));
+                return 1;
+            }
+            filled[g] = buf.data();
+            std::cout << "----##############MaxGapEstimate = " << res.best_estimate << "\t" << "MaxLikelihood = " << res.best_lik << std::endl;
+            std::cout << "Total_Reads = " << res.total_reads << "\t" << "Discard = " << res.discarded << std::endl;
+        } else {
+            filled[g].assign((size_t)gi.length, 'N');
+        }
+        fprintf(gap_out, "%d\t%d\t%ld\t%d\t%d\t%s\n", (int)g, gi.contig_no, gi.start, gi.length, (int)filled[g].size(), filled[g].c_str());
+        std::cout << "Gap " << g << " is done." << std::endl;
+    }
+    fclose(gap_out);
+    api.destroy(ctx);
+    time(&t1);
+    std::cout << "Total time to fill gaps in seconds = " << difftime(t1, t0) << std::endl;
+
+    // ---- stitch
+    std::cout << "# of Contig = " << sc.seqs.size() << std::endl;
+    fbhost::stitch(sc, filled, "filledContigs.fa");
+    std::cout << "Figbird.cpp ends successfully" << std::endl;
+    return 0;
+}

@@ -65,7 +65,7 @@ class FbStats(C.Structure):
     _fields_ = [
         ("n_gaps", C.c_long), ("n_units", C.c_long), ("n_records", C.c_long),
         ("likelihoods", C.c_long), ("finalize_likelihoods", C.c_long), ("base_terms", C.c_long),
-        ("em_kernel_ms", C.c_double), ("finalize_kernel_ms", C.c_double),
+        ("em_kernel_ms", C.c_double), ("finalize_kernel_ms", C.c_double), ("step_ms", C.c_double),
         ("em_launches", C.c_int), ("finalize_launches", C.c_int),
         ("h2d_bytes", C.c_long), ("d2h_bytes", C.c_long), ("algorithmic_bytes", C.c_long),
     ]
@@ -76,7 +76,7 @@ class FbStats(C.Structure):
 
 # Every symbol include/figbird_cuda.h declares; tests check the library exports all of them.
 ABI_SYMBOLS = [
-    "fb_create", "fb_destroy", "fb_add_gap", "fb_set_partition", "fb_owns_gap", "fb_run", "fb_upload",
+    "fb_create", "fb_destroy", "fb_add_gap", "fb_add_gap_file", "fb_set_partition", "fb_owns_gap", "fb_run", "fb_upload",
     "fb_run_device", "fb_result", "fb_estimate_liks", "fb_best_string", "fb_dump_profile", "fb_get_stats",
     "fb_clear_gaps", "fb_gap_range", "fb_last_error", "fb_status_str", "fb_abi_version",
 ]
@@ -97,6 +97,7 @@ def load_library():
     L.fb_destroy.argtypes = [vp]
     L.fb_destroy.restype = None
     L.fb_add_gap.argtypes = [vp, C.c_int, C.c_long, C.c_int, C.c_char_p, C.c_long, C.POINTER(_FbRecord), C.c_int]
+    L.fb_add_gap_file.argtypes = [vp, C.c_int, C.c_long, C.c_int, C.c_char_p, C.c_long, C.c_char_p]
     L.fb_set_partition.argtypes = [vp, C.c_int, C.c_int]
     L.fb_owns_gap.argtypes = [vp, C.c_int]
     L.fb_run.argtypes = [vp]
@@ -229,11 +230,13 @@ class GapFiller:
         self.contigNo = None
 
     def initGapFiller(self, contigNo, gapStart, originalGap, gapFile, contig):
-        """figbird.cpp:1610-1618 + the gap-file parse.  gapFile: path, or a list of (pos1, len1, strand1, seq2)."""
-        recs = read_gap_file(gapFile) if isinstance(gapFile, (str, bytes, os.PathLike)) else list(gapFile)
+        """figbird.cpp:1610-1618 + the gap-file parse.  gapFile: path (parsed inside the library, as placeReads
+        does), or an already parsed list of (pos1, len1, strand1, seq2)."""
         self.contigNo, self.gapStart, self.originalGap = int(contigNo), int(gapStart), int(originalGap)
-        self.index = self._ctx._add_gap(self.contigNo, self.gapStart, self.originalGap, contig, recs)
-        self.n_records = len(recs)
+        if isinstance(gapFile, (str, bytes, os.PathLike)):
+            self.index = self._ctx._add_gap_file(self.contigNo, self.gapStart, self.originalGap, contig, os.fsencode(gapFile))
+        else:
+            self.index = self._ctx._add_gap(self.contigNo, self.gapStart, self.originalGap, contig, list(gapFile))
         return self
 
     def _result(self):
@@ -313,6 +316,9 @@ class FigbirdContext:
             arr[i].seq2 = seq
             arr[i].len2 = len(seq)
         return self._check(self._L.fb_add_gap(self._h, contig_no, gap_start, orig, contig, len(contig), arr, len(recs)))
+
+    def _add_gap_file(self, contig_no, gap_start, orig, contig, path):
+        return self._check(self._L.fb_add_gap_file(self._h, contig_no, gap_start, orig, contig, len(contig), path))
 
     def add_workdir(self, wd, scaffolds="scaffolds.fa"):
         """Register every gap of a GapProber working directory (gapInfo.txt + Gaps/), like figbird.cpp:2819-2842."""

@@ -74,6 +74,7 @@ typedef struct fb_stats {
     long base_terms;            /* likelihoods x mate length                                          */
     double em_kernel_ms;        /* CUDA-event time of the EM kernel launches of the last fb_run_device */
     double finalize_kernel_ms;
+    double step_ms;             /* CUDA-event time of the whole last fb_run_device (kernels, copies, host phases) */
     int em_launches, finalize_launches;
     long h2d_bytes, d2h_bytes;  /* of the last fb_upload + fb_run_device                               */
     long algorithmic_bytes;     /* SURVEY §8(d) HBM byte model summed over (unit, iteration)            */
@@ -92,6 +93,12 @@ void fb_destroy(fb_ctx* ctx);
  * Returns the gap index (>= 0) or a negative fb_status. */
 int fb_add_gap(fb_ctx* ctx, int contig_no, long gap_start, int orig_gap, const char* contig, long contig_len,
                const fb_record* recs, int nrec);
+
+/* Same, parsing the gap file in the library exactly as placeReads does on every call (figbird.cpp:1680-1812):
+ * fgets line pairs of at most 1023 bytes, '@' lines skipped, tab-separated columns
+ * qname flag rname pos cigar tlen seq.  A missing file is FB_EINVAL. */
+int fb_add_gap_file(fb_ctx* ctx, int contig_no, long gap_start, int orig_gap, const char* contig, long contig_len,
+                    const char* gap_file);
 
 /* Restrict this context to its share of the work when several processes (one per GPU) split one gap
  * set: gaps are dealt to `world` ranks by descending cost (longest-processing-time first); this
