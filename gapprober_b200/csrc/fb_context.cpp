@@ -104,6 +104,9 @@ struct PinBuf {
     }
 };
 
+// doubles of global workspace per CTA when the tables do not fit shared memory: pq (5*nrs + 32 pad rows of double2) + counts
+inline size_t gws_stride_of(int nr_stride, int gp_stride) { return (size_t)10 * nr_stride + 64 + 5 * (size_t)gp_stride + 16; }
+
 struct Bin {
     int first_unit, n_units;      // range in the sorted unit array
     int gpmax, lmax;
@@ -559,7 +562,7 @@ int fb_upload(fb_ctx* c) {
         }
         b.smem = fb_em_smem_bytes(b.nr_stride, b.gp_stride, b.p_stride, b.chunk, pwin, b.global_tables);
         b.grid = std::min(b.n_units, c->sm_count * ctas);
-        if (b.global_tables) gws_need = std::max(gws_need, (size_t)b.grid * ((size_t)10 * b.nr_stride + 5 * (size_t)b.gp_stride + 16));
+        if (b.global_tables) gws_need = std::max(gws_need, (size_t)b.grid * gws_stride_of(b.nr_stride, b.gp_stride));
     }
     // ---- device buffers + host->device copies
     const size_t ng = c->h_gapmeta.size(), nr = c->h_rmeta.size();
@@ -661,7 +664,7 @@ int fb_run_device(fb_ctx* c) {
         p.gp_stride = b.gp_stride;
         p.p_stride = b.p_stride;
         p.chunk = b.chunk;
-        p.gws_stride = (size_t)10 * b.nr_stride + 5 * (size_t)b.gp_stride + 16;
+        p.gws_stride = gws_stride_of(b.nr_stride, b.gp_stride);
         FB_CUDA(c, fb_launch_em(p, b.grid, b.global_tables, b.smem, c->stream));
         st.em_launches++;
     }
@@ -879,7 +882,7 @@ int fb_dump_profile(fb_ctx* c, int gap, int estimate, double* probs, double* cou
             p.gp_stride = b.gp_stride;
             p.p_stride = b.p_stride;
             p.chunk = b.chunk;
-            p.gws_stride = (size_t)10 * b.nr_stride + 5 * (size_t)b.gp_stride + 16;
+            p.gws_stride = gws_stride_of(b.nr_stride, b.gp_stride);
             p.dump_probs = c->d_dump.p;
             p.dump_counts = c->d_dump.p + n;
             p.dump_unit = 0;

@@ -58,21 +58,55 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
     return v;
 }
 
-struct EmSmem {
-    double2* eo;
-    double* ild;
-    double2* pq;
-    double* cnt;
-    double* w;
+// ---------------------------------------------------------------------------------------------------
+// Shared-memory plan of the EM kernel.  Per CTA:
+//   eo, ild          model tables (read-position error rates, insert-length window)
+//   pq[5][nrs+pad]   {P[row][c], Q[row][c]} per base class, class 4 = {0, Q[row][4]}          (E-step reads)
+//   cnt[5][gps]      counts of the gap rows                                                  (M-step accumulates)
+//   w[2][chunk][ps]  placement scores of two in-flight record chunks
+//   st[3]            staged record chunks: window, flags, class bit-masks, per-position table offsets
+// One unit runs as a software pipeline over chunks of records: in round r the CTA's warps pull, from one
+// dynamic queue, M-step tasks of chunk r-2, E-step tasks of chunk r-1 and staging tasks of chunk r, and
+// meet at ONE barrier per round.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kPadRows = 32;   // a lane's second placement sits 32 rows further; invalid lanes may read (not use) past the end
+
+struct Stage {
     int* rlo;
     int* rhi;
     int* rtb;
     int* rfl;
     unsigned long long* rmax;
-    uint8_t* clsoff;
-    uint8_t* codes;
-    uint8_t* jl;
+    uint32_t* mask;   // [chunk][5][4] bit j of class c: base j of the record is c
+    uint32_t* off;    // [chunk][128] byte offset of class(base j) inside pq
 };
+
+struct EmSmem {
+    double2* eo;
+    double* ild;
+    double2* pq;
+    double* cnt;
+    double* w0;              // two score buffers, w_stride doubles apart
+    size_t w_stride;
+    unsigned char* st0;      // three staged chunks, st_stride bytes apart
+    size_t st_stride;
+    int chunk;
+};
+
+// Carve one staged chunk out of its slab (same order as em_carve lays it out).
+__device__ __forceinline__ Stage stage_at(const EmSmem& s, int k) {
+    unsigned char* b = s.st0 + (size_t)k * s.st_stride;
+    Stage t;
+    t.rmax = reinterpret_cast<unsigned long long*>(b);
+    b += sizeof(unsigned long long) * s.chunk;
+    t.rlo = reinterpret_cast<int*>(b);
+    t.rhi = t.rlo + s.chunk;
+    t.rtb = t.rhi + s.chunk;
+    t.rfl = t.rtb + s.chunk;
+    t.mask = reinterpret_cast<uint32_t*>(t.rfl + s.chunk);
+    t.off = t.mask + 20 * s.chunk;
+    return t;
+}
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
@@ -88,27 +122,23 @@ __host__ __device__ inline size_t em_carve(unsigned char* base, EmSmem* s, int n
     a = take(sizeof(double2) * FB_MAX_READ); if (s) s->eo = (double2*)a;
     a = take(sizeof(double) * pwin); if (s) s->ild = (double*)a;
     if (!global_tables) {
-        a = take(sizeof(double2) * 5 * (size_t)nr_stride); if (s) s->pq = (double2*)a;
+        a = take(sizeof(double2) * (5 * (size_t)nr_stride + kPadRows)); if (s) s->pq = (double2*)a;
         a = take(sizeof(double) * 5 * (size_t)gp_stride); if (s) s->cnt = (double*)a;
     }
-    a = take(sizeof(double) * (size_t)chunk * p_stride); if (s) s->w = (double*)a;
-    a = take(sizeof(unsigned long long) * chunk); if (s) s->rmax = (unsigned long long*)a;
-    a = take(sizeof(int) * chunk); if (s) s->rlo = (int*)a;
-    a = take(sizeof(int) * chunk); if (s) s->rhi = (int*)a;
-    a = take(sizeof(int) * chunk); if (s) s->rtb = (int*)a;
-    a = take(sizeof(int) * chunk); if (s) s->rfl = (int*)a;
-    a = take((size_t)8 * chunk); if (s) s->clsoff = a;
-    a = take((size_t)FB_MAX_READ * chunk); if (s) s->codes = a;
-    a = take((size_t)FB_MAX_READ * chunk); if (s) s->jl = a;
+    const size_t wbytes = align16(sizeof(double) * (size_t)chunk * p_stride);
+    a = take(2 * wbytes);
+    if (s) { s->w0 = (double*)a; s->w_stride = wbytes / sizeof(double); }
+    // one staged chunk: rmax[chunk] u64 | rlo, rhi, rtb, rfl [chunk] int | mask[chunk][20] u32 | off[chunk][128] u32
+    const size_t sbytes = align16((size_t)chunk * (8 + 4 * 4 + 20 * 4 + FB_MAX_READ * 4));
+    a = take(3 * sbytes);
+    if (s) { s->st0 = a; s->st_stride = sbytes; s->chunk = chunk; }
     return off;
 }
 
-// Unpack one record's bases into byte codes (0-3 ACGT, 4 other, 5 past the end) and build, per base
-// class, the list of read positions holding it in DESCENDING order (so that placements are visited in
-// ascending order by the M-step).  One warp per record.
-__device__ __forceinline__ void load_record(const uint4* __restrict__ codes, const uint4* __restrict__ nmask, int rec, int L2,
-                                            uint8_t* cs, uint8_t* jl, uint8_t* clsoff, int lane) {
-    // 128-bit loads: lanes 0,1 fetch the 2-bit codes, lane 2 the non-ACGT mask
+// 2-bit codes + non-ACGT mask of one record -> this lane's four base classes (positions 4*lane .. 4*lane+3):
+// 0-3 ACGT, 4 other, 5 past the end.  128-bit loads by lanes 0-2, redistributed with shuffles.
+__device__ __forceinline__ void fetch_classes(const uint4* __restrict__ codes, const uint4* __restrict__ nmask, int rec, int L2,
+                                              int lane, unsigned cls[4]) {
     uint4 v = make_uint4(0, 0, 0, 0);
     if (lane < 2) v = __ldg(&codes[(size_t)rec * 2 + lane]);
     else if (lane == 2) v = __ldg(&nmask[rec]);
@@ -121,31 +151,58 @@ __device__ __forceinline__ void load_record(const uint4* __restrict__ codes, con
     unsigned m0 = __shfl_sync(0xffffffffu, v.x, 2), m1 = __shfl_sync(0xffffffffu, v.y, 2);
     unsigned m2 = __shfl_sync(0xffffffffu, v.z, 2), m3 = __shfl_sync(0xffffffffu, v.w, 2);
     unsigned mw = msel == 0 ? m0 : msel == 1 ? m1 : msel == 2 ? m2 : m3;
-    unsigned packed = 0;
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         int j = lane * 4 + q;
         unsigned c = (cw >> (2 * (j & 15))) & 3u;
         if ((mw >> (j & 31)) & 1u) c = 4;
         if (j >= L2) c = 5;
-        packed |= c << (8 * q);
+        cls[q] = c;
     }
-    reinterpret_cast<uint32_t*>(cs)[lane] = packed;
+}
+
+// Byte-code form used by the finalize kernel.
+__device__ __forceinline__ void load_record_bytes(const uint4* __restrict__ codes, const uint4* __restrict__ nmask, int rec, int L2,
+                                                  uint8_t* cs, int lane) {
+    unsigned cls[4];
+    fetch_classes(codes, nmask, rec, L2, lane, cls);
+    reinterpret_cast<uint32_t*>(cs)[lane] = cls[0] | (cls[1] << 8) | (cls[2] << 16) | (cls[3] << 24);
     __syncwarp();
-    int base = 0;
-#pragma unroll 1
-    for (int c = 0; c < 5; c++) {
-        if (lane == 0) clsoff[c] = (uint8_t)base;
+}
+
+// E-step of 64 placements of one record: lane owns placements ua and ua+32 (two independent product chains).
+// The running score is multiplied base by base in read order (figbird.cpp:1840-1864); REV selects the
+// read-position index k = L2-1-j of a reverse-complemented mate (figbird.cpp:1845-1852).
+template <bool REV>
+__device__ __forceinline__ void score_pair(const unsigned char* pa, const uint32_t* __restrict__ off, const double2* __restrict__ eo,
+                                           int L2, double& sa, double& sb) {
+    const double2* ep = REV ? eo + (L2 - 1) : eo;
+    int j0 = 0;
+    for (; j0 + 4 <= L2; j0 += 4) {
+        const uint4 o = *reinterpret_cast<const uint4*>(off + j0);
+        const uint32_t oo[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-        for (int b = FB_MAX_READ / 32 - 1; b >= 0; b--) {
-            int j = b * 32 + lane;
-            bool has = cs[j] == c;
-            unsigned m = __ballot_sync(0xffffffffu, has);
-            if (has) jl[base + __popc(m >> lane) - 1] = (uint8_t)j;   // rank among set bits at or above this lane
-            base += __popc(m);
+        for (int q = 0; q < 4; q++) {
+            const unsigned char* a = pa + oo[q] + q * 16;
+            const double2 va = *reinterpret_cast<const double2*>(a);
+            const double2 vb = *reinterpret_cast<const double2*>(a + 32 * 16);
+            const double2 e = REV ? ep[-q] : ep[q];                         // {1 - e[k], e[k]}
+            sa = dmul(sa, dadd(dmul(va.x, e.x), dmul(e.y, va.y)));          // figbird.cpp:1855 / 1862
+            sb = dmul(sb, dadd(dmul(vb.x, e.x), dmul(e.y, vb.y)));
         }
+        pa += 64;
+        ep += REV ? -4 : 4;
     }
-    if (lane == 0) clsoff[5] = (uint8_t)base;
+    for (; j0 < L2; j0++) {
+        const unsigned char* a = pa + off[j0];
+        const double2 va = *reinterpret_cast<const double2*>(a);
+        const double2 vb = *reinterpret_cast<const double2*>(a + 32 * 16);
+        const double2 e = *ep;
+        sa = dmul(sa, dadd(dmul(va.x, e.x), dmul(e.y, va.y)));
+        sb = dmul(sb, dadd(dmul(vb.x, e.x), dmul(e.y, vb.y)));
+        pa += 16;
+        ep += REV ? -1 : 1;
+    }
 }
 
 template <bool GT>
@@ -157,22 +214,28 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const FbE
     if (GT) {
         double* g = p.gws + (size_t)blockIdx.x * p.gws_stride;
         s.pq = reinterpret_cast<double2*>(g);
-        s.cnt = g + (size_t)10 * p.nr_stride;
+        s.cnt = g + 2 * ((size_t)5 * p.nr_stride + kPadRows);
     }
     __shared__ int s_unit;
+    __shared__ int s_queue[2];
     __shared__ double sT[25];
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = FB_THREADS / 32;
-    const int D = p.D;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int D = p.D, CH = p.chunk, PS = p.p_stride;
 
     for (int i = tid; i < p.max_read_len && i < FB_MAX_READ; i += FB_THREADS) s.eo[i] = p.eo[i];
     for (int i = tid; i < pwin; i += FB_THREADS) s.ild[i] = p.ild[i];
     if (tid < 25) sT[tid] = p.T[tid];
+    if (GT) {
+        for (int i = tid; i < kPadRows; i += FB_THREADS) s.pq[5 * (size_t)p.nr_stride + i] = make_double2(0.0, 0.0);
+    }
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_unit = atomicAdd(p.work_counter, 1);
+        if (tid == 0) {
+            s_unit = atomicAdd(p.work_counter, 1);
+            s_queue[0] = 0;
+        }
         __syncthreads();
         const int ui = s_unit;
         if (ui >= p.n_units) break;
@@ -205,94 +268,121 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const FbE
         }
         __syncthreads();
 
+        const int nchunks = (nrec + CH - 1) / CH;
+        const int nrg = (gp + 31) >> 5;               // M-step row groups
+        const int nblk = (PS + 63) >> 6;              // E-step blocks of 64 placements per record
+        int round = 0;                                // global round counter: selects the queue slot
         for (int it = 0; it < p.num_iter; it++) {
             const bool last = it == p.num_iter - 1;
-            for (int c0 = 0; c0 < nrec; c0 += p.chunk) {
-                const int nch = min(p.chunk, nrec - c0);
-                // ---- stage this round's records: unpack bases, class lists, placement window
-                for (int rl = warp; rl < nch; rl += NW) {
-                    const int rec = gm.rec_off + c0 + rl;
-                    const FbRecMeta rm = p.rmeta[rec];
-                    const int L2 = rm.flags & 0xff;
-                    load_record(p.codes, p.nmask, rec, L2, s.codes + rl * FB_MAX_READ, s.jl + rl * FB_MAX_READ, s.clsoff + rl * 8, lane);
-                    if (lane == 0) {
-                        // placements i in [gapStart-L2+1, gapStart+gp) (figbird.cpp:1826) -> u in [D-L2+1, D+gp-1]
-                        s.rlo[rl] = max(rm.a_lo, D - L2 + 1);
-                        s.rhi[rl] = min(rm.a_hi, D + gp - 1);
-                        s.rtb[rl] = rm.tb;
-                        s.rfl[rl] = rm.flags;
-                        s.rmax[rl] = 0ull;
-                    }
-                }
-                __syncthreads();
-
-                // ---- E-step: warp per (record, group of 32 placements); lanes over placements
-                const int gmaxg = (p.p_stride + 31) >> 5;
-                for (int task = warp; task < nch * gmaxg; task += NW) {
-                    const int rl = task / gmaxg, g = task - rl * gmaxg;
-                    const int lo = s.rlo[rl], hi = s.rhi[rl];
-                    if (lo + 32 * g > hi) continue;
-                    const int fl2 = s.rfl[rl], L2 = fl2 & 0xff;
-                    const bool rev = (fl2 >> 8) & 1, left = (fl2 >> 9) & 1;
-                    const int u = lo + 32 * g + lane;
-                    const bool valid = u <= hi;
-                    const int uu = valid ? u : lo;
-                    const int t = left ? uu + s.rtb[rl] : s.rtb[rl] - uu;
-                    double sc = s.ild[t - p.thr_min];
-                    const double2* pq = s.pq + (uu - R0);
-                    const uint32_t* cw = reinterpret_cast<const uint32_t*>(s.codes + rl * FB_MAX_READ);
-                    const double2* ep = rev ? s.eo + (L2 - 1) : s.eo;
-                    const int es = rev ? -1 : 1;
-                    for (int j0 = 0; j0 < L2; j0 += 4) {
-                        const uint32_t c4 = cw[j0 >> 2];
-#pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            const int j = j0 + q;
-                            if (j < L2) {
-                                const int c = (c4 >> (8 * q)) & 0xff;
-                                const double2 v = pq[c * nrs + j];     // {P[row][c], Q[row][c]}; class 4 holds {0, Q[row][4]}
-                                const double2 e = ep[j * es];          // {1 - e[k], e[k]}
-                                const double aa = dadd(dmul(v.x, e.x), dmul(e.y, v.y));   // figbird.cpp:1855 / 1862
-                                sc = dmul(sc, aa);
+            // rounds of the pipeline: stage chunk r | E-step chunk r-1 | M-step chunk r-2
+            for (int r = 0; r < nchunks + 2; r++, round++) {
+                const int cl = r, ce = r - 1, cm = r - 2;
+                const int n_l = cl < nchunks ? min(CH, nrec - cl * CH) : 0;
+                const int n_e = (ce >= 0 && ce < nchunks) ? min(CH, nrec - ce * CH) : 0;
+                const int n_m = (cm >= 0 && cm < nchunks) ? min(CH, nrec - cm * CH) : 0;
+                const Stage SL = stage_at(s, cl % 3), SE = stage_at(s, (ce + 3) % 3), SM = stage_at(s, (cm + 3) % 3);
+                double* wE = s.w0 + ((ce + 2) & 1) * s.w_stride;
+                const double* wM = s.w0 + ((cm + 2) & 1) * s.w_stride;
+                if (last && tid < n_m)   // per-record maximum of the last iteration (feeds figbird.cpp:1951-1955 on the host)
+                    p.unit_maxprob[unit.mp_off + cm * CH + tid] = __longlong_as_double((long long)SM.rmax[tid]);
+                const int tM = n_m ? nrg * 5 : 0, tE = n_e * nblk, tL = n_l;
+                const int ntask = tM + tE + tL;
+                int* queue = &s_queue[round & 1];
+                for (;;) {
+                    int task = 0;
+                    if (lane == 0) task = atomicAdd(queue, 1);
+                    task = __shfl_sync(0xffffffffu, task, 0);
+                    if (task >= ntask) break;
+                    if (task < tM) {
+                        // ---- M-step: lane per gap row, warp per (32 rows, base class).  Within a cell the CPU adds in
+                        // (record asc, placement asc) order (figbird.cpp:1718, 1826, 1874): walking a record's class
+                        // mask from high j to low j visits its placements in ascending order.
+                        const int c = task / nrg, rg = task - c * nrg;
+                        const int xg = rg * 32 + lane, x0 = D + rg * 32, x = x0 + lane;
+                        const bool rowok = xg < gp;
+                        double acc = rowok ? s.cnt[c * gps + xg] : 0.0;
+                        for (int rl = 0; rl < n_m; rl++) {
+                            const int lo = SM.rlo[rl], hi = SM.rhi[rl];
+                            const int L2 = SM.rfl[rl] & 0xff;
+                            const int jhi = min(L2 - 1, x0 + 31 - lo), jlo = max(0, x0 - hi);   // j with any lane inside [lo, hi]
+                            if (hi < lo || jhi < jlo) continue;
+                            const uint32_t* mk = SM.mask + rl * 20 + c * 4;
+                            const double* wr = wM + rl * PS - lo;
+                            const unsigned span = (unsigned)(hi - lo);
+                            for (int wd = jhi >> 5; wd >= (jlo >> 5); wd--) {
+                                uint32_t m = mk[wd];
+                                if (wd == (jhi >> 5)) m &= 0xffffffffu >> (31 - (jhi & 31));
+                                if (wd == (jlo >> 5)) m &= 0xffffffffu << (jlo & 31);
+                                const int xw = x - wd * 32;
+                                while (m) {
+                                    const int b = 31 - __clz(m);
+                                    m ^= 1u << b;
+                                    const int u = xw - b;
+                                    if (rowok && (unsigned)(u - lo) <= span) acc = dadd(acc, wr[u]);   // figbird.cpp:1879
+                                }
                             }
                         }
-                    }
-                    if (valid) s.w[rl * p.p_stride + (u - lo)] = sc;
-                    // tempProb > maxProb with maxProb starting at 0: NaN and non-positive scores never win
-                    unsigned long long bits = (valid && sc > 0.0) ? (unsigned long long)__double_as_longlong(sc) : 0ull;
-                    bits = warp_max_u64(bits);
-                    if (lane == 0 && bits) atomicMax(&s.rmax[rl], bits);
-                }
-                __syncthreads();
-
-                // ---- M-step: lane per gap row, warp per (32 rows, base class).  Within a cell the CPU adds in
-                // (record asc, placement asc) order; walking a class list in descending j is ascending placement.
-                const int nrg = (gp + 31) >> 5;
-                for (int task = warp; task < nrg * 5; task += NW) {
-                    const int c = task / nrg, rg = task - c * nrg;
-                    const int xg = rg * 32 + lane;
-                    const int x = D + xg, x0 = D + rg * 32;
-                    const bool rowok = xg < gp;
-                    double acc = rowok ? s.cnt[c * gps + xg] : 0.0;
-                    for (int rl = 0; rl < nch; rl++) {
-                        const int lo = s.rlo[rl], hi = s.rhi[rl];
-                        const int L2 = s.rfl[rl] & 0xff;
-                        if (hi < lo || x0 + 31 < lo || x0 > hi + L2 - 1) continue;
-                        const uint8_t* jl = s.jl + rl * FB_MAX_READ;
-                        const int qb = s.clsoff[rl * 8 + c], qe = s.clsoff[rl * 8 + c + 1];
-                        const double* wr = s.w + rl * p.p_stride - lo;
-                        for (int q = qb; q < qe; q++) {
-                            const int j = jl[q];
-                            if (j > x0 + 31 - lo) continue;   // every lane would sit left of the window
-                            if (j < x0 - hi) break;           // ... or right of it, and j only decreases
-                            const int u = x - j;
-                            if (rowok && u >= lo && u <= hi) acc = dadd(acc, wr[u]);   // figbird.cpp:1879
+                        if (rowok) s.cnt[c * gps + xg] = acc;
+                    } else if (task < tM + tE) {
+                        // ---- E-step: warp per (record, 64 placements); lanes over placements
+                        const int te = task - tM;
+                        const int rl = te / nblk, blk = te - rl * nblk;
+                        const int lo = SE.rlo[rl], hi = SE.rhi[rl];
+                        if (lo + 64 * blk > hi) continue;
+                        const int fl2 = SE.rfl[rl], L2 = fl2 & 0xff, tb = SE.rtb[rl];
+                        const bool rev = (fl2 >> 8) & 1, left = (fl2 >> 9) & 1;
+                        const int ua = lo + 64 * blk + lane, ub = ua + 32;
+                        const bool va_ok = ua <= hi, vb_ok = ub <= hi;
+                        const int uc = va_ok ? ua : lo;                      // invalid lanes shadow a valid placement
+                        const int ta = left ? uc + tb : tb - uc;
+                        const int tbb = vb_ok ? (left ? ub + tb : tb - ub) : ta;
+                        double sa = s.ild[ta - p.thr_min], sb = s.ild[tbb - p.thr_min];
+                        const unsigned char* pa = reinterpret_cast<const unsigned char*>(s.pq + (uc - R0));
+                        const uint32_t* off = SE.off + rl * FB_MAX_READ;
+                        if (rev) score_pair<true>(pa, off, s.eo, L2, sa, sb);
+                        else score_pair<false>(pa, off, s.eo, L2, sa, sb);
+                        double* wrow = wE + rl * PS - lo;
+                        if (va_ok) wrow[ua] = sa;
+                        if (vb_ok) wrow[ub] = sb;
+                        // tempProb > maxProb with maxProb starting at 0: NaN and non-positive scores never win
+                        unsigned long long ba = (va_ok && sa > 0.0) ? (unsigned long long)__double_as_longlong(sa) : 0ull;
+                        unsigned long long bb = (vb_ok && sb > 0.0) ? (unsigned long long)__double_as_longlong(sb) : 0ull;
+                        ba = warp_max_u64(ba > bb ? ba : bb);
+                        if (lane == 0 && ba) atomicMax(&SE.rmax[rl], ba);
+                    } else {
+                        // ---- stage one record: placement window, class bit-masks, per-position table offsets
+                        const int rl = task - tM - tE;
+                        const int rec = gm.rec_off + cl * CH + rl;
+                        const FbRecMeta rm = p.rmeta[rec];
+                        const int L2 = rm.flags & 0xff;
+                        unsigned cls[4];
+                        fetch_classes(p.codes, p.nmask, rec, L2, lane, cls);
+                        uint4 o;
+                        o.x = min(cls[0], 4u) * (unsigned)nrs * 16u;
+                        o.y = min(cls[1], 4u) * (unsigned)nrs * 16u;
+                        o.z = min(cls[2], 4u) * (unsigned)nrs * 16u;
+                        o.w = min(cls[3], 4u) * (unsigned)nrs * 16u;
+                        reinterpret_cast<uint4*>(SL.off + rl * FB_MAX_READ)[lane] = o;
+                        const unsigned grp = 0xffu << (lane & 24);           // the 8 lanes sharing one 32-bit mask word
+#pragma unroll
+                        for (int c = 0; c < 5; c++) {
+                            unsigned nib = 0;
+#pragma unroll
+                            for (int q = 0; q < 4; q++) nib |= (cls[q] == (unsigned)c ? 1u : 0u) << q;
+                            unsigned word = __reduce_or_sync(grp, nib << (4 * (lane & 7)));
+                            if ((lane & 7) == 0) SL.mask[rl * 20 + c * 4 + (lane >> 3)] = word;
+                        }
+                        if (lane == 0) {
+                            // placements i in [gapStart-L2+1, gapStart+gp) (figbird.cpp:1826) -> u in [D-L2+1, D+gp-1]
+                            SL.rlo[rl] = max(rm.a_lo, D - L2 + 1);
+                            SL.rhi[rl] = min(rm.a_hi, D + gp - 1);
+                            SL.rtb[rl] = rm.tb;
+                            SL.rfl[rl] = rm.flags;
+                            SL.rmax[rl] = 0ull;
                         }
                     }
-                    if (rowok) s.cnt[c * gps + xg] = acc;
                 }
-                if (last && tid < nch)
-                    p.unit_maxprob[unit.mp_off + c0 + tid] = __longlong_as_double((long long)s.rmax[tid]);
+                if (tid == 0) s_queue[(round + 1) & 1] = 0;   // nobody touches the other slot during this round
                 __syncthreads();
             }
 
@@ -356,8 +446,6 @@ __global__ void __launch_bounds__(FB_FIN_THREADS) fb_finalize_kernel(const FbFin
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint8_t* gcode = smem_raw;                                     // [gmax_stride] codes of flank+best+flank window
     __shared__ uint8_t cs[FB_MAX_READ];
-    __shared__ uint8_t jl_unused[FB_MAX_READ];
-    __shared__ uint8_t clsoff_unused[8];
     __shared__ double sT[25];
     __shared__ double red_v[FB_FIN_THREADS / 32];
     __shared__ int red_u[FB_FIN_THREADS / 32];
@@ -387,7 +475,7 @@ __global__ void __launch_bounds__(FB_FIN_THREADS) fb_finalize_kernel(const FbFin
         const FbRecMeta rm = p.rmeta[rec];
         const int L2 = rm.flags & 0xff;
         const bool rev = (rm.flags >> 8) & 1, left = (rm.flags >> 9) & 1;
-        if (warp == 0) load_record(p.codes, p.nmask, rec, L2, cs, jl_unused, clsoff_unused, lane);
+        if (warp == 0) load_record_bytes(p.codes, p.nmask, rec, L2, cs, lane);
         __syncthreads();
         const int lo = max(rm.a_lo, D - L2 + 1), hi = min(rm.a_hi, D + gb - 1);
         double bv = 0.0;
