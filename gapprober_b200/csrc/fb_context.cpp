@@ -129,8 +129,8 @@ struct fb_ctx {
     int max_read_len = 0, thr_min = 0, thr_max = 0, cutoff = 0, D = 200, num_iter = 5;
     double T[25];
     std::vector<double> epos, match;
+    std::vector<double2> h_eo;   // {1 - e[k], e[k]}, copied into every EM launch's parameters
     // model (device)
-    DevBuf<double2> d_eo;
     DevBuf<double> d_ild, d_epos, d_match;
 
     // gaps + records (host staging)
@@ -247,7 +247,8 @@ int fb_create(const fb_model* m, int device, fb_ctx** out) {
     for (int i = 0; i < 5; i++)
         for (int j = 0; j < 5; j++) c->T[i * 5 + j] = m->error_type[i][j];
     const int n = std::min(m->max_read_len, FB_MAX_READ);
-    std::vector<double2> eo(FB_MAX_READ, make_double2(0, 0));
+    std::vector<double2>& eo = c->h_eo;
+    eo.assign(FB_MAX_READ, make_double2(0, 0));
     c->epos.assign(FB_MAX_READ, 0.0);
     c->match.assign(FB_MAX_READ, 0.0);
     for (int k = 0; k < n; k++) {
@@ -256,9 +257,8 @@ int fb_create(const fb_model* m, int device, fb_ctx** out) {
         c->match[k] = 1 - m->error_pos[k] - m->in_pos[k] - m->del_pos[k];           // figbird.cpp:2272
     }
     const int pwin = m->thr_max - m->thr_min + 1;
-    if (c->d_eo.ensure(FB_MAX_READ) || c->d_ild.ensure(pwin) || c->d_epos.ensure(FB_MAX_READ) || c->d_match.ensure(FB_MAX_READ))
+    if (c->d_ild.ensure(pwin) || c->d_epos.ensure(FB_MAX_READ) || c->d_match.ensure(FB_MAX_READ))
         return bail(FB_ECUDA);
-    cudaMemcpy(c->d_eo.p, eo.data(), sizeof(double2) * FB_MAX_READ, cudaMemcpyHostToDevice);
     cudaMemcpy(c->d_ild.p, m->ild + m->thr_min, sizeof(double) * pwin, cudaMemcpyHostToDevice);
     cudaMemcpy(c->d_epos.p, c->epos.data(), sizeof(double) * FB_MAX_READ, cudaMemcpyHostToDevice);
     cudaMemcpy(c->d_match.p, c->match.data(), sizeof(double) * FB_MAX_READ, cudaMemcpyHostToDevice);
@@ -270,7 +270,7 @@ int fb_create(const fb_model* m, int device, fb_ctx** out) {
 void fb_destroy(fb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    c->d_eo.release(); c->d_ild.release(); c->d_epos.release(); c->d_match.release();
+    c->d_ild.release(); c->d_epos.release(); c->d_match.release();
     c->d_gapmeta.release(); c->d_flank.release(); c->d_codes.release(); c->d_nmask.release(); c->d_rmeta.release();
     c->d_units.release(); c->d_counters.release(); c->d_maxprob.release(); c->d_gws.release(); c->d_finprob.release();
     c->d_dump.release(); c->d_cons.release(); c->d_finpos.release(); c->d_gaplist.release(); c->d_bestgp.release();
@@ -616,7 +616,7 @@ namespace {
 
 void fill_em_params(fb_ctx* c, FbEmParams& p) {
     memset(&p, 0, sizeof p);
-    p.eo = c->d_eo.p;
+    memcpy(p.eo_tab, c->h_eo.data(), sizeof p.eo_tab);
     p.ild = c->d_ild.p;
     memcpy(p.T, c->T, sizeof p.T);
     p.thr_min = c->thr_min;

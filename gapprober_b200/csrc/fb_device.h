@@ -35,7 +35,8 @@ struct FbUnit {
 
 struct FbEmParams {
     // model
-    const double2* eo;      // [max_read_len] {1 - e[k], e[k]}
+    double2 eo_tab[FB_MAX_READ];   // {1 - e[k], e[k]} per read position: lives in the kernel-parameter constant bank, so the
+                                   // E-step fetches it through the constant cache instead of shared-memory bandwidth
     const double* ild;      // insertLengthDistSmoothed[thr_min .. thr_max]
     double T[25];           // errorTypeProbs
     int thr_min, thr_max, D, num_iter, max_read_len;

@@ -79,10 +79,12 @@ struct Stage {
     unsigned long long* rmax;
     uint32_t* mask;   // [chunk][5][4] bit j of class c: base j of the record is c
     uint32_t* off;    // [chunk][128] byte offset of class(base j) inside pq
+    uint8_t* jl;      // [chunk][128] read positions sorted by (class asc, position DESC)
+    uint8_t* cum;     // [chunk][32]  cum[c*4+w] = index in jl of the first position of class c that lies in mask word <= w
+                      //              (i.e. class start + number of class-c positions in words above w); cum[20+c] = class end
 };
 
 struct EmSmem {
-    double2* eo;
     double* ild;
     double2* pq;
     double* cnt;
@@ -105,6 +107,8 @@ __device__ __forceinline__ Stage stage_at(const EmSmem& s, int k) {
     t.rfl = t.rtb + s.chunk;
     t.mask = reinterpret_cast<uint32_t*>(t.rfl + s.chunk);
     t.off = t.mask + 20 * s.chunk;
+    t.jl = reinterpret_cast<uint8_t*>(t.off + FB_MAX_READ * s.chunk);
+    t.cum = t.jl + FB_MAX_READ * s.chunk;
     return t;
 }
 
@@ -119,7 +123,6 @@ __host__ __device__ inline size_t em_carve(unsigned char* base, EmSmem* s, int n
         return p;
     };
     unsigned char* a;
-    a = take(sizeof(double2) * FB_MAX_READ); if (s) s->eo = (double2*)a;
     a = take(sizeof(double) * pwin); if (s) s->ild = (double*)a;
     if (!global_tables) {
         a = take(sizeof(double2) * (5 * (size_t)nr_stride + kPadRows)); if (s) s->pq = (double2*)a;
@@ -128,8 +131,9 @@ __host__ __device__ inline size_t em_carve(unsigned char* base, EmSmem* s, int n
     const size_t wbytes = align16(sizeof(double) * (size_t)chunk * p_stride);
     a = take(2 * wbytes);
     if (s) { s->w0 = (double*)a; s->w_stride = wbytes / sizeof(double); }
-    // one staged chunk: rmax[chunk] u64 | rlo, rhi, rtb, rfl [chunk] int | mask[chunk][20] u32 | off[chunk][128] u32
-    const size_t sbytes = align16((size_t)chunk * (8 + 4 * 4 + 20 * 4 + FB_MAX_READ * 4));
+    // one staged chunk: rmax[chunk] u64 | rlo, rhi, rtb, rfl [chunk] int | mask[chunk][20] u32 | off[chunk][128] u32 |
+    //                   jl[chunk][128] u8 | cum[chunk][32] u8
+    const size_t sbytes = align16((size_t)chunk * (8 + 4 * 4 + 20 * 4 + FB_MAX_READ * 4 + FB_MAX_READ + 32));
     a = take(3 * sbytes);
     if (s) { s->st0 = a; s->st_stride = sbytes; s->chunk = chunk; }
     return off;
@@ -173,10 +177,17 @@ __device__ __forceinline__ void load_record_bytes(const uint4* __restrict__ code
 // E-step of 64 placements of one record: lane owns placements ua and ua+32 (two independent product chains).
 // The running score is multiplied base by base in read order (figbird.cpp:1840-1864); REV selects the
 // read-position index k = L2-1-j of a reverse-complemented mate (figbird.cpp:1845-1852).
-template <bool REV>
-__device__ __forceinline__ void score_pair(const unsigned char* pa, const uint32_t* __restrict__ off, const double2* __restrict__ eo,
+// acc += w[.] for lanes whose placement offset lies inside the record's window (one predicated LDS + DADD).
+__device__ __forceinline__ void add_if_inside(double& acc, unsigned saddr, unsigned uoff, unsigned span) {
+    asm("{\n\t.reg .pred p;\n\t.reg .f64 v;\n\tsetp.le.u32 p, %2, %3;\n\t@p ld.shared.f64 v, [%1];\n\t@p add.rn.f64 %0, %0, v;\n\t}"
+        : "+d"(acc)
+        : "r"(saddr), "r"(uoff), "r"(span));
+}
+
+template <bool REV, bool TWO>
+__device__ __forceinline__ void score_pair(const unsigned char* pa, const uint32_t* __restrict__ off, const FbEmParams& p,
                                            int L2, double& sa, double& sb) {
-    const double2* ep = REV ? eo + (L2 - 1) : eo;
+    int k = REV ? L2 - 1 : 0;    // read-position index of base j (figbird.cpp:1845-1852)
     int j0 = 0;
     for (; j0 + 4 <= L2; j0 += 4) {
         const uint4 o = *reinterpret_cast<const uint4*>(off + j0);
@@ -185,28 +196,32 @@ __device__ __forceinline__ void score_pair(const unsigned char* pa, const uint32
         for (int q = 0; q < 4; q++) {
             const unsigned char* a = pa + oo[q] + q * 16;
             const double2 va = *reinterpret_cast<const double2*>(a);
-            const double2 vb = *reinterpret_cast<const double2*>(a + 32 * 16);
-            const double2 e = REV ? ep[-q] : ep[q];                         // {1 - e[k], e[k]}
+            const double2 e = p.eo_tab[REV ? k - q : k + q];                // {1 - e[k], e[k]} via the constant cache
             sa = dmul(sa, dadd(dmul(va.x, e.x), dmul(e.y, va.y)));          // figbird.cpp:1855 / 1862
-            sb = dmul(sb, dadd(dmul(vb.x, e.x), dmul(e.y, vb.y)));
+            if (TWO) {
+                const double2 vb = *reinterpret_cast<const double2*>(a + 32 * 16);
+                sb = dmul(sb, dadd(dmul(vb.x, e.x), dmul(e.y, vb.y)));
+            }
         }
         pa += 64;
-        ep += REV ? -4 : 4;
+        k += REV ? -4 : 4;
     }
     for (; j0 < L2; j0++) {
         const unsigned char* a = pa + off[j0];
         const double2 va = *reinterpret_cast<const double2*>(a);
-        const double2 vb = *reinterpret_cast<const double2*>(a + 32 * 16);
-        const double2 e = *ep;
+        const double2 e = p.eo_tab[k];
         sa = dmul(sa, dadd(dmul(va.x, e.x), dmul(e.y, va.y)));
-        sb = dmul(sb, dadd(dmul(vb.x, e.x), dmul(e.y, vb.y)));
+        if (TWO) {
+            const double2 vb = *reinterpret_cast<const double2*>(a + 32 * 16);
+            sb = dmul(sb, dadd(dmul(vb.x, e.x), dmul(e.y, vb.y)));
+        }
         pa += 16;
-        ep += REV ? -1 : 1;
+        k += REV ? -1 : 1;
     }
 }
 
 template <bool GT>
-__global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const FbEmParams p) {
+__global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __grid_constant__ FbEmParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EmSmem s;
     const int pwin = p.thr_max - p.thr_min + 1;
@@ -223,7 +238,6 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const FbE
     const int tid = threadIdx.x, lane = tid & 31;
     const int D = p.D, CH = p.chunk, PS = p.p_stride;
 
-    for (int i = tid; i < p.max_read_len && i < FB_MAX_READ; i += FB_THREADS) s.eo[i] = p.eo[i];
     for (int i = tid; i < pwin; i += FB_THREADS) s.ild[i] = p.ild[i];
     if (tid < 25) sT[tid] = p.T[tid];
     if (GT) {
@@ -298,28 +312,30 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const FbE
                         // (record asc, placement asc) order (figbird.cpp:1718, 1826, 1874): walking a record's class
                         // mask from high j to low j visits its placements in ascending order.
                         const int c = task / nrg, rg = task - c * nrg;
-                        const int xg = rg * 32 + lane, x0 = D + rg * 32, x = x0 + lane;
+                        const int xg = rg * 32 + lane, x0 = D + rg * 32;
                         const bool rowok = xg < gp;
+                        const int x = rowok ? x0 + lane : -(1 << 28);      // rows past the gap never fall inside a window
                         double acc = rowok ? s.cnt[c * gps + xg] : 0.0;
+                        const unsigned wM_s = (unsigned)__cvta_generic_to_shared(wM);
                         for (int rl = 0; rl < n_m; rl++) {
                             const int lo = SM.rlo[rl], hi = SM.rhi[rl];
                             const int L2 = SM.rfl[rl] & 0xff;
                             const int jhi = min(L2 - 1, x0 + 31 - lo), jlo = max(0, x0 - hi);   // j with any lane inside [lo, hi]
                             if (hi < lo || jhi < jlo) continue;
+                            // exact sub-range of the class list: skip positions above jhi and below jlo
                             const uint32_t* mk = SM.mask + rl * 20 + c * 4;
-                            const double* wr = wM + rl * PS - lo;
+                            const uint8_t* cum = SM.cum + rl * 32;
+                            const int wh = jhi >> 5, wl = jlo >> 5;
+                            const int qs = cum[c * 4 + wh] + __popc((mk[wh] >> (jhi & 31)) >> 1);
+                            const int qe = (wl == 0 ? cum[20 + c] : cum[c * 4 + wl - 1]) - __popc(mk[wl] & ((1u << (jlo & 31)) - 1u));
+                            const uint8_t* jl = SM.jl + rl * FB_MAX_READ;
+                            const unsigned wbase = wM_s + (unsigned)(rl * PS) * 8u;
                             const unsigned span = (unsigned)(hi - lo);
-                            for (int wd = jhi >> 5; wd >= (jlo >> 5); wd--) {
-                                uint32_t m = mk[wd];
-                                if (wd == (jhi >> 5)) m &= 0xffffffffu >> (31 - (jhi & 31));
-                                if (wd == (jlo >> 5)) m &= 0xffffffffu << (jlo & 31);
-                                const int xw = x - wd * 32;
-                                while (m) {
-                                    const int b = 31 - __clz(m);
-                                    m ^= 1u << b;
-                                    const int u = xw - b;
-                                    if (rowok && (unsigned)(u - lo) <= span) acc = dadd(acc, wr[u]);   // figbird.cpp:1879
-                                }
+                            const int xlo = x - lo;
+#pragma unroll 4
+                            for (int q = qs; q < qe; q++) {
+                                const unsigned uoff = (unsigned)(xlo - (int)jl[q]);
+                                add_if_inside(acc, wbase + uoff * 8u, uoff, span);   // figbird.cpp:1879
                             }
                         }
                         if (rowok) s.cnt[c * gps + xg] = acc;
@@ -339,8 +355,14 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const FbE
                         double sa = s.ild[ta - p.thr_min], sb = s.ild[tbb - p.thr_min];
                         const unsigned char* pa = reinterpret_cast<const unsigned char*>(s.pq + (uc - R0));
                         const uint32_t* off = SE.off + rl * FB_MAX_READ;
-                        if (rev) score_pair<true>(pa, off, s.eo, L2, sa, sb);
-                        else score_pair<false>(pa, off, s.eo, L2, sa, sb);
+                        const bool two = lo + 64 * blk + 32 <= hi;           // any lane with a second placement?
+                        if (two) {
+                            if (rev) score_pair<true, true>(pa, off, p, L2, sa, sb);
+                            else score_pair<false, true>(pa, off, p, L2, sa, sb);
+                        } else {
+                            if (rev) score_pair<true, false>(pa, off, p, L2, sa, sb);
+                            else score_pair<false, false>(pa, off, p, L2, sa, sb);
+                        }
                         double* wrow = wE + rl * PS - lo;
                         if (va_ok) wrow[ua] = sa;
                         if (vb_ok) wrow[ub] = sb;
@@ -371,6 +393,35 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const FbE
                             for (int q = 0; q < 4; q++) nib |= (cls[q] == (unsigned)c ? 1u : 0u) << q;
                             unsigned word = __reduce_or_sync(grp, nib << (4 * (lane & 7)));
                             if ((lane & 7) == 0) SL.mask[rl * 20 + c * 4 + (lane >> 3)] = word;
+                        }
+                        __syncwarp();
+                        {
+                            // class-sorted, position-descending list: slot = class start + (positions of that class above j)
+                            const uint32_t* mk = SL.mask + rl * 20;
+                            uint8_t* cum = SL.cum + rl * 32;
+                            uint8_t* jl = SL.jl + rl * FB_MAX_READ;
+                            int start = 0;
+#pragma unroll
+                            for (int c = 0; c < 5; c++) {
+                                const int n3 = __popc(mk[c * 4 + 3]), n2 = __popc(mk[c * 4 + 2]), n1 = __popc(mk[c * 4 + 1]), n0 = __popc(mk[c * 4]);
+                                const int above[4] = {n3 + n2 + n1, n3 + n2, n3, 0};   // positions in words above w
+                                if (lane == 0) {
+                                    cum[c * 4 + 0] = (uint8_t)(start + above[0]);
+                                    cum[c * 4 + 1] = (uint8_t)(start + above[1]);
+                                    cum[c * 4 + 2] = (uint8_t)(start + above[2]);
+                                    cum[c * 4 + 3] = (uint8_t)(start + above[3]);
+                                    cum[20 + c] = (uint8_t)(start + n3 + n2 + n1 + n0);
+                                }
+#pragma unroll
+                                for (int q = 0; q < 4; q++) {
+                                    if (cls[q] == (unsigned)c) {
+                                        const int j = lane * 4 + q, w = j >> 5;
+                                        const int higher = __popc((mk[c * 4 + w] >> (j & 31)) >> 1);
+                                        jl[start + (w == 3 ? 0 : w == 2 ? n3 : w == 1 ? n3 + n2 : n3 + n2 + n1) + higher] = (uint8_t)j;
+                                    }
+                                }
+                                start += n3 + n2 + n1 + n0;
+                            }
                         }
                         if (lane == 0) {
                             // placements i in [gapStart-L2+1, gapStart+gp) (figbird.cpp:1826) -> u in [D-L2+1, D+gp-1]
