@@ -426,25 +426,42 @@ void gap_cost(fb_ctx* c, HostGap& g) {
 
 extern "C" {
 
+int fb_partition_plan(const double* cost, int n, int world, int* owner) {
+    if (n < 0 || world < 1 || (n > 0 && (!cost || !owner))) return FB_EINVAL;
+    // longest-processing-time first: items by descending cost, each to the least loaded rank
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+    std::vector<double> load(world, 0.0);
+    for (int i : order) {
+        int best = 0;
+        for (int r = 1; r < world; r++)
+            if (load[r] < load[best]) best = r;
+        load[best] += cost[i];
+        owner[i] = best;
+    }
+    return FB_OK;
+}
+
+double fb_gap_cost(fb_ctx* c, int gap) {
+    if (!c || gap < 0 || gap >= (int)c->gaps.size()) return -1.0;
+    gap_cost(c, c->gaps[gap]);
+    return c->gaps[gap].cost;
+}
+
 int fb_set_partition(fb_ctx* c, int rank, int world) {
     if (!c || world < 1 || rank < 0 || rank >= world) return FB_EINVAL;
     c->part_rank = rank;
     c->part_world = world;
-    // longest-processing-time first: gaps by descending cost, each to the least loaded rank
-    std::vector<int> order(c->gaps.size());
-    for (size_t i = 0; i < order.size(); i++) {
-        order[i] = (int)i;
+    const int n = (int)c->gaps.size();
+    std::vector<double> cost(n);
+    std::vector<int> owner(n);
+    for (int i = 0; i < n; i++) {
         gap_cost(c, c->gaps[i]);
+        cost[i] = c->gaps[i].cost;
     }
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return c->gaps[a].cost > c->gaps[b].cost; });
-    std::vector<double> load(world, 0.0);
-    for (int gi : order) {
-        int best = 0;
-        for (int r = 1; r < world; r++)
-            if (load[r] < load[best]) best = r;
-        load[best] += c->gaps[gi].cost;
-        c->gaps[gi].owned = best == rank;
-    }
+    fb_partition_plan(cost.data(), n, world, owner.data());
+    for (int i = 0; i < n; i++) c->gaps[i].owned = owner[i] == rank;
     c->uploaded = c->ran = false;
     return FB_OK;
 }

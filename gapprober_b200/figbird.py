@@ -76,7 +76,7 @@ class FbStats(C.Structure):
 
 # Every symbol include/figbird_cuda.h declares; tests check the library exports all of them.
 ABI_SYMBOLS = [
-    "fb_create", "fb_destroy", "fb_add_gap", "fb_add_gap_file", "fb_set_partition", "fb_owns_gap", "fb_run", "fb_upload",
+    "fb_create", "fb_destroy", "fb_add_gap", "fb_add_gap_file", "fb_set_partition", "fb_owns_gap", "fb_partition_plan", "fb_gap_cost", "fb_run", "fb_upload",
     "fb_run_device", "fb_result", "fb_estimate_liks", "fb_best_string", "fb_dump_profile", "fb_get_stats",
     "fb_clear_gaps", "fb_gap_range", "fb_last_error", "fb_status_str", "fb_abi_version",
 ]
@@ -100,6 +100,9 @@ def load_library():
     L.fb_add_gap_file.argtypes = [vp, C.c_int, C.c_long, C.c_int, C.c_char_p, C.c_long, C.c_char_p]
     L.fb_set_partition.argtypes = [vp, C.c_int, C.c_int]
     L.fb_owns_gap.argtypes = [vp, C.c_int]
+    L.fb_partition_plan.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int, C.POINTER(C.c_int)]
+    L.fb_gap_cost.argtypes = [vp, C.c_int]
+    L.fb_gap_cost.restype = C.c_double
     L.fb_run.argtypes = [vp]
     L.fb_upload.argtypes = [vp]
     L.fb_run_device.argtypes = [vp]
@@ -118,6 +121,17 @@ def load_library():
     L.fb_abi_version.restype = C.c_int
     _lib = L
     return L
+
+
+def partition_plan(costs, world):
+    """Owner rank of every work item: descending cost, each to the least loaded rank (the rule fb_set_partition uses)."""
+    cost = np.ascontiguousarray(costs, dtype=np.float64)
+    owner = np.zeros(cost.size, dtype=np.int32)
+    rc = load_library().fb_partition_plan(cost.ctypes.data_as(C.POINTER(C.c_double)), cost.size, int(world),
+                                          owner.ctypes.data_as(C.POINTER(C.c_int)))
+    if rc != FB_OK:
+        raise FigbirdError(rc, "fb_partition_plan")
+    return owner
 
 
 def gap_range(original_gap):

@@ -107,6 +107,11 @@ int fb_add_gap_file(fb_ctx* ctx, int contig_no, long gap_start, int orig_gap, co
 int fb_set_partition(fb_ctx* ctx, int rank, int world);
 /* 1 if gap `gap` is run by this context under the current partition. */
 int fb_owns_gap(fb_ctx* ctx, int gap);
+/* The dealing rule itself, as pure host code (no GPU needed): items by descending cost, each to the least loaded
+ * rank, ties to the lower rank; owner[i] receives the rank of item i.  fb_set_partition applies it to fb_gap_cost. */
+int fb_partition_plan(const double* cost, int n, int world, int* owner);
+/* Work estimate of a registered gap: over its estimates, in-window placements x mate length (+ a constant per estimate). */
+double fb_gap_cost(fb_ctx* ctx, int gap);
 
 /* GapFiller::fillGap for every registered gap (figbird.cpp:2436-2510): estimate scan, num_iter EM
  * iterations per estimate, best-estimate selection, finalize.  fb_run = fb_upload + fb_run_device. */

@@ -1,0 +1,30 @@
+"""The drop-in binary (gapprober_b200/bin/figbird.out: host preamble + GPU hot path) against the reference binary
+(oracle/_ref/figbird.out) in the same generated working directory: same files, same stdout."""
+import filecmp
+import os
+import shutil
+import subprocess
+
+import pytest
+
+import refrun
+
+pytestmark = pytest.mark.gpu
+
+ARGS = ["--genome", "150000", "--scaffolds", "3", "--gap-list", "60,120,250,90,400,33", "--cov", "40", "--ins-mean", "180", "--ins-sd", "20", "--err", "0.01"]
+
+
+def test_dropin_outputs_equal_reference(built, tmp_path):
+    if not refrun.have_ref():
+        pytest.skip("oracle/_ref binaries not built")
+    from gapprober_b200 import build, synth
+    a, b = str(tmp_path / "ours"), str(tmp_path / "ref")
+    synth.generate(a, ARGS, seed=31)
+    shutil.copytree(a, b)
+    ours = subprocess.run([build.build_host(), "scaffolds.fa", " 0", "250"], cwd=a, stdout=subprocess.PIPE, text=True)
+    assert ours.returncode == 0, ours.stdout
+    ref = subprocess.run([refrun.REF_FIGBIRD, "scaffolds.fa", " 0", "250"], cwd=b, stdout=subprocess.PIPE, text=True, check=True)
+    for f in ("gapout.txt", "filledContigs.fa", "mappedInserts.txt"):
+        assert filecmp.cmp(os.path.join(a, f), os.path.join(b, f), shallow=False), f
+    strip = lambda s: [ln for ln in s.splitlines() if not ln.startswith("Total time to fill gaps")]
+    assert strip(ours.stdout) == strip(ref.stdout)

@@ -1,0 +1,127 @@
+"""Edge cases of the hot path on the GPU, each checked against the oracle (C restatement) on the same inputs:
+empty and ragged inputs, the longest gaps (global-memory table variant), heavy multi-hit duplication, partition
+invariance, idempotence, and the error contract."""
+import os
+
+import numpy as np
+import pytest
+
+import golden_lib as G
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_against_oracle(fb, gf, omodel, window, D, orig, recs):
+    r = gf.result()
+    orc = O.fill_gap(omodel, window, D, orig, recs)
+    assert np.array_equal(gf.estimateLikelihoods(), orc["liks"])
+    assert r["best_estimate"] == orc["best_estimate"]
+    assert r["filled"] == orc["filled"]
+    assert (r["total_reads"], r["discarded"]) == (orc["total_reads"], orc["discarded"])
+    return r, orc
+
+
+def test_gap_without_records(built):
+    from gapprober_b200 import FigbirdContext
+    case = G.Case("lib180_100bp_60x")
+    g = case.gaps[0]
+    with FigbirdContext(case.figbird_model()) as fb:
+        gf = fb.GapFiller().initGapFiller(0, case.D, g["orig"], [], g["window"])
+        fb.fillGaps()
+        r, orc = _check_against_oracle(fb, gf, case.oracle_model(), g["window"], case.D, g["orig"], [])
+        assert r["best_estimate"] == r["gap_max"] and set(r["filled"]) == {ord("N")}   # all-zero likelihood ties: last estimate wins
+
+
+def test_ragged_read_lengths_and_lower_case(built):
+    from gapprober_b200 import FigbirdContext
+    case = G.Case("multi_gap_err1pct")
+    rng = np.random.default_rng(11)
+    with FigbirdContext(case.figbird_model()) as fb:
+        todo = []
+        for g in case.gaps[:3]:
+            recs = []
+            for p, l1, s1, seq in g["recs"]:
+                n = int(rng.integers(25, len(seq) + 1))
+                q = seq[:n] if rng.random() < 0.5 else seq[len(seq) - n:]
+                if rng.random() < 0.2:
+                    q = q.lower()          # reverse() accepts lower case, charCodes does not (figbird.cpp:1390, 2753)
+                recs.append((p, l1, s1, q))
+            todo.append((fb.GapFiller().initGapFiller(0, case.D, g["orig"], recs, g["window"]), g, recs))
+        fb.fillGaps()
+        for gf, g, recs in todo:
+            _check_against_oracle(fb, gf, case.oracle_model(), g["window"], case.D, g["orig"], recs)
+
+
+def test_long_gap_uses_global_tables(built, tmp_path):
+    """A 3000 bp gap scans estimates 2850..3150: the profile no longer fits shared memory and the kernel variant that
+    keeps it in global memory runs.  Same answers as the oracle."""
+    from gapprober_b200 import FigbirdContext, FigbirdModel, build, synth
+    wd = str(tmp_path / "long")
+    synth.generate(wd, ["--genome", "60000", "--gap-list", "3000", "--cov", "10", "--ins-mean", "180", "--ins-sd", "20", "--err", "0.01"], seed=13)
+    model = FigbirdModel.load(build.learn_model(wd))
+    omodel = O.Model.load(os.path.join(wd, "fb_model.bin"))
+    _, seqs = O.read_fasta(os.path.join(wd, "scaffolds.fa"))
+    c, s, l = O.read_gap_info(os.path.join(wd, "gapInfo.txt"))[0]
+    recs = O.read_gap_file(os.path.join(wd, "Gaps", "gaps_0.sam"))
+    with FigbirdContext(model) as fb:
+        gf = fb.GapFiller().initGapFiller(c, s, l, os.path.join(wd, "Gaps", "gaps_0.sam"), seqs[c])
+        fb.fillGaps()
+        r, orc = _check_against_oracle(fb, gf, omodel, seqs[c], s, l, recs)
+        assert r["gap_max"] == 3150
+        probs, counts = gf.dumpProfile(r["best_estimate"])
+        o2 = O.fill_gap(omodel, seqs[c], s, l, recs, dump_estimate=r["best_estimate"])
+        assert np.array_equal(probs, o2["probs"], equal_nan=True) and np.array_equal(counts, o2["counts"], equal_nan=True)
+
+
+def test_multihit_duplicates_many_chunks(built, tmp_path):
+    """bowtie2 -k style duplication: 10 copies of every record, several hundred records in one gap."""
+    from gapprober_b200 import FigbirdContext, FigbirdModel, build, synth
+    wd = str(tmp_path / "k10")
+    synth.generate(wd, ["--genome", "60000", "--gap-list", "100", "--cov", "30", "--ins-mean", "180", "--ins-sd", "20", "--err", "0.01", "--multihit", "10"], seed=17)
+    model = FigbirdModel.load(build.learn_model(wd))
+    omodel = O.Model.load(os.path.join(wd, "fb_model.bin"))
+    _, seqs = O.read_fasta(os.path.join(wd, "scaffolds.fa"))
+    c, s, l = O.read_gap_info(os.path.join(wd, "gapInfo.txt"))[0]
+    recs = O.read_gap_file(os.path.join(wd, "Gaps", "gaps_0.sam"))
+    assert len(recs) > 150
+    with FigbirdContext(model) as fb:
+        gf = fb.GapFiller().initGapFiller(c, s, l, recs, seqs[c])
+        fb.fillGaps()
+        _check_against_oracle(fb, gf, omodel, seqs[c], s, l, recs)
+
+
+def test_partition_invariance_and_idempotence(built):
+    from gapprober_b200 import FigbirdContext
+    case = G.Case("multi_gap_err1pct")
+    with FigbirdContext(case.figbird_model()) as fb:
+        gfs = [fb.GapFiller().initGapFiller(0, case.D, g["orig"], g["recs"], g["window"]) for g in case.gaps]
+        fb.fillGaps()
+        full = [(gf.result()["filled"], gf.estimateLikelihoods().tobytes()) for gf in gfs]
+        fb.runDevice()                                  # same inputs, second pass: identical
+        assert full == [(gf.result()["filled"], gf.estimateLikelihoods().tobytes()) for gf in gfs]
+        seen = {}
+        for rank in range(3):
+            fb.setPartition(rank, 3)
+            fb.fillGaps()
+            for i, gf in enumerate(gfs):
+                if fb.ownsGap(i):
+                    assert i not in seen
+                    seen[i] = (gf.result()["filled"], gf.estimateLikelihoods().tobytes())
+        assert [seen[i] for i in range(len(gfs))] == full
+
+
+def test_error_contract(built):
+    from gapprober_b200 import FigbirdContext, FigbirdError
+    case = G.Case("lib180_100bp_60x")
+    g = case.gaps[0]
+    with FigbirdContext(case.figbird_model()) as fb:
+        with pytest.raises(FigbirdError) as e:      # gap closer than max_distance to the scaffold start: reference reads out of bounds
+            fb.GapFiller().initGapFiller(0, case.D - 1, g["orig"], g["recs"], g["window"][1:])
+        assert e.value.status == -2
+        gf = fb.GapFiller().initGapFiller(0, case.D, g["orig"], g["recs"], g["window"])
+        with pytest.raises(FigbirdError) as e:      # result before run
+            gf.result()
+        assert e.value.status == -5
+        fb.fillGaps()
+        assert gf.result()["filled"] == g["filled"]
