@@ -68,7 +68,7 @@ def test_long_gap_uses_global_tables(built, tmp_path):
         gf = fb.GapFiller().initGapFiller(c, s, l, os.path.join(wd, "Gaps", "gaps_0.sam"), seqs[c])
         fb.fillGaps()
         r, orc = _check_against_oracle(fb, gf, omodel, seqs[c], s, l, recs)
-        assert r["gap_max"] == 3150
+        assert r["gap_max"] == O.gap_range(3000)[1] == 3149      # 3000*1.05f truncates (float arithmetic, figbird.cpp:2453)
         probs, counts = gf.dumpProfile(r["best_estimate"])
         o2 = O.fill_gap(omodel, seqs[c], s, l, recs, dump_estimate=r["best_estimate"])
         assert np.array_equal(probs, o2["probs"], equal_nan=True) and np.array_equal(counts, o2["counts"], equal_nan=True)
