@@ -19,10 +19,23 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <string>
 #include <vector>
 
 namespace {
+
+// FB_TRACE=1: phase wall times on stderr
+struct Trace {
+    bool on = getenv("FB_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char* what) {
+        if (!on) return;
+        auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "[fb_trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
 
 inline int base_code(char ch) {   // charCodes, figbird.cpp:2753-2776
     switch (ch) {
@@ -120,7 +133,8 @@ struct Bin {
 
 struct fb_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    std::vector<cudaEvent_t> bin_done, bin_copied;   // per EM launch: kernel finished / its results are on the host
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, evs = nullptr, eve = nullptr;
     int max_smem = 0, sm_count = 0;
     std::string err;
@@ -232,6 +246,7 @@ int fb_create(const fb_model* m, int device, fb_ctx** out) {
     if (cudaSetDevice(device) != cudaSuccess) return bail(FB_ECUDA);
     if (fb_kernels_init(&c->max_smem, &c->sm_count) != cudaSuccess) return bail(FB_ECUDA);
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FB_ECUDA);
+    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(FB_ECUDA);
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
     cudaEventCreate(&c->ev2);
@@ -282,6 +297,9 @@ void fb_destroy(fb_ctx* c) {
     if (c->ev3) cudaEventDestroy(c->ev3);
     if (c->evs) cudaEventDestroy(c->evs);
     if (c->eve) cudaEventDestroy(c->eve);
+    for (cudaEvent_t e : c->bin_done) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->bin_copied) cudaEventDestroy(e);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -475,6 +493,7 @@ int fb_upload(fb_ctx* c) {
     if (!c) return FB_EINVAL;
     FB_CUDA(c, cudaSetDevice(c->device));
     const int D = c->D, pwin = c->thr_max - c->thr_min + 1;
+    Trace tr;
     // ---- units: every (owned gap, estimate); heaviest first so persistent CTAs balance (LPT)
     struct U { int gap, gp; double cost; long liks; };
     std::vector<U> us;
@@ -581,6 +600,14 @@ int fb_upload(fb_ctx* c) {
         b.grid = std::min(b.n_units, c->sm_count * ctas);
         if (b.global_tables) gws_need = std::max(gws_need, (size_t)b.grid * gws_stride_of(b.nr_stride, b.gp_stride));
     }
+    tr.lap("upload: units + bins");
+    while (c->bin_done.size() < c->bins.size()) {
+        cudaEvent_t a, b;
+        FB_CUDA(c, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        FB_CUDA(c, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        c->bin_done.push_back(a);
+        c->bin_copied.push_back(b);
+    }
     // ---- device buffers + host->device copies
     const size_t ng = c->h_gapmeta.size(), nr = c->h_rmeta.size();
     FB_CUDA(c, c->d_gapmeta.ensure(ng));
@@ -621,6 +648,7 @@ int fb_upload(fb_ctx* c) {
     FB_CUDA(c, up(c->d_rmeta.p, c->h_rmeta.data(), nr * sizeof(FbRecMeta)));
     FB_CUDA(c, up(c->d_units.p, c->h_units.data(), c->h_units.size() * sizeof(FbUnit)));
     FB_CUDA(c, cudaStreamSynchronize(c->stream));
+    tr.lap("upload: alloc + H2D");
     st.h2d_bytes = h2d;
     c->uploaded = true;
     c->ran = false;
@@ -663,6 +691,7 @@ int fb_run_device(fb_ctx* c) {
     fb_stats& st = c->stats;
     const int D = c->D;
     long d2h = 0;
+    Trace tr;
     st.em_launches = st.finalize_launches = 0;
     st.finalize_likelihoods = 0;
 
@@ -684,17 +713,23 @@ int fb_run_device(fb_ctx* c) {
         p.gws_stride = gws_stride_of(b.nr_stride, b.gp_stride);
         FB_CUDA(c, fb_launch_em(p, b.grid, b.global_tables, b.smem, c->stream));
         st.em_launches++;
+        // this bin's slice of unit_maxprob goes home on the copy stream while the next bin computes
+        FB_CUDA(c, cudaEventRecord(c->bin_done[bi], c->stream));
+        FB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->bin_done[bi], 0));
+        const FbUnit& u0 = c->h_units[b.first_unit];
+        const FbUnit& u1 = c->h_units[b.first_unit + b.n_units - 1];
+        const size_t lo = (size_t)u0.mp_off, hi = (size_t)u1.mp_off + c->unit_nrec[b.first_unit + b.n_units - 1];
+        if (hi > lo) {
+            FB_CUDA(c, cudaMemcpyAsync(c->h_maxprob.p + lo, c->d_maxprob.p + lo, (hi - lo) * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+            d2h += (long)((hi - lo) * sizeof(double));
+        }
+        FB_CUDA(c, cudaEventRecord(c->bin_copied[bi], c->copy_stream));
     }
     FB_CUDA(c, cudaEventRecord(c->ev1, c->stream));
-    size_t mp_total = 0;
-    if (!c->h_units.empty()) mp_total = (size_t)c->h_units.back().mp_off + c->unit_nrec.back();
-    if (mp_total) {
-        FB_CUDA(c, cudaMemcpyAsync(c->h_maxprob.p, c->d_maxprob.p, mp_total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        d2h += (long)(mp_total * sizeof(double));
-    }
-    FB_CUDA(c, cudaStreamSynchronize(c->stream));
+    tr.lap("run: launches enqueued");
 
-    // ---- likelihood per unit (figbird.cpp:1951-1955) and best estimate per gap (figbird.cpp:2479-2490)
+    // ---- likelihood per unit (figbird.cpp:1951-1955): the per-record maxima of a bin are copied back on a second
+    // stream as soon as that bin's launch has finished, and the host sums glibc log() over them while later bins run.
     for (HostGap& g : c->gaps) {
         if (!g.owned) continue;
         g.liks.assign(g.gmax - g.gmin + 1, 0.0);
@@ -703,16 +738,23 @@ int fb_run_device(fb_ctx* c) {
     std::vector<std::vector<long long>> cons_off(c->gaps.size());
     for (size_t gi = 0; gi < c->gaps.size(); gi++)
         if (c->gaps[gi].owned) cons_off[gi].assign(c->gaps[gi].gmax - c->gaps[gi].gmin + 1, 0);
-    for (size_t ui = 0; ui < c->h_units.size(); ui++) {
-        const FbUnit& u = c->h_units[ui];
-        HostGap& g = c->gaps[u.gap];
-        const double* mp = c->h_maxprob.p + u.mp_off;
-        double lik = 0;
-        for (int r = 0; r < g.nrec; r++)
-            if (mp[r] > 0) lik += log(mp[r]);
-        g.liks[u.gp - g.gmin] = lik;
-        cons_off[u.gap][u.gp - g.gmin] = u.cons_off;
+    for (size_t bi = 0; bi < c->bins.size(); bi++) {
+        const Bin& b = c->bins[bi];
+        FB_CUDA(c, cudaEventSynchronize(c->bin_copied[bi]));
+        for (int k = 0; k < b.n_units; k++) {
+            const FbUnit& u = c->h_units[b.first_unit + k];
+            HostGap& g = c->gaps[u.gap];
+            const double* mp = c->h_maxprob.p + u.mp_off;
+            double lik = 0;
+            for (int r = 0; r < g.nrec; r++)
+                if (mp[r] > 0) lik += log(mp[r]);
+            g.liks[u.gp - g.gmin] = lik;
+            cons_off[u.gap][u.gp - g.gmin] = u.cons_off;
+        }
     }
+    FB_CUDA(c, cudaStreamSynchronize(c->stream));
+    tr.lap("run: EM + host log sums");
+    // best estimate per gap (figbird.cpp:2479-2490)
     std::vector<int> gaplist, bestgp(c->gaps.size(), 0);
     for (size_t gi = 0; gi < c->gaps.size(); gi++) {
         HostGap& g = c->gaps[gi];
@@ -773,6 +815,7 @@ int fb_run_device(fb_ctx* c) {
         FB_CUDA(c, cudaStreamSynchronize(c->stream));
     }
 
+    tr.lap("run: select + finalize kernel");
     // ---- finalize on the host: cut-off, +1 counts, computeSequence(1), getConcensus
     std::vector<int> cnt;
     for (int gi : gaplist) {
@@ -808,6 +851,7 @@ int fb_run_device(fb_ctx* c) {
         }
         g.done = true;
     }
+    tr.lap("run: host finalize");
     FB_CUDA(c, cudaEventRecord(c->eve, c->stream));
     FB_CUDA(c, cudaEventSynchronize(c->eve));
     float ms = 0;
