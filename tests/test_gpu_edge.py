@@ -91,6 +91,24 @@ def test_multihit_duplicates_many_chunks(built, tmp_path):
         _check_against_oracle(fb, gf, omodel, seqs[c], s, l, recs)
 
 
+def test_long_reads_125bp(built, tmp_path):
+    """Mates of 125 bp (beyond the reference's 100-byte scratch buffer, figbird.cpp:1698; within the packed layout's 128)."""
+    from gapprober_b200 import FigbirdContext, FigbirdModel, build, synth
+    wd = str(tmp_path / "l125")
+    synth.generate(wd, ["--genome", "60000", "--gap-list", "150,40", "--cov", "40", "--read-len", "125", "--ins-mean", "300", "--ins-sd", "25",
+                        "--err", "0.01"], seed=19)
+    model = FigbirdModel.load(build.learn_model(wd))
+    assert model.max_read_len == 125
+    omodel = O.Model.load(os.path.join(wd, "fb_model.bin"))
+    _, seqs = O.read_fasta(os.path.join(wd, "scaffolds.fa"))
+    with FigbirdContext(model) as fb:
+        gfs = fb.add_workdir(wd)
+        fb.fillGaps()
+        for gi, (c, s, l) in enumerate(O.read_gap_info(os.path.join(wd, "gapInfo.txt"))):
+            recs = O.read_gap_file(os.path.join(wd, "Gaps", f"gaps_{gi}.sam"))
+            _check_against_oracle(fb, gfs[gi], omodel, seqs[c], s, l, recs)
+
+
 def test_partition_invariance_and_idempotence(built):
     from gapprober_b200 import FigbirdContext
     case = G.Case("multi_gap_err1pct")
