@@ -1,0 +1,50 @@
+"""Seeded randomised parity: libraries, error rates, coverage, gap sizes, duplication and N rates drawn at random;
+every case is run through the REFERENCE binary (oracle/_ref/figbird_dump.out) and through the CUDA path on the GPU,
+and the per-estimate likelihoods, the winning estimate and the filled sequences must be identical."""
+import os
+
+import numpy as np
+import pytest
+
+import refrun
+
+pytestmark = pytest.mark.gpu
+
+
+def _draw(seed):
+    r = np.random.default_rng(1000 + seed)
+    mean = int(r.integers(150, 520))
+    sd = int(r.integers(8, max(9, mean // 9)))
+    ngaps = int(r.integers(2, 6))
+    kinds = r.integers(0, 4, size=ngaps)
+    gaps = [int(r.integers(1, 30)) if k == 0 else int(r.integers(30, 200)) if k == 1 else int(r.integers(200, 420)) if k == 2
+            else int(r.integers(420, 760)) for k in kinds]
+    args = ["--genome", str(int(r.integers(60, 140)) * 1000), "--scaffolds", str(int(r.integers(1, 3))),
+            "--gap-list", ",".join(map(str, gaps)), "--cov", str(int(r.integers(8, 90))), "--ins-mean", str(mean), "--ins-sd", str(sd),
+            "--read-len", str(int(r.choice([36, 50, 76, 99, 100]))), "--err", f"{float(r.choice([0, 0.002, 0.01, 0.03])):g}",
+            "--nrate", f"{float(r.choice([0, 0, 0.005])):g}", "--multihit", str(int(r.choice([1, 1, 1, 2, 4]))),
+            "--len-noise", str(int(r.choice([0, 0, 5, 25])))]
+    return args
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_case_matches_reference(seed, built, tmp_path):
+    if not refrun.have_ref():
+        pytest.skip("oracle/_ref binaries not built")
+    from gapprober_b200 import FigbirdContext, FigbirdModel, build, synth
+    wd = str(tmp_path / f"fuzz{seed}")
+    args = _draw(seed)
+    synth.generate(wd, args, seed=500 + seed)
+    ref = refrun.run_reference(wd, dump_probs=False)
+    model = FigbirdModel.load(build.learn_model(wd, out="mine.bin"))           # host preamble ...
+    assert open(os.path.join(wd, "mine.bin"), "rb").read() == open(os.path.join(wd, "fb_model.bin"), "rb").read(), args   # ... equals the reference's model
+    with FigbirdContext(model) as fb:
+        gfs = fb.add_workdir(wd)
+        fb.fillGaps()
+        for gi, gf in enumerate(gfs):
+            d = ref["dump"][f"Gaps/gaps_{gi}.sam"]
+            r = gf.result()
+            want = np.array([d["est"][e] for e in range(r["gap_min"], r["gap_max"] + 1)])
+            assert np.array_equal(gf.estimateLikelihoods(), want), (args, gi)
+            assert r["best_estimate"] == d["best"][0] and gf.bestString().decode() == d["best"][2], (args, gi)
+            assert r["filled"].decode() == ref["gapout"][gi]["filled"], (args, gi)
