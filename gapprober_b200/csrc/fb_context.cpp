@@ -127,6 +127,7 @@ struct Bin {
     bool global_tables;
     size_t smem;
     int grid;
+    size_t gws_off;   // doubles: this bin's slice of the global workspace (bins run concurrently)
 };
 
 }  // namespace
@@ -134,6 +135,7 @@ struct Bin {
 struct fb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
+    std::vector<cudaStream_t> bin_streams;            // one per EM launch (size bin)
     std::vector<cudaEvent_t> bin_done, bin_copied;   // per EM launch: kernel finished / its results are on the host
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, evs = nullptr, eve = nullptr;
     int max_smem = 0, sm_count = 0;
@@ -178,6 +180,7 @@ struct fb_ctx {
     PinBuf<unsigned char> h_stage;   // pinned staging for the host->device copies
 
     fb_stats stats;
+    double t_parse_ms = 0, t_pack_ms = 0;   // FB_TRACE: time spent in fb_add_gap_file since the last upload
 
     int fail(int code, const char* fmt, ...) {
         char buf[512];
@@ -297,6 +300,7 @@ void fb_destroy(fb_ctx* c) {
     if (c->ev3) cudaEventDestroy(c->ev3);
     if (c->evs) cudaEventDestroy(c->evs);
     if (c->eve) cudaEventDestroy(c->eve);
+    for (cudaStream_t t : c->bin_streams) cudaStreamDestroy(t);
     for (cudaEvent_t e : c->bin_done) cudaEventDestroy(e);
     for (cudaEvent_t e : c->bin_copied) cudaEventDestroy(e);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -389,6 +393,7 @@ int fb_add_gap(fb_ctx* c, int contig_no, long gap_start, int orig_gap, const cha
 
 int fb_add_gap_file(fb_ctx* c, int contig_no, long gap_start, int orig_gap, const char* contig, long contig_len, const char* gap_file) {
     if (!c || !gap_file) return FB_EINVAL;
+    const auto t_begin = std::chrono::steady_clock::now();
     FILE* fp = fopen(gap_file, "r");
     if (!fp) return c->fail(FB_EINVAL, "cannot open %s", gap_file);
     // placeReads' parse, figbird.cpp:1718-1801
@@ -416,7 +421,11 @@ int fb_add_gap_file(fb_ctx* c, int contig_no, long gap_start, int orig_gap, cons
     }
     fclose(fp);
     for (size_t i = 0; i < recs.size(); i++) recs[i].seq2 = seqs[i].c_str();
-    return fb_add_gap(c, contig_no, gap_start, orig_gap, contig, contig_len, recs.data(), (int)recs.size());
+    const auto t_parsed = std::chrono::steady_clock::now();
+    const int rc = fb_add_gap(c, contig_no, gap_start, orig_gap, contig, contig_len, recs.data(), (int)recs.size());
+    c->t_parse_ms += std::chrono::duration<double, std::milli>(t_parsed - t_begin).count();
+    c->t_pack_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_parsed).count();
+    return rc;
 }
 
 }  // extern "C"
@@ -494,6 +503,8 @@ int fb_upload(fb_ctx* c) {
     FB_CUDA(c, cudaSetDevice(c->device));
     const int D = c->D, pwin = c->thr_max - c->thr_min + 1;
     Trace tr;
+    if (tr.on) fprintf(stderr, "[fb_trace] add_gap_file: parse %.3f ms, pack %.3f ms\n", c->t_parse_ms, c->t_pack_ms);
+    c->t_parse_ms = c->t_pack_ms = 0;
     // ---- units: every (owned gap, estimate); heaviest first so persistent CTAs balance (LPT)
     struct U { int gap, gp; double cost; long liks; };
     std::vector<U> us;
@@ -580,8 +591,9 @@ int fb_upload(fb_ctx* c) {
         b.global_tables = false;
         b.chunk = 0;
         int ctas = 2;
-        for (int want : {16, 8}) {
-            if (fb_em_smem_bytes(b.nr_stride, b.gp_stride, b.p_stride, want, pwin, false) <= two_cta) { b.chunk = want; break; }
+        const int pref = getenv("FB_CHUNK") ? atoi(getenv("FB_CHUNK")) : 16;   // tuning knob: records per pipeline round
+        for (int want : {pref, 8, 4}) {
+            if (want >= 1 && fb_em_smem_bytes(b.nr_stride, b.gp_stride, b.p_stride, want, pwin, false) <= two_cta) { b.chunk = want; break; }
         }
         if (!b.chunk) {
             ctas = 1;
@@ -598,7 +610,8 @@ int fb_upload(fb_ctx* c) {
         }
         b.smem = fb_em_smem_bytes(b.nr_stride, b.gp_stride, b.p_stride, b.chunk, pwin, b.global_tables);
         b.grid = std::min(b.n_units, c->sm_count * ctas);
-        if (b.global_tables) gws_need = std::max(gws_need, (size_t)b.grid * gws_stride_of(b.nr_stride, b.gp_stride));
+        b.gws_off = gws_need;
+        if (b.global_tables) gws_need += (size_t)b.grid * gws_stride_of(b.nr_stride, b.gp_stride);
     }
     tr.lap("upload: units + bins");
     while (c->bin_done.size() < c->bins.size()) {
@@ -607,6 +620,9 @@ int fb_upload(fb_ctx* c) {
         FB_CUDA(c, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
         c->bin_done.push_back(a);
         c->bin_copied.push_back(b);
+        cudaStream_t bs;
+        FB_CUDA(c, cudaStreamCreateWithFlags(&bs, cudaStreamNonBlocking));
+        c->bin_streams.push_back(bs);
     }
     // ---- device buffers + host->device copies
     const size_t ng = c->h_gapmeta.size(), nr = c->h_rmeta.size();
@@ -711,10 +727,16 @@ int fb_run_device(fb_ctx* c) {
         p.p_stride = b.p_stride;
         p.chunk = b.chunk;
         p.gws_stride = gws_stride_of(b.nr_stride, b.gp_stride);
-        FB_CUDA(c, fb_launch_em(p, b.grid, b.global_tables, b.smem, c->stream));
+        p.gws = c->d_gws.p + b.gws_off;
+        // every bin runs on its own stream: as the persistent CTAs of one bin drain, CTAs of the next bin take over the
+        // freed SMs, so only the last (smallest) bin has a tail
+        cudaStream_t bs = c->bin_streams[bi];
+        FB_CUDA(c, cudaStreamWaitEvent(bs, c->ev0, 0));
+        FB_CUDA(c, fb_launch_em(p, b.grid, b.global_tables, b.smem, bs));
         st.em_launches++;
-        // this bin's slice of unit_maxprob goes home on the copy stream while the next bin computes
-        FB_CUDA(c, cudaEventRecord(c->bin_done[bi], c->stream));
+        // this bin's slice of unit_maxprob goes home on the copy stream while the other bins compute
+        FB_CUDA(c, cudaEventRecord(c->bin_done[bi], bs));
+        FB_CUDA(c, cudaStreamWaitEvent(c->stream, c->bin_done[bi], 0));
         FB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->bin_done[bi], 0));
         const FbUnit& u0 = c->h_units[b.first_unit];
         const FbUnit& u1 = c->h_units[b.first_unit + b.n_units - 1];
@@ -944,6 +966,7 @@ int fb_dump_profile(fb_ctx* c, int gap, int estimate, double* probs, double* cou
             p.p_stride = b.p_stride;
             p.chunk = b.chunk;
             p.gws_stride = gws_stride_of(b.nr_stride, b.gp_stride);
+            p.gws = c->d_gws.p + b.gws_off;
             p.dump_probs = c->d_dump.p;
             p.dump_counts = c->d_dump.p + n;
             p.dump_unit = 0;
