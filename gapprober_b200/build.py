@@ -48,10 +48,12 @@ def build_library(force=False, verbose=False):
 def build_tools(force=False):
     os.makedirs(BIN, exist_ok=True)
     out = []
-    for name in ("fb_synth",):
+    host = os.path.join(CSRC, "host")
+    for name in ("fb_synth", "fb_split"):
         src = os.path.join(TOOLS, name + ".cpp")
         exe = os.path.join(BIN, name)
-        if force or _newer(exe, [src]):
+        deps = [src] + ([os.path.join(host, "fb_split.hpp"), os.path.join(host, "fb_io.hpp")] if name == "fb_split" else [])
+        if force or _newer(exe, deps):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-o", exe, src])
         out.append(exe)
     return out
@@ -62,7 +64,8 @@ def build_host(force=False):
     os.makedirs(BIN, exist_ok=True)
     host = os.path.join(CSRC, "host")
     src = os.path.join(host, "figbird.cpp")
-    deps = [src, os.path.join(host, "fb_preamble.hpp"), os.path.join(host, "fb_io.hpp"), os.path.join(ROOT, "include", "figbird_cuda.h")]
+    deps = [src, os.path.join(host, "fb_preamble.hpp"), os.path.join(host, "fb_io.hpp"), os.path.join(host, "fb_split.hpp"),
+            os.path.join(ROOT, "include", "figbird_cuda.h")]
     exe = os.path.join(BIN, "figbird.out")
     if force or _newer(exe, deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, src])

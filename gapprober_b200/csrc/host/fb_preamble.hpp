@@ -123,8 +123,10 @@ public:
     }
 
     // Pass 1 over the file, then computeProbabilites, then pass 2 (computeLikelihood) and the cut-off.
-    bool learn(const char* myout_path, Model& out) {
-        FILE* fp = fopen(myout_path, "r");
+    // With `mem` the same text is read from memory (the splitter's in-memory hand-off) instead of from myout_path.
+    bool learn(const char* myout_path, Model& out, const std::string* mem = nullptr) {
+        mem_ = mem;
+        FILE* fp = open_input(myout_path);
         if (!fp) return false;
         std::vector<char> line(kMaxRecLen);
         while (fgets(line.data(), kMaxRecLen, fp)) {
@@ -162,6 +164,12 @@ public:
     int thr_max() const { return thr_max_; }
 
 private:
+    FILE* open_input(const char* path) const {
+        if (mem_) return mem_->empty() ? fopen("/dev/null", "r") : fmemopen((void*)mem_->data(), mem_->size(), "r");
+        return fopen(path, "r");
+    }
+    const std::string* mem_ = nullptr;
+
     // updateInsertCounts, figbird.cpp:164-203
     void count_insert(int v) {
         if (v <= 0) return;
@@ -397,7 +405,7 @@ private:
 
     // computeLikelihood, figbird.cpp:1135-1351: only its side effects (gapProbs histogram, insertCountsMapped) are used.
     bool score_pairs(const char* path) {
-        FILE* fp = fopen(path, "r");
+        FILE* fp = open_input(path);
         if (!fp) return false;
         std::vector<char> l1(kMaxRecLen), l2(kMaxRecLen);
         std::string pre1 = "*", pre2 = "*", md1, md2;

@@ -12,6 +12,9 @@
 //   FIGBIRD_DEVICE=<n>       CUDA device (default 0)
 //   FIGBIRD_MODEL_OUT=<path> also write the learned model ("FBM1" file)
 //   FIGBIRD_PREAMBLE_ONLY=1  stop after the preamble (used by the benchmark to build its model)
+//   FIGBIRD_FROM_SAM=<path>  in-memory hand-off: split <path> (bowtie2's result.sam) in this process the way
+//                            main.cpp does (fb_split.hpp) and feed the proper pairs to the preamble and the gap records to
+//                            the GPU without writing myout.sam or Gaps/*.sam (gapInfo.txt and stat.txt are still written)
 // There is no CPU fallback: if the library or a GPU is missing the program prints why and exits 1.
 
 #include <dlfcn.h>
@@ -28,6 +31,7 @@
 #include "../../../include/figbird_cuda.h"
 #include "fb_io.hpp"
 #include "fb_preamble.hpp"
+#include "fb_split.hpp"
 
 namespace {
 
@@ -97,17 +101,40 @@ int main(int argc, char* argv[]) {
         printf("Can't open contig file\n");
         return 1;
     }
-    FILE* probe = fopen("myout.sam", "r");
-    if (!probe) {
-        printf("Can't open map file\n");
-        return 1;
-    }
-    fclose(probe);
+    const char* from_sam = getenv("FIGBIRD_FROM_SAM");
+    fbhost::Splitter* split = nullptr;
+    std::string myout_text;
     long total_count = 0, un_count = 0;
     int max_read_len = 0, max_insert = 0;
-    if (FILE* st = fopen("stat.txt", "r")) {
-        if (fscanf(st, "%ld %ld %d %d", &total_count, &un_count, &max_read_len, &max_insert) != 4) max_read_len = 0;
-        fclose(st);
+    if (from_sam) {
+        split = new fbhost::Splitter(sc);
+        char* buf = nullptr;
+        size_t len = 0;
+        FILE* mem = open_memstream(&buf, &len);
+        if (!split->run(from_sam, mem, nullptr, nullptr, nullptr, false)) {
+            printf("Can't open map file\n");
+            return 1;
+        }
+        fclose(mem);
+        myout_text.assign(buf, len);
+        free(buf);
+        total_count = split->total_count;
+        un_count = split->un_count;
+        max_read_len = (int)split->max_read_len;
+        max_insert = 5000;
+        if (FILE* gi = fopen("gapInfo.txt", "w")) { split->write_gap_info(gi); fclose(gi); }
+        if (FILE* st = fopen("stat.txt", "w")) { split->write_stat(st); fclose(st); }
+    } else {
+        FILE* probe = fopen("myout.sam", "r");
+        if (!probe) {
+            printf("Can't open map file\n");
+            return 1;
+        }
+        fclose(probe);
+        if (FILE* st = fopen("stat.txt", "r")) {
+            if (fscanf(st, "%ld %ld %d %d", &total_count, &un_count, &max_read_len, &max_insert) != 4) max_read_len = 0;
+            fclose(st);
+        }
     }
     if (max_read_len < 1) {
         printf("Can't read stat.txt\n");
@@ -117,7 +144,7 @@ int main(int argc, char* argv[]) {
     // ---- preamble (host): model tables + gapProbCutOff
     fbhost::Preamble pre(max_read_len, max_insert, sc.lengths());
     fbhost::Model hm;
-    if (!pre.learn("myout.sam", hm)) {
+    if (!pre.learn("myout.sam", hm, from_sam ? &myout_text : nullptr)) {
         printf("Can't open map file\n");
         return 1;
     }
@@ -166,7 +193,9 @@ int main(int argc, char* argv[]) {
     time_t t0, t1;
     time(&t0);
     std::vector<fbhost::GapInfo> gaps;
-    if (!fbhost::read_gap_info("gapInfo.txt", gaps)) {
+    if (split) {
+        for (const fbhost::SplitGap& g : split->gaps) gaps.push_back({g.contig_no, g.start, g.length});
+    } else if (!fbhost::read_gap_info("gapInfo.txt", gaps)) {
         printf("Can't open gapInfo.txt\n");
         return 1;
     }
@@ -175,7 +204,9 @@ int main(int argc, char* argv[]) {
         char name[64];
         snprintf(name, sizeof name, "Gaps/gaps_%zu.sam", g);
         std::vector<fbhost::GapRecord> recs;
-        if (!fbhost::read_gap_file(name, recs)) {
+        if (split) {
+            recs.swap(split->gaps[g].records);
+        } else if (!fbhost::read_gap_file(name, recs)) {
             printf("Can't open %s\n", name);
             return 1;
         }

@@ -28,3 +28,26 @@ def test_dropin_outputs_equal_reference(built, tmp_path):
         assert filecmp.cmp(os.path.join(a, f), os.path.join(b, f), shallow=False), f
     strip = lambda s: [ln for ln in s.splitlines() if not ln.startswith("Total time to fill gaps")]
     assert strip(ours.stdout) == strip(ref.stdout)
+
+
+def test_in_memory_handoff_from_result_sam(built, tmp_path):
+    """FIGBIRD_FROM_SAM: result.sam -> split -> preamble -> GPU in one process, no myout.sam / Gaps/ on disk; same gapout.txt
+    and filledContigs.fa as the reference pipeline main.out -> figbird.out."""
+    if not refrun.have_ref():
+        pytest.skip("oracle/_ref binaries not built")
+    from gapprober_b200 import build, synth
+    a, b = str(tmp_path / "ours"), str(tmp_path / "ref")
+    synth.generate(a, ARGS, seed=33, direct=False, sam=True)
+    shutil.copytree(a, b)
+    os.makedirs(os.path.join(b, "Gaps"), exist_ok=True)
+    shutil.rmtree(os.path.join(a, "Gaps"), ignore_errors=True)
+    env = dict(os.environ, FIGBIRD_FROM_SAM="result.sam")
+    ours = subprocess.run([build.build_host(), "scaffolds.fa", " 0", "250"], cwd=a, env=env, stdout=subprocess.PIPE, text=True)
+    assert ours.returncode == 0, ours.stdout
+    subprocess.run([refrun.REF_MAIN, "scaffolds.fa", "250"], cwd=b, check=True, stdout=subprocess.DEVNULL)
+    ref = subprocess.run([refrun.REF_FIGBIRD, "scaffolds.fa", " 0", "250"], cwd=b, stdout=subprocess.PIPE, text=True, check=True)
+    for f in ("gapout.txt", "filledContigs.fa", "mappedInserts.txt", "gapInfo.txt", "stat.txt"):
+        assert filecmp.cmp(os.path.join(a, f), os.path.join(b, f), shallow=False), f
+    assert not os.path.exists(os.path.join(a, "myout.sam")) and not os.path.exists(os.path.join(a, "Gaps"))
+    strip = lambda s: [ln for ln in s.splitlines() if not ln.startswith("Total time to fill gaps")]
+    assert strip(ours.stdout) == strip(ref.stdout)
