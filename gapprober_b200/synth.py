@@ -20,6 +20,11 @@ CONFIGS = {
     # human chr14 scale: 88 Mb, ~5000 gaps, 40x; the model is learned from a 400k-pair sample of the proper pairs
     "cfg4_chr14": ["--genome", "88000000", "--scaffolds", "40", "--gaps", "5000", "--gap-min", "50", "--gap-max", "500",
                    "--cov", "40", "--err", "0.01", "--ins-mean", "180", "--ins-sd", "20", "--model-pairs", "400000"],
+    # single-gap stress sweep, two corners: long gap x high coverage x duplicated anchors (bowtie2 -k style)
+    "cfg5_stress_g5000_c300_k10": ["--genome", "200000", "--gap-list", "5000", "--cov", "300", "--err", "0.01", "--ins-mean", "500",
+                                   "--ins-sd", "50", "--multihit", "10", "--model-pairs", "200000"],
+    "cfg5_stress_g100_c300_k50": ["--genome", "200000", "--gap-list", "100", "--cov", "300", "--err", "0.01", "--ins-mean", "180",
+                                  "--ins-sd", "20", "--multihit", "50", "--model-pairs", "200000"],
 }
 
 
