@@ -12,7 +12,7 @@ finalize).  Workload at N=1: BASELINE.json configs[1] (R. sphaeroides scale, ~20
 
 `value`  : inputs resident in HBM (fb_run_device), whole job, max over ranks.
 `e2e`    : the same work through the public entry point from HOST data: gap files parsed and packed by the
-           library, pinned host->device copies, kernels, device->host copies (fb_add_gap_file + fb_run).
+           library (host threads), pinned host->device copies, kernels, device->host copies (fb_add_gap_files + fb_run).
 `roofline`: the EM kernel against the measured HBM peak with SURVEY §8(d)'s algorithmic bytes — reported as asked,
            but shared-memory bandwidth is the binding roof of this path (see `smem` and DESIGN.md).
 """
@@ -268,9 +268,7 @@ def run_ours(a):
 
     def register():
         fb.clearGaps()
-        for i in mine:
-            c, s, l = gaps[i]
-            fb.GapFiller().initGapFiller(c, s, l, gap_files[i], seqs[c])
+        fb.add_gap_files([(gaps[i][0], gaps[i][1], gaps[i][2], gap_files[i], seqs[gaps[i][0]]) for i in mine])
 
     def allmax(x):
         if world == 1:

@@ -19,7 +19,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <chrono>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -316,34 +318,64 @@ int fb_clear_gaps(fb_ctx* c) {
     return FB_OK;
 }
 
-int fb_add_gap(fb_ctx* c, int contig_no, long gap_start, int orig_gap, const char* contig, long contig_len,
-               const fb_record* recs, int nrec) {
-    if (!c || !contig || nrec < 0 || (nrec > 0 && !recs)) return FB_EINVAL;
-    const int D = c->D;
+}  // extern "C"
+
+namespace {
+
+// One gap packed for the device, built without touching the context (so gaps can be packed by several threads).
+struct PackedGap {
+    HostGap g;
+    std::vector<uint8_t> flank, bytes;
+    std::vector<uint4> codes, nmask;
+    std::vector<FbRecMeta> rmeta;
+    int status = FB_OK;
+    std::string err;
+};
+
+struct PackConsts {
+    int D, thr_min, thr_max, max_read_len;
+};
+
+void pack_fail(PackedGap& out, int code, const char* fmt, ...) {
+    char buf[256];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    out.status = code;
+    out.err = buf;
+}
+
+void pack_gap(const PackConsts& k, int contig_no, long gap_start, int orig_gap, const char* contig, long contig_len,
+              const fb_record* recs, int nrec, PackedGap& out) {
+    const int D = k.D;
     // Outside these bounds the reference indexes past its arrays: refuse.
     if (orig_gap < 1 || gap_start < D || gap_start + orig_gap + D > contig_len)
-        return c->fail(FB_EDOMAIN, "gap at %ld (+%d) is closer than %d to a scaffold end", gap_start, orig_gap, D);
+        return pack_fail(out, FB_EDOMAIN, "gap at %ld (+%d) is closer than %d to a scaffold end", gap_start, orig_gap, D);
     for (int r = 0; r < nrec; r++) {
-        if (recs[r].len2 < 1 || recs[r].len2 > FB_MAX_READ || recs[r].len2 > c->max_read_len || recs[r].len2 > D || !recs[r].seq2)
-            return c->fail(FB_EDOMAIN, "record %d: mate length %d unsupported", r, recs[r].len2);
+        if (recs[r].len2 < 1 || recs[r].len2 > FB_MAX_READ || recs[r].len2 > k.max_read_len || recs[r].len2 > D || !recs[r].seq2)
+            return pack_fail(out, FB_EDOMAIN, "record %d: mate length %d unsupported", r, recs[r].len2);
     }
-    HostGap g;
+    HostGap& g = out.g;
     g.contig_no = contig_no;
     g.gap_start = gap_start;
     g.orig = orig_gap;
     fb_gap_range(orig_gap, &g.gmin, &g.gmax);
-    if (g.gmax < g.gmin) return c->fail(FB_EDOMAIN, "empty estimate range for gap length %d", orig_gap);
-    g.rec_off = (int)c->h_rmeta.size();
+    if (g.gmax < g.gmin) return pack_fail(out, FB_EDOMAIN, "empty estimate range for gap length %d", orig_gap);
+    g.rec_off = 0;
     g.nrec = nrec;
     g.lmax = 1;
     // flanks: D bases before the gap, D bases after the ORIGINAL gap (figbird.cpp:1657-1670)
-    const size_t fo = c->h_flank.size();
-    c->h_flank.resize(fo + 2 * (size_t)D);
+    out.flank.resize(2 * (size_t)D);
     for (int i = 0; i < D; i++) {
-        c->h_flank[fo + i] = (uint8_t)base_code(contig[gap_start - D + i]);
-        c->h_flank[fo + D + i] = (uint8_t)base_code(contig[gap_start + orig_gap + i]);
+        out.flank[i] = (uint8_t)base_code(contig[gap_start - D + i]);
+        out.flank[D + i] = (uint8_t)base_code(contig[gap_start + orig_gap + i]);
     }
     const long sp = gap_start - D;
+    out.bytes.assign((size_t)nrec * FB_MAX_READ, 5);
+    out.codes.reserve((size_t)nrec * 2);
+    out.nmask.reserve(nrec);
+    out.rmeta.reserve(nrec);
     for (int r = 0; r < nrec; r++) {
         const fb_record& rc = recs[r];
         const int L2 = rc.len2;
@@ -351,52 +383,41 @@ int fb_add_gap(fb_ctx* c, int contig_no, long gap_start, int orig_gap, const cha
         const bool rev = rc.strand1 == 0;             // isReverse, figbird.cpp:1803-1812
         const bool left = rc.pos1 < gap_start;        // figbird.cpp:1822
         uint32_t cw[8] = {0, 0, 0, 0, 0, 0, 0, 0}, nm[4] = {0, 0, 0, 0};
-        const size_t bo = c->h_bytes.size();
-        c->h_bytes.resize(bo + FB_MAX_READ, 5);
+        uint8_t* bo = &out.bytes[(size_t)r * FB_MAX_READ];
         for (int j = 0; j < L2; j++) {
             int code = rev ? revcomp_code(rc.seq2[L2 - 1 - j]) : base_code(rc.seq2[j]);
-            c->h_bytes[bo + j] = (uint8_t)code;
+            bo[j] = (uint8_t)code;
             if (code < 4) cw[j >> 4] |= (uint32_t)code << (2 * (j & 15));
             else nm[j >> 5] |= 1u << (j & 31);
         }
-        c->h_codes.push_back(make_uint4(cw[0], cw[1], cw[2], cw[3]));
-        c->h_codes.push_back(make_uint4(cw[4], cw[5], cw[6], cw[7]));
-        c->h_nmask.push_back(make_uint4(nm[0], nm[1], nm[2], nm[3]));
+        out.codes.push_back(make_uint4(cw[0], cw[1], cw[2], cw[3]));
+        out.codes.push_back(make_uint4(cw[4], cw[5], cw[6], cw[7]));
+        out.nmask.push_back(make_uint4(nm[0], nm[1], nm[2], nm[3]));
         FbRecMeta m;
         long tb, lo, hi;
         if (left) {          // t = u + tb
             tb = sp - rc.pos1 + L2;
-            lo = c->thr_min - tb;
-            hi = c->thr_max - tb;
+            lo = k.thr_min - tb;
+            hi = k.thr_max - tb;
         } else {             // t = tb - u
             tb = (long)rc.pos1 + rc.len1 - sp;
-            lo = tb - c->thr_max;
-            hi = tb - c->thr_min;
+            lo = tb - k.thr_max;
+            hi = tb - k.thr_min;
         }
         const long LIM = 1L << 30;
         m.tb = (int)std::max(-LIM, std::min(LIM, tb));
         m.a_lo = (int)std::max(-LIM, std::min(LIM, lo));
         m.a_hi = (int)std::max(-LIM, std::min(LIM, hi));
         m.flags = L2 | (rev ? 256 : 0) | (left ? 512 : 0);
-        c->h_rmeta.push_back(m);
+        out.rmeta.push_back(m);
     }
-    FbGapMeta gm;
-    gm.rec_off = g.rec_off;
-    gm.nrec = nrec;
-    gm.orig = orig_gap;
-    gm.lmax = g.lmax;
-    c->h_gapmeta.push_back(gm);
-    c->gaps.push_back(g);
-    c->uploaded = c->ran = false;
-    return (int)c->gaps.size() - 1;
 }
 
-int fb_add_gap_file(fb_ctx* c, int contig_no, long gap_start, int orig_gap, const char* contig, long contig_len, const char* gap_file) {
-    if (!c || !gap_file) return FB_EINVAL;
-    const auto t_begin = std::chrono::steady_clock::now();
-    FILE* fp = fopen(gap_file, "r");
-    if (!fp) return c->fail(FB_EINVAL, "cannot open %s", gap_file);
-    // placeReads' parse, figbird.cpp:1718-1801
+// placeReads' parse of one gap file (figbird.cpp:1718-1801), then pack.
+void parse_and_pack(const PackConsts& k, int contig_no, long gap_start, int orig_gap, const char* contig, long contig_len,
+                    const char* gap_file, PackedGap& out) {
+    FILE* fp = gap_file ? fopen(gap_file, "r") : nullptr;
+    if (!fp) return pack_fail(out, FB_EINVAL, "cannot open %s", gap_file ? gap_file : "(null)");
     std::vector<fb_record> recs;
     std::vector<std::string> seqs;
     char l1[1024], l2[1024];
@@ -405,10 +426,10 @@ int fb_add_gap_file(fb_ctx* c, int contig_no, long gap_start, int orig_gap, cons
         if (!fgets(l2, sizeof l2, fp)) break;
         char *s1 = nullptr, *s2 = nullptr, *col[7];
         bool ok = (col[0] = strtok_r(l1, "\t", &s1)) != nullptr;
-        for (int k = 1; k < 7 && ok; k++) ok = (col[k] = strtok_r(nullptr, "\t", &s1)) != nullptr;
+        for (int q = 1; q < 7 && ok; q++) ok = (col[q] = strtok_r(nullptr, "\t", &s1)) != nullptr;
         if (!ok) continue;
         char* m = strtok_r(l2, "\t", &s2);
-        for (int k = 1; k < 7 && m; k++) m = strtok_r(nullptr, "\t", &s2);
+        for (int q = 1; q < 7 && m; q++) m = strtok_r(nullptr, "\t", &s2);
         if (!m) continue;
         fb_record r;
         r.strand1 = (atoi(col[1]) & 16) >> 4;
@@ -421,11 +442,89 @@ int fb_add_gap_file(fb_ctx* c, int contig_no, long gap_start, int orig_gap, cons
     }
     fclose(fp);
     for (size_t i = 0; i < recs.size(); i++) recs[i].seq2 = seqs[i].c_str();
-    const auto t_parsed = std::chrono::steady_clock::now();
-    const int rc = fb_add_gap(c, contig_no, gap_start, orig_gap, contig, contig_len, recs.data(), (int)recs.size());
-    c->t_parse_ms += std::chrono::duration<double, std::milli>(t_parsed - t_begin).count();
-    c->t_pack_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_parsed).count();
-    return rc;
+    pack_gap(k, contig_no, gap_start, orig_gap, contig, contig_len, recs.data(), (int)recs.size(), out);
+}
+
+int append_gap(fb_ctx* c, PackedGap& pk) {
+    if (pk.status != FB_OK) return c->fail(pk.status, "%s", pk.err.c_str());
+    pk.g.rec_off = (int)c->h_rmeta.size();
+    c->h_flank.insert(c->h_flank.end(), pk.flank.begin(), pk.flank.end());
+    c->h_bytes.insert(c->h_bytes.end(), pk.bytes.begin(), pk.bytes.end());
+    c->h_codes.insert(c->h_codes.end(), pk.codes.begin(), pk.codes.end());
+    c->h_nmask.insert(c->h_nmask.end(), pk.nmask.begin(), pk.nmask.end());
+    c->h_rmeta.insert(c->h_rmeta.end(), pk.rmeta.begin(), pk.rmeta.end());
+    FbGapMeta gm;
+    gm.rec_off = pk.g.rec_off;
+    gm.nrec = pk.g.nrec;
+    gm.orig = pk.g.orig;
+    gm.lmax = pk.g.lmax;
+    c->h_gapmeta.push_back(gm);
+    c->gaps.push_back(pk.g);
+    c->uploaded = c->ran = false;
+    return (int)c->gaps.size() - 1;
+}
+
+PackConsts consts_of(const fb_ctx* c) { return PackConsts{c->D, c->thr_min, c->thr_max, c->max_read_len}; }
+
+// Run fn(i) for i in [0, n) on up to `threads` host threads (0 = one per hardware thread, at most 16).
+template <typename F>
+void parallel_for(int n, int threads, F fn) {
+    int hw = (int)std::thread::hardware_concurrency();
+    if (threads <= 0) threads = std::max(1, std::min(hw > 0 ? hw : 1, 16));
+    threads = std::min(threads, n);
+    if (threads <= 1) {
+        for (int i = 0; i < n; i++) fn(i);
+        return;
+    }
+    std::atomic<int> next(0);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++)
+        pool.emplace_back([&]() {
+            for (;;) {
+                int i = next.fetch_add(1);
+                if (i >= n) break;
+                fn(i);
+            }
+        });
+    for (auto& th : pool) th.join();
+}
+
+}  // namespace
+
+extern "C" {
+
+int fb_add_gap(fb_ctx* c, int contig_no, long gap_start, int orig_gap, const char* contig, long contig_len,
+               const fb_record* recs, int nrec) {
+    if (!c || !contig || nrec < 0 || (nrec > 0 && !recs)) return FB_EINVAL;
+    PackedGap pk;
+    pack_gap(consts_of(c), contig_no, gap_start, orig_gap, contig, contig_len, recs, nrec, pk);
+    return append_gap(c, pk);
+}
+
+int fb_add_gap_file(fb_ctx* c, int contig_no, long gap_start, int orig_gap, const char* contig, long contig_len, const char* gap_file) {
+    if (!c || !gap_file || !contig) return FB_EINVAL;
+    PackedGap pk;
+    parse_and_pack(consts_of(c), contig_no, gap_start, orig_gap, contig, contig_len, gap_file, pk);
+    return append_gap(c, pk);
+}
+
+int fb_add_gap_files(fb_ctx* c, const fb_gap_desc* descs, int n, int* handles, int threads) {
+    if (!c || n < 0 || (n > 0 && (!descs || !handles))) return FB_EINVAL;
+    const PackConsts k = consts_of(c);
+    std::vector<PackedGap> packed((size_t)n);
+    parallel_for(n, threads, [&](int i) {
+        const fb_gap_desc& d = descs[i];
+        if (!d.contig) pack_fail(packed[i], FB_EINVAL, "gap %d: null contig", i);
+        else parse_and_pack(k, d.contig_no, d.gap_start, d.orig_gap, d.contig, d.contig_len, d.gap_file, packed[i]);
+    });
+    int bad = 0;
+    for (int i = 0; i < n; i++) {        // appended in the order given: handles are dense and deterministic
+        handles[i] = append_gap(c, packed[i]);
+        if (handles[i] < 0) bad++;
+    }
+    if (!bad) return FB_OK;
+    const std::string last = c->err;
+    return c->fail(FB_EDOMAIN, "%d of %d gaps were refused (see handles); last: %s", bad, n, last.c_str());
 }
 
 }  // extern "C"
@@ -505,20 +604,25 @@ int fb_upload(fb_ctx* c) {
     Trace tr;
     if (tr.on) fprintf(stderr, "[fb_trace] add_gap_file: parse %.3f ms, pack %.3f ms\n", c->t_parse_ms, c->t_pack_ms);
     c->t_parse_ms = c->t_pack_ms = 0;
-    // ---- units: every (owned gap, estimate); heaviest first so persistent CTAs balance (LPT)
+    // ---- units: every (owned gap, estimate); heaviest first so persistent CTAs balance (LPT).
+    // The per-gap sums are independent: computed on several host threads, merged in gap order.
     struct U { int gap, gp; double cost; long liks; };
-    std::vector<U> us;
+    struct GapUnits { std::vector<U> us; long liks = 0, terms = 0, bytes = 0; };
     fb_stats& st = c->stats;
     memset(&st, 0, sizeof st);
-    for (size_t gi = 0; gi < c->gaps.size(); gi++) {
+    std::vector<GapUnits> per_gap(c->gaps.size());
+    parallel_for((int)c->gaps.size(), 0, [&](int gi) {
         HostGap& g = c->gaps[gi];
         g.done = false;
         g.likelihoods = 0;
-        if (!g.owned) continue;
-        st.n_gaps++;
-        st.n_records += g.nrec;
+        if (!g.owned) return;
+        GapUnits& out = per_gap[gi];
+        long rec_bytes = 0;      // packed bases + mask + metadata in, per-record maximum out
+        for (int r = 0; r < g.nrec; r++) {
+            int L2 = c->h_rmeta[g.rec_off + r].flags & 0xff;
+            rec_bytes += (L2 + 3) / 4 + (L2 + 7) / 8 + 8 + 8;
+        }
         for (int gp = g.gmin; gp <= g.gmax; gp++) {
-            double cost = 0;
             long liks = 0, terms = 0;
             for (int r = 0; r < g.nrec; r++) {
                 const FbRecMeta& m = c->h_rmeta[g.rec_off + r];
@@ -526,20 +630,22 @@ int fb_upload(fb_ctx* c) {
                 liks += pl;
                 terms += pl * (m.flags & 0xff);
             }
-            cost = (double)terms + 2000.0;
-            us.push_back({(int)gi, gp, cost, liks});
-            g.likelihoods += liks * c->num_iter;
-            st.likelihoods += liks * c->num_iter;
-            st.base_terms += terms * c->num_iter;
-            // packed bases + mask + meta in, counts out / profile in, per-record maximum out
-            long bytes = 0;
-            for (int r = 0; r < g.nrec; r++) {
-                int L2 = c->h_rmeta[g.rec_off + r].flags & 0xff;
-                bytes += (L2 + 3) / 4 + (L2 + 7) / 8 + 8 + 8;
-            }
-            bytes += 2L * 40 * gp;
-            st.algorithmic_bytes += bytes * c->num_iter;
+            out.us.push_back({gi, gp, (double)terms + 2000.0, liks});
+            out.liks += liks * c->num_iter;
+            out.terms += terms * c->num_iter;
+            out.bytes += (rec_bytes + 2L * 40 * gp) * c->num_iter;   // + counts out / profile in
         }
+        g.likelihoods = out.liks;
+    });
+    std::vector<U> us;
+    for (size_t gi = 0; gi < c->gaps.size(); gi++) {
+        if (!c->gaps[gi].owned) continue;
+        st.n_gaps++;
+        st.n_records += c->gaps[gi].nrec;
+        st.likelihoods += per_gap[gi].liks;
+        st.base_terms += per_gap[gi].terms;
+        st.algorithmic_bytes += per_gap[gi].bytes;
+        us.insert(us.end(), per_gap[gi].us.begin(), per_gap[gi].us.end());
     }
     st.n_units = (long)us.size();
     // bins by estimate size (shared-memory footprint decides occupancy), then cost-descending inside a bin
@@ -838,18 +944,18 @@ int fb_run_device(fb_ctx* c) {
     }
 
     tr.lap("run: select + finalize kernel");
-    // ---- finalize on the host: cut-off, +1 counts, computeSequence(1), getConcensus
-    std::vector<int> cnt;
-    for (int gi : gaplist) {
-        HostGap& g = c->gaps[gi];
+    // ---- finalize on the host: cut-off, +1 counts, computeSequence(1), getConcensus (gaps are independent: host threads)
+    std::vector<long> fin_liks(gaplist.size(), 0);
+    parallel_for((int)gaplist.size(), 0, [&](int k) {
+        HostGap& g = c->gaps[gaplist[k]];
         const int gb = g.best_est;
-        cnt.assign((size_t)gb * 5, 0);
+        std::vector<int> cnt((size_t)gb * 5, 0);
         int disc = 0;
         for (int r = 0; r < g.nrec; r++) {
             const int rec = g.rec_off + r;
             const FbRecMeta& m = c->h_rmeta[rec];
             const int L2 = m.flags & 0xff;
-            st.finalize_likelihoods += placements(m, D, gb);
+            fin_liks[k] += placements(m, D, gb);
             const double mp = c->h_finprob.p[rec];
             if (-log(mp) <= c->cutoff) {                       // figbird.cpp:2293
                 const int pos = c->h_finpos.p[rec];
@@ -867,12 +973,13 @@ int fb_run_device(fb_ctx* c) {
         g.filled.assign((size_t)gb, 'N');
         for (int i = 0; i < gb; i++) {                          // computeSequence(1), figbird.cpp:1989-2045
             int mx = 0, idx = -1;
-            for (int k = 0; k < 5; k++)
-                if (cnt[(size_t)i * 5 + k] > mx) { mx = cnt[(size_t)i * 5 + k]; idx = k; }
+            for (int q = 0; q < 5; q++)
+                if (cnt[(size_t)i * 5 + q] > mx) { mx = cnt[(size_t)i * 5 + q]; idx = q; }
             g.filled[i] = idx < 0 ? 'N' : "ACGTN"[idx];
         }
         g.done = true;
-    }
+    });
+    for (long v : fin_liks) st.finalize_likelihoods += v;
     tr.lap("run: host finalize");
     FB_CUDA(c, cudaEventRecord(c->eve, c->stream));
     FB_CUDA(c, cudaEventSynchronize(c->eve));

@@ -54,6 +54,11 @@ class _FbRecord(C.Structure):
     _fields_ = [("pos1", C.c_int), ("len1", C.c_int), ("strand1", C.c_int), ("seq2", C.c_char_p), ("len2", C.c_int)]
 
 
+class _FbGapDesc(C.Structure):
+    _fields_ = [("contig_no", C.c_int), ("gap_start", C.c_long), ("orig_gap", C.c_int), ("contig", C.c_char_p),
+                ("contig_len", C.c_long), ("gap_file", C.c_char_p)]
+
+
 class _FbGapResult(C.Structure):
     _fields_ = [
         ("gap_min", C.c_int), ("gap_max", C.c_int), ("best_estimate", C.c_int), ("best_lik", C.c_double),
@@ -76,7 +81,7 @@ class FbStats(C.Structure):
 
 # Every symbol include/figbird_cuda.h declares; tests check the library exports all of them.
 ABI_SYMBOLS = [
-    "fb_create", "fb_destroy", "fb_add_gap", "fb_add_gap_file", "fb_set_partition", "fb_owns_gap", "fb_partition_plan", "fb_gap_cost", "fb_run", "fb_upload",
+    "fb_create", "fb_destroy", "fb_add_gap", "fb_add_gap_file", "fb_add_gap_files", "fb_set_partition", "fb_owns_gap", "fb_partition_plan", "fb_gap_cost", "fb_run", "fb_upload",
     "fb_run_device", "fb_result", "fb_estimate_liks", "fb_best_string", "fb_dump_profile", "fb_get_stats",
     "fb_clear_gaps", "fb_gap_range", "fb_last_error", "fb_status_str", "fb_abi_version",
 ]
@@ -98,6 +103,7 @@ def load_library():
     L.fb_destroy.restype = None
     L.fb_add_gap.argtypes = [vp, C.c_int, C.c_long, C.c_int, C.c_char_p, C.c_long, C.POINTER(_FbRecord), C.c_int]
     L.fb_add_gap_file.argtypes = [vp, C.c_int, C.c_long, C.c_int, C.c_char_p, C.c_long, C.c_char_p]
+    L.fb_add_gap_files.argtypes = [vp, C.POINTER(_FbGapDesc), C.c_int, C.POINTER(C.c_int), C.c_int]
     L.fb_set_partition.argtypes = [vp, C.c_int, C.c_int]
     L.fb_owns_gap.argtypes = [vp, C.c_int]
     L.fb_partition_plan.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int, C.POINTER(C.c_int)]
@@ -334,13 +340,38 @@ class FigbirdContext:
     def _add_gap_file(self, contig_no, gap_start, orig, contig, path):
         return self._check(self._L.fb_add_gap_file(self._h, contig_no, gap_start, orig, contig, len(contig), path))
 
-    def add_workdir(self, wd, scaffolds="scaffolds.fa"):
+    def add_gap_files(self, gaps, threads=0):
+        """Register many gaps at once: gaps = [(contigNo, gapStart, originalGap, gapFilePath, contig bytes)].  The library
+        parses and packs the files on several host threads (fb_add_gap_files).  Returns the GapFiller objects."""
+        n = len(gaps)
+        descs = (_FbGapDesc * max(1, n))()
+        keep = []
+        for i, (c, s, l, path, contig) in enumerate(gaps):
+            p = os.fsencode(path)
+            keep.append(p)
+            descs[i].contig_no, descs[i].gap_start, descs[i].orig_gap = int(c), int(s), int(l)
+            descs[i].contig, descs[i].contig_len, descs[i].gap_file = contig, len(contig), p
+        handles = (C.c_int * max(1, n))()
+        rc = self._L.fb_add_gap_files(self._h, descs, n, handles, int(threads))
+        out = []
+        for i, (c, s, l, path, contig) in enumerate(gaps):
+            if handles[i] < 0:
+                continue
+            g = GapFiller(self)
+            g.contigNo, g.gapStart, g.originalGap, g.index = int(c), int(s), int(l), handles[i]
+            while len(self._gaps) <= g.index:
+                self._gaps.append(None)
+            self._gaps[g.index] = g
+            out.append(g)
+        self._check(rc)
+        return out
+
+    def add_workdir(self, wd, scaffolds="scaffolds.fa", threads=0):
         """Register every gap of a GapProber working directory (gapInfo.txt + Gaps/), like figbird.cpp:2819-2842."""
         _, seqs = read_scaffolds(os.path.join(wd, scaffolds))
-        out = []
-        for gi, (c, s, l) in enumerate(read_gap_info(os.path.join(wd, "gapInfo.txt"))):
-            out.append(self.GapFiller().initGapFiller(c, s, l, os.path.join(wd, "Gaps", f"gaps_{gi}.sam"), seqs[c]))
-        return out
+        gaps = [(c, s, l, os.path.join(wd, "Gaps", f"gaps_{gi}.sam"), seqs[c])
+                for gi, (c, s, l) in enumerate(read_gap_info(os.path.join(wd, "gapInfo.txt")))]
+        return self.add_gap_files(gaps, threads)
 
     def setPartition(self, rank, world):
         self._check(self._L.fb_set_partition(self._h, rank, world))

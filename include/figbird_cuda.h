@@ -100,6 +100,19 @@ int fb_add_gap(fb_ctx* ctx, int contig_no, long gap_start, int orig_gap, const c
 int fb_add_gap_file(fb_ctx* ctx, int contig_no, long gap_start, int orig_gap, const char* contig, long contig_len,
                     const char* gap_file);
 
+/* Bulk form: parse and pack n gap files on several host threads (threads = 0: one per hardware thread, at most 16), then
+ * register them in the order given.  handles[i] receives the gap index or a negative fb_status for gap i; the call
+ * returns FB_OK only if every gap was accepted. */
+typedef struct fb_gap_desc {
+    int contig_no;
+    long gap_start;
+    int orig_gap;
+    const char* contig;
+    long contig_len;
+    const char* gap_file;
+} fb_gap_desc;
+int fb_add_gap_files(fb_ctx* ctx, const fb_gap_desc* descs, int n, int* handles, int threads);
+
 /* Restrict this context to its share of the work when several processes (one per GPU) split one gap
  * set: gaps are dealt to `world` ranks by descending cost (longest-processing-time first); this
  * context runs those of `rank`.  Results of other ranks' gaps are absent (fb_result -> FB_ESTATE).
