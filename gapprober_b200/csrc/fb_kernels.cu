@@ -177,11 +177,38 @@ __device__ __forceinline__ void load_record_bytes(const uint4* __restrict__ code
 // E-step of 64 placements of one record: lane owns placements ua and ua+32 (two independent product chains).
 // The running score is multiplied base by base in read order (figbird.cpp:1840-1864); REV selects the
 // read-position index k = L2-1-j of a reverse-complemented mate (figbird.cpp:1845-1852).
-// acc += w[.] for lanes whose placement offset lies inside the record's window (one predicated LDS + DADD).
-__device__ __forceinline__ void add_if_inside(double& acc, unsigned saddr, unsigned uoff, unsigned span) {
-    asm("{\n\t.reg .pred p;\n\t.reg .f64 v;\n\tsetp.le.u32 p, %2, %3;\n\t@p ld.shared.f64 v, [%1];\n\t@p add.rn.f64 %0, %0, v;\n\t}"
-        : "+d"(acc)
-        : "r"(saddr), "r"(uoff), "r"(span));
+// M-step inner step for one list entry: a lane owns four gap rows 32 apart (four independent accumulators, so four
+// add chains are in flight).  Row t's placement offset is uoff0 + 32t; it contributes when that offset lies inside the
+// record's window (lim[t] = window length, or 0 for a row past the gap).  Rows outside add +0.0, which is exact here:
+// the accumulators are sums of non-negative scores (or NaN) and never -0.0.
+__device__ __forceinline__ void add4_if_inside(double& a0, double& a1, double& a2, double& a3, unsigned saddr0, unsigned uoff0,
+                                               unsigned lim0, unsigned lim1, unsigned lim2, unsigned lim3) {
+    asm("{\n\t"
+        ".reg .pred p0, p1, p2, p3;\n\t"
+        ".reg .f64 v0, v1, v2, v3;\n\t"
+        ".reg .u32 u1, u2, u3;\n\t"
+        "add.u32 u1, %5, 32;\n\t"
+        "add.u32 u2, %5, 64;\n\t"
+        "add.u32 u3, %5, 96;\n\t"
+        "setp.lt.u32 p0, %5, %6;\n\t"
+        "setp.lt.u32 p1, u1, %7;\n\t"
+        "setp.lt.u32 p2, u2, %8;\n\t"
+        "setp.lt.u32 p3, u3, %9;\n\t"
+        "mov.f64 v0, 0d0000000000000000;\n\t"
+        "mov.f64 v1, 0d0000000000000000;\n\t"
+        "mov.f64 v2, 0d0000000000000000;\n\t"
+        "mov.f64 v3, 0d0000000000000000;\n\t"
+        "@p0 ld.shared.f64 v0, [%4];\n\t"
+        "@p1 ld.shared.f64 v1, [%4+256];\n\t"
+        "@p2 ld.shared.f64 v2, [%4+512];\n\t"
+        "@p3 ld.shared.f64 v3, [%4+768];\n\t"
+        "add.rn.f64 %0, %0, v0;\n\t"
+        "add.rn.f64 %1, %1, v1;\n\t"
+        "add.rn.f64 %2, %2, v2;\n\t"
+        "add.rn.f64 %3, %3, v3;\n\t"
+        "}"
+        : "+d"(a0), "+d"(a1), "+d"(a2), "+d"(a3)
+        : "r"(saddr0), "r"(uoff0), "r"(lim0), "r"(lim1), "r"(lim2), "r"(lim3));
 }
 
 template <bool REV, bool TWO>
@@ -283,7 +310,7 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
         __syncthreads();
 
         const int nchunks = (nrec + CH - 1) / CH;
-        const int nrg = (gp + 31) >> 5;               // M-step row groups
+        const int nrb = (gp + 127) >> 7;              // M-step row blocks of 128 rows
         const int nblk = (PS + 63) >> 6;              // E-step blocks of 64 placements per record
         int round = 0;                                // global round counter: selects the queue slot
         for (int it = 0; it < p.num_iter; it++) {
@@ -299,7 +326,7 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
                 const double* wM = s.w0 + ((cm + 2) & 1) * s.w_stride;
                 if (last && tid < n_m)   // per-record maximum of the last iteration (feeds figbird.cpp:1951-1955 on the host)
                     p.unit_maxprob[unit.mp_off + cm * CH + tid] = __longlong_as_double((long long)SM.rmax[tid]);
-                const int tM = n_m ? nrg * 5 : 0, tE = n_e * nblk, tL = n_l;
+                const int tM = n_m ? nrb * 5 : 0, tE = n_e * nblk, tL = n_l;
                 const int ntask = tM + tE + tL;
                 int* queue = &s_queue[round & 1];
                 for (;;) {
@@ -308,19 +335,19 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
                     task = __shfl_sync(0xffffffffu, task, 0);
                     if (task >= ntask) break;
                     if (task < tM) {
-                        // ---- M-step: lane per gap row, warp per (32 rows, base class).  Within a cell the CPU adds in
-                        // (record asc, placement asc) order (figbird.cpp:1718, 1826, 1874): walking a record's class
-                        // mask from high j to low j visits its placements in ascending order.
-                        const int c = task / nrg, rg = task - c * nrg;
-                        const int xg = rg * 32 + lane, x0 = D + rg * 32;
-                        const bool rowok = xg < gp;
-                        const int x = rowok ? x0 + lane : -(1 << 28);      // rows past the gap never fall inside a window
-                        double acc = rowok ? s.cnt[c * gps + xg] : 0.0;
+                        // ---- M-step: a lane owns four gap rows (32 apart), a warp one (128 rows, base class) cell block.  Within a
+                        // cell the CPU adds in (record asc, placement asc) order (figbird.cpp:1718, 1826, 1874): walking a record's
+                        // class list from high j to low j visits its placements in ascending order.
+                        const int c = task / nrb, rb = task - c * nrb;
+                        const int xg = rb * 128 + lane, x0 = D + rb * 128;
+                        const bool ok0 = xg < gp, ok1 = xg + 32 < gp, ok2 = xg + 64 < gp, ok3 = xg + 96 < gp;
+                        double* cr = s.cnt + c * gps + xg;
+                        double a0 = ok0 ? cr[0] : 0.0, a1 = ok1 ? cr[32] : 0.0, a2 = ok2 ? cr[64] : 0.0, a3 = ok3 ? cr[96] : 0.0;
                         const unsigned wM_s = (unsigned)__cvta_generic_to_shared(wM);
                         for (int rl = 0; rl < n_m; rl++) {
                             const int lo = SM.rlo[rl], hi = SM.rhi[rl];
                             const int L2 = SM.rfl[rl] & 0xff;
-                            const int jhi = min(L2 - 1, x0 + 31 - lo), jlo = max(0, x0 - hi);   // j with any lane inside [lo, hi]
+                            const int jhi = min(L2 - 1, x0 + 127 - lo), jlo = max(0, x0 - hi);   // j with any row of the block inside [lo, hi]
                             if (hi < lo || jhi < jlo) continue;
                             // exact sub-range of the class list: skip positions above jhi and below jlo
                             const uint32_t* mk = SM.mask + rl * 20 + c * 4;
@@ -329,16 +356,20 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
                             const int qs = cum[c * 4 + wh] + __popc((mk[wh] >> (jhi & 31)) >> 1);
                             const int qe = (wl == 0 ? cum[20 + c] : cum[c * 4 + wl - 1]) - __popc(mk[wl] & ((1u << (jlo & 31)) - 1u));
                             const uint8_t* jl = SM.jl + rl * FB_MAX_READ;
-                            const unsigned wbase = wM_s + (unsigned)(rl * PS) * 8u;
-                            const unsigned span = (unsigned)(hi - lo);
-                            const int xlo = x - lo;
-#pragma unroll 4
+                            const unsigned len = (unsigned)(hi - lo) + 1u;
+                            const unsigned l0 = ok0 ? len : 0u, l1 = ok1 ? len : 0u, l2 = ok2 ? len : 0u, l3 = ok3 ? len : 0u;
+                            const int xlo = x0 + lane - lo;
+                            const unsigned wbase = wM_s + (unsigned)(rl * PS + xlo) * 8u;
+#pragma unroll 2
                             for (int q = qs; q < qe; q++) {
-                                const unsigned uoff = (unsigned)(xlo - (int)jl[q]);
-                                add_if_inside(acc, wbase + uoff * 8u, uoff, span);   // figbird.cpp:1879
+                                const unsigned j = jl[q];
+                                add4_if_inside(a0, a1, a2, a3, wbase - j * 8u, (unsigned)xlo - j, l0, l1, l2, l3);   // figbird.cpp:1879
                             }
                         }
-                        if (rowok) s.cnt[c * gps + xg] = acc;
+                        if (ok0) cr[0] = a0;
+                        if (ok1) cr[32] = a1;
+                        if (ok2) cr[64] = a2;
+                        if (ok3) cr[96] = a3;
                     } else if (task < tM + tE) {
                         // ---- E-step: warp per (record, 64 placements); lanes over placements
                         const int te = task - tM;

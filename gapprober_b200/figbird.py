@@ -94,9 +94,10 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise FigbirdError(-3, f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
-    L = C.CDLL(LIB_PATH)
+    path = os.environ.get("FIGBIRD_CUDA_LIB", LIB_PATH)     # same override the drop-in binary honours
+    if not os.path.exists(path):
+        raise FigbirdError(-3, f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    L = C.CDLL(path)
     vp = C.c_void_p
     L.fb_create.argtypes = [C.POINTER(_FbModel), C.c_int, C.POINTER(vp)]
     L.fb_destroy.argtypes = [vp]
