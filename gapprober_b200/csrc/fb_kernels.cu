@@ -261,6 +261,7 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
     __shared__ int s_unit;
     __shared__ int s_queue[2];
     __shared__ double sT[25];
+    __shared__ double2 sRow[5][5];   // {P,Q} per base class of a row whose counts are one-hot in base b (flanks, and b=4: untouched gap rows)
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int D = p.D, CH = p.chunk, PS = p.p_stride;
@@ -269,6 +270,18 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
     if (tid < 25) sT[tid] = p.T[tid];
     if (GT) {
         for (int i = tid; i < kPadRows; i += FB_THREADS) s.pq[5 * (size_t)p.nr_stride + i] = make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    if (tid < 5) {
+        // initialize() only ever produces five different rows (figbird.cpp:1657-1673): compute them once
+        double c[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) c[k] = (k == tid) ? 1.0 : 0.0;
+        double P[4], Q[5];
+        profile_row(c, sT, P, Q);
+#pragma unroll
+        for (int k = 0; k < 4; k++) sRow[tid][k] = make_double2(P[k], Q[k]);
+        sRow[tid][4] = make_double2(0.0, Q[4]);
     }
 
     for (;;) {
@@ -294,14 +307,8 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
             int b = 4;
             if (x < D) b = fl[x];
             else if (x >= D + gp) b = fl[D + (x - D - gp)];
-            double c[5];
 #pragma unroll
-            for (int k = 0; k < 5; k++) c[k] = (k == b) ? 1.0 : 0.0;
-            double P[4], Q[5];
-            profile_row(c, sT, P, Q);
-#pragma unroll
-            for (int k = 0; k < 4; k++) s.pq[k * nrs + xr] = make_double2(P[k], Q[k]);
-            s.pq[4 * nrs + xr] = make_double2(0.0, Q[4]);
+            for (int k = 0; k < 5; k++) s.pq[k * nrs + xr] = sRow[b][k];
         }
         for (int i = tid; i < gp; i += FB_THREADS) {
 #pragma unroll
@@ -312,12 +319,14 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
         const int nchunks = (nrec + CH - 1) / CH;
         const int nrb = (gp + 127) >> 7;              // M-step row blocks of 128 rows
         const int nblk = (PS + 63) >> 6;              // E-step blocks of 64 placements per record
+        const bool keep_staged = nchunks <= 3;        // every chunk owns one of the three stage buffers for the whole unit
         int round = 0;                                // global round counter: selects the queue slot
         for (int it = 0; it < p.num_iter; it++) {
             const bool last = it == p.num_iter - 1;
-            // rounds of the pipeline: stage chunk r | E-step chunk r-1 | M-step chunk r-2
-            for (int r = 0; r < nchunks + 2; r++, round++) {
-                const int cl = r, ce = r - 1, cm = r - 2;
+            // rounds of the pipeline: stage chunk r+1 | E-step chunk r | M-step chunk r-1   (r = -1 stages chunk 0)
+            for (int r = ((it == 0 || !keep_staged) ? -1 : 0); r <= nchunks; r++, round++) {
+                const int cl = r + 1, ce = r, cm = r - 1;
+                const bool full_stage = it == 0 || !keep_staged;       // otherwise only the per-record maximum is reset
                 const int n_l = cl < nchunks ? min(CH, nrec - cl * CH) : 0;
                 const int n_e = (ce >= 0 && ce < nchunks) ? min(CH, nrec - ce * CH) : 0;
                 const int n_m = (cm >= 0 && cm < nchunks) ? min(CH, nrec - cm * CH) : 0;
@@ -344,19 +353,29 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
                         double* cr = s.cnt + c * gps + xg;
                         double a0 = ok0 ? cr[0] : 0.0, a1 = ok1 ? cr[32] : 0.0, a2 = ok2 ? cr[64] : 0.0, a3 = ok3 ? cr[96] : 0.0;
                         const unsigned wM_s = (unsigned)__cvta_generic_to_shared(wM);
+                        // per-record set-up, one record per lane: window, and the exact sub-range [qs, qe) of its class list whose
+                        // positions put some row of this block inside the window (two popcounts)
+                        int v_lo = 0, v_len = 0, v_qs = 0, v_qe = 0;
+                        if (lane < n_m) {
+                            const int lo = SM.rlo[lane], hi = SM.rhi[lane];
+                            const int L2 = SM.rfl[lane] & 0xff;
+                            const int jhi = min(L2 - 1, x0 + 127 - lo), jlo = max(0, x0 - hi);
+                            if (hi >= lo && jhi >= jlo) {
+                                const uint32_t* mk = SM.mask + lane * 20 + c * 4;
+                                const uint8_t* cum = SM.cum + lane * 32;
+                                const int wh = jhi >> 5, wl = jlo >> 5;
+                                v_qs = cum[c * 4 + wh] + __popc((mk[wh] >> (jhi & 31)) >> 1);
+                                v_qe = (wl == 0 ? cum[20 + c] : cum[c * 4 + wl - 1]) - __popc(mk[wl] & ((1u << (jlo & 31)) - 1u));
+                                v_lo = lo;
+                                v_len = hi - lo + 1;
+                            }
+                        }
                         for (int rl = 0; rl < n_m; rl++) {
-                            const int lo = SM.rlo[rl], hi = SM.rhi[rl];
-                            const int L2 = SM.rfl[rl] & 0xff;
-                            const int jhi = min(L2 - 1, x0 + 127 - lo), jlo = max(0, x0 - hi);   // j with any row of the block inside [lo, hi]
-                            if (hi < lo || jhi < jlo) continue;
-                            // exact sub-range of the class list: skip positions above jhi and below jlo
-                            const uint32_t* mk = SM.mask + rl * 20 + c * 4;
-                            const uint8_t* cum = SM.cum + rl * 32;
-                            const int wh = jhi >> 5, wl = jlo >> 5;
-                            const int qs = cum[c * 4 + wh] + __popc((mk[wh] >> (jhi & 31)) >> 1);
-                            const int qe = (wl == 0 ? cum[20 + c] : cum[c * 4 + wl - 1]) - __popc(mk[wl] & ((1u << (jlo & 31)) - 1u));
+                            const int qs = __shfl_sync(0xffffffffu, v_qs, rl), qe = __shfl_sync(0xffffffffu, v_qe, rl);
+                            if (qs >= qe) continue;
+                            const int lo = __shfl_sync(0xffffffffu, v_lo, rl);
+                            const unsigned len = (unsigned)__shfl_sync(0xffffffffu, v_len, rl);
                             const uint8_t* jl = SM.jl + rl * FB_MAX_READ;
-                            const unsigned len = (unsigned)(hi - lo) + 1u;
                             const unsigned l0 = ok0 ? len : 0u, l1 = ok1 ? len : 0u, l2 = ok2 ? len : 0u, l3 = ok3 ? len : 0u;
                             const int xlo = x0 + lane - lo;
                             const unsigned wbase = wM_s + (unsigned)(rl * PS + xlo) * 8u;
@@ -405,6 +424,10 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
                     } else {
                         // ---- stage one record: placement window, class bit-masks, per-position table offsets
                         const int rl = task - tM - tE;
+                        if (!full_stage) {               // the staged tables of this chunk are still in place: new iteration, new maximum
+                            if (lane == 0) SL.rmax[rl] = 0ull;
+                            continue;
+                        }
                         const int rec = gm.rec_off + cl * CH + rl;
                         const FbRecMeta rm = p.rmeta[rec];
                         const int L2 = rm.flags & 0xff;
@@ -468,6 +491,8 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
                 __syncthreads();
             }
 
+            // chunk 0 of a kept staging gets its per-record maxima reset here, a barrier ahead of the next iteration's E tasks
+            if (keep_staged && !last && tid < min(CH, nrec)) stage_at(s, 0).rmax[tid] = 0ull;
             // ---- computeProbsGap + computeErrorProbsGap on the gap rows (flank rows never change)
             for (int xg = tid; xg < gp; xg += FB_THREADS) {
                 double c[5];
