@@ -177,15 +177,14 @@ __device__ __forceinline__ void load_record_bytes(const uint4* __restrict__ code
 // E-step of 64 placements of one record: lane owns placements ua and ua+32 (two independent product chains).
 // The running score is multiplied base by base in read order (figbird.cpp:1840-1864); REV selects the
 // read-position index k = L2-1-j of a reverse-complemented mate (figbird.cpp:1845-1852).
-// M-step inner step for one list entry: a lane owns four gap rows 32 apart (four independent accumulators, so four
-// add chains are in flight).  Row t's placement offset is uoff0 + 32t; it contributes when that offset lies inside the
-// record's window (lim[t] = window length, or 0 for a row past the gap).  Rows outside add +0.0, which is exact here:
-// the accumulators are sums of non-negative scores (or NaN) and never -0.0.
-__device__ __forceinline__ void add4_if_inside(double& a0, double& a1, double& a2, double& a3, unsigned saddr0, unsigned uoff0,
-                                               unsigned lim0, unsigned lim1, unsigned lim2, unsigned lim3) {
+// M-step loads for one list entry: a lane owns four gap rows 32 apart.  Row t's placement offset is uoff0 + 32t; its
+// score is fetched when that offset lies inside the record's window (lim t = window length, or 0 for a row past the
+// gap) and is +0.0 otherwise — adding +0.0 is exact here: the accumulators are sums of non-negative scores (or NaN),
+// never -0.0.  Loads and adds are separate so that the loads of later entries can be in flight during the adds.
+__device__ __forceinline__ void load4_in_window(double& v0, double& v1, double& v2, double& v3, unsigned saddr0, unsigned uoff0,
+                                                unsigned lim0, unsigned lim1, unsigned lim2, unsigned lim3) {
     asm("{\n\t"
         ".reg .pred p0, p1, p2, p3;\n\t"
-        ".reg .f64 v0, v1, v2, v3;\n\t"
         ".reg .u32 u1, u2, u3;\n\t"
         "add.u32 u1, %5, 32;\n\t"
         "add.u32 u2, %5, 64;\n\t"
@@ -194,20 +193,16 @@ __device__ __forceinline__ void add4_if_inside(double& a0, double& a1, double& a
         "setp.lt.u32 p1, u1, %7;\n\t"
         "setp.lt.u32 p2, u2, %8;\n\t"
         "setp.lt.u32 p3, u3, %9;\n\t"
-        "mov.f64 v0, 0d0000000000000000;\n\t"
-        "mov.f64 v1, 0d0000000000000000;\n\t"
-        "mov.f64 v2, 0d0000000000000000;\n\t"
-        "mov.f64 v3, 0d0000000000000000;\n\t"
-        "@p0 ld.shared.f64 v0, [%4];\n\t"
-        "@p1 ld.shared.f64 v1, [%4+256];\n\t"
-        "@p2 ld.shared.f64 v2, [%4+512];\n\t"
-        "@p3 ld.shared.f64 v3, [%4+768];\n\t"
-        "add.rn.f64 %0, %0, v0;\n\t"
-        "add.rn.f64 %1, %1, v1;\n\t"
-        "add.rn.f64 %2, %2, v2;\n\t"
-        "add.rn.f64 %3, %3, v3;\n\t"
+        "mov.f64 %0, 0d0000000000000000;\n\t"
+        "mov.f64 %1, 0d0000000000000000;\n\t"
+        "mov.f64 %2, 0d0000000000000000;\n\t"
+        "mov.f64 %3, 0d0000000000000000;\n\t"
+        "@p0 ld.shared.f64 %0, [%4];\n\t"
+        "@p1 ld.shared.f64 %1, [%4+256];\n\t"
+        "@p2 ld.shared.f64 %2, [%4+512];\n\t"
+        "@p3 ld.shared.f64 %3, [%4+768];\n\t"
         "}"
-        : "+d"(a0), "+d"(a1), "+d"(a2), "+d"(a3)
+        : "=&d"(v0), "=&d"(v1), "=&d"(v2), "=&d"(v3)
         : "r"(saddr0), "r"(uoff0), "r"(lim0), "r"(lim1), "r"(lim2), "r"(lim3));
 }
 
@@ -379,10 +374,17 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
                             const unsigned l0 = ok0 ? len : 0u, l1 = ok1 ? len : 0u, l2 = ok2 ? len : 0u, l3 = ok3 ? len : 0u;
                             const int xlo = x0 + lane - lo;
                             const unsigned wbase = wM_s + (unsigned)(rl * PS + xlo) * 8u;
-#pragma unroll 2
+                            // loads and adds are separate statements: with the loop unrolled, the list bytes and the score loads of
+                            // several entries are issued before the first add, so only the adds form the dependent chain
+#pragma unroll 4
                             for (int q = qs; q < qe; q++) {
                                 const unsigned j = jl[q];
-                                add4_if_inside(a0, a1, a2, a3, wbase - j * 8u, (unsigned)xlo - j, l0, l1, l2, l3);   // figbird.cpp:1879
+                                double v0, v1, v2, v3;
+                                load4_in_window(v0, v1, v2, v3, wbase - j * 8u, (unsigned)xlo - j, l0, l1, l2, l3);
+                                a0 = dadd(a0, v0);   // figbird.cpp:1879
+                                a1 = dadd(a1, v1);
+                                a2 = dadd(a2, v2);
+                                a3 = dadd(a3, v3);
                             }
                         }
                         if (ok0) cr[0] = a0;
