@@ -70,6 +70,7 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
 // meet at ONE barrier per round.
 // ---------------------------------------------------------------------------------------------------
 constexpr int kPadRows = 32;   // a lane's second placement sits 32 rows further; invalid lanes may read (not use) past the end
+constexpr int kPadW = 64;      // zeros either side of every score row: the M-step reads up to 63 placements outside a window
 
 struct Stage {
     int* rlo;
@@ -78,7 +79,7 @@ struct Stage {
     int* rfl;
     unsigned long long* rmax;
     uint32_t* mask;   // [chunk][5][4] bit j of class c: base j of the record is c
-    uint32_t* off;    // [chunk][128] byte offset of class(base j) inside pq
+    uint32_t* cls4;   // [chunk][16]  base classes, 4 bits each (8 per word), in scoring orientation
     uint8_t* jl;      // [chunk][128] read positions sorted by (class asc, position DESC)
     uint8_t* cum;     // [chunk][32]  cum[c*4+w] = index in jl of the first position of class c that lies in mask word <= w
                       //              (i.e. class start + number of class-c positions in words above w); cum[20+c] = class end
@@ -106,8 +107,8 @@ __device__ __forceinline__ Stage stage_at(const EmSmem& s, int k) {
     t.rtb = t.rhi + s.chunk;
     t.rfl = t.rtb + s.chunk;
     t.mask = reinterpret_cast<uint32_t*>(t.rfl + s.chunk);
-    t.off = t.mask + 20 * s.chunk;
-    t.jl = reinterpret_cast<uint8_t*>(t.off + FB_MAX_READ * s.chunk);
+    t.cls4 = t.mask + 20 * s.chunk;
+    t.jl = reinterpret_cast<uint8_t*>(t.cls4 + 16 * s.chunk);
     t.cum = t.jl + FB_MAX_READ * s.chunk;
     return t;
 }
@@ -128,12 +129,13 @@ __host__ __device__ inline size_t em_carve(unsigned char* base, EmSmem* s, int n
         a = take(sizeof(double2) * (5 * (size_t)nr_stride + kPadRows)); if (s) s->pq = (double2*)a;
         a = take(sizeof(double) * 5 * (size_t)gp_stride); if (s) s->cnt = (double*)a;
     }
-    const size_t wbytes = align16(sizeof(double) * (size_t)chunk * p_stride);
+    // a score buffer: kPadW zeros, then per record slot [p_stride scores][kPadW zeros]; neighbouring rows share a pad
+    const size_t wbytes = align16(sizeof(double) * ((size_t)kPadW + (size_t)chunk * (p_stride + kPadW)));
     a = take(2 * wbytes);
     if (s) { s->w0 = (double*)a; s->w_stride = wbytes / sizeof(double); }
-    // one staged chunk: rmax[chunk] u64 | rlo, rhi, rtb, rfl [chunk] int | mask[chunk][20] u32 | off[chunk][128] u32 |
+    // one staged chunk: rmax[chunk] u64 | rlo, rhi, rtb, rfl [chunk] int | mask[chunk][20] u32 | cls4[chunk][16] u32 |
     //                   jl[chunk][128] u8 | cum[chunk][32] u8
-    const size_t sbytes = align16((size_t)chunk * (8 + 4 * 4 + 20 * 4 + FB_MAX_READ * 4 + FB_MAX_READ + 32));
+    const size_t sbytes = align16((size_t)chunk * (8 + 4 * 4 + 20 * 4 + 16 * 4 + FB_MAX_READ + 32));
     a = take(3 * sbytes);
     if (s) { s->st0 = a; s->st_stride = sbytes; s->chunk = chunk; }
     return off;
@@ -177,46 +179,16 @@ __device__ __forceinline__ void load_record_bytes(const uint4* __restrict__ code
 // E-step of 64 placements of one record: lane owns placements ua and ua+32 (two independent product chains).
 // The running score is multiplied base by base in read order (figbird.cpp:1840-1864); REV selects the
 // read-position index k = L2-1-j of a reverse-complemented mate (figbird.cpp:1845-1852).
-// M-step loads for one list entry: a lane owns four gap rows 32 apart.  Row t's placement offset is uoff0 + 32t; its
-// score is fetched when that offset lies inside the record's window (lim t = window length, or 0 for a row past the
-// gap) and is +0.0 otherwise — adding +0.0 is exact here: the accumulators are sums of non-negative scores (or NaN),
-// never -0.0.  Loads and adds are separate so that the loads of later entries can be in flight during the adds.
-__device__ __forceinline__ void load4_in_window(double& v0, double& v1, double& v2, double& v3, unsigned saddr0, unsigned uoff0,
-                                                unsigned lim0, unsigned lim1, unsigned lim2, unsigned lim3) {
-    asm("{\n\t"
-        ".reg .pred p0, p1, p2, p3;\n\t"
-        ".reg .u32 u1, u2, u3;\n\t"
-        "add.u32 u1, %5, 32;\n\t"
-        "add.u32 u2, %5, 64;\n\t"
-        "add.u32 u3, %5, 96;\n\t"
-        "setp.lt.u32 p0, %5, %6;\n\t"
-        "setp.lt.u32 p1, u1, %7;\n\t"
-        "setp.lt.u32 p2, u2, %8;\n\t"
-        "setp.lt.u32 p3, u3, %9;\n\t"
-        "mov.f64 %0, 0d0000000000000000;\n\t"
-        "mov.f64 %1, 0d0000000000000000;\n\t"
-        "mov.f64 %2, 0d0000000000000000;\n\t"
-        "mov.f64 %3, 0d0000000000000000;\n\t"
-        "@p0 ld.shared.f64 %0, [%4];\n\t"
-        "@p1 ld.shared.f64 %1, [%4+256];\n\t"
-        "@p2 ld.shared.f64 %2, [%4+512];\n\t"
-        "@p3 ld.shared.f64 %3, [%4+768];\n\t"
-        "}"
-        : "=&d"(v0), "=&d"(v1), "=&d"(v2), "=&d"(v3)
-        : "r"(saddr0), "r"(uoff0), "r"(lim0), "r"(lim1), "r"(lim2), "r"(lim3));
-}
-
 template <bool REV, bool TWO>
-__device__ __forceinline__ void score_pair(const unsigned char* pa, const uint32_t* __restrict__ off, const FbEmParams& p,
+__device__ __forceinline__ void score_pair(const unsigned char* pa, const uint32_t* __restrict__ cls4, unsigned cstride, const FbEmParams& p,
                                            int L2, double& sa, double& sb) {
     int k = REV ? L2 - 1 : 0;    // read-position index of base j (figbird.cpp:1845-1852)
     int j0 = 0;
     for (; j0 + 4 <= L2; j0 += 4) {
-        const uint4 o = *reinterpret_cast<const uint4*>(off + j0);
-        const uint32_t oo[4] = {o.x, o.y, o.z, o.w};
+        const uint32_t cw = cls4[j0 >> 3] >> ((j0 & 4) * 4);                // four base classes, 4 bits each
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            const unsigned char* a = pa + oo[q] + q * 16;
+            const unsigned char* a = pa + ((cw >> (4 * q)) & 7u) * cstride + q * 16;   // class table of this base, row of this placement
             const double2 va = *reinterpret_cast<const double2*>(a);
             const double2 e = p.eo_tab[REV ? k - q : k + q];                // {1 - e[k], e[k]} via the constant cache
             sa = dmul(sa, dadd(dmul(va.x, e.x), dmul(e.y, va.y)));          // figbird.cpp:1855 / 1862
@@ -229,7 +201,8 @@ __device__ __forceinline__ void score_pair(const unsigned char* pa, const uint32
         k += REV ? -4 : 4;
     }
     for (; j0 < L2; j0++) {
-        const unsigned char* a = pa + off[j0];
+        const unsigned c = (cls4[j0 >> 3] >> ((j0 & 7) * 4)) & 7u;
+        const unsigned char* a = pa + c * cstride;
         const double2 va = *reinterpret_cast<const double2*>(a);
         const double2 e = p.eo_tab[k];
         sa = dmul(sa, dadd(dmul(va.x, e.x), dmul(e.y, va.y)));
@@ -266,6 +239,9 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
     if (GT) {
         for (int i = tid; i < kPadRows; i += FB_THREADS) s.pq[5 * (size_t)p.nr_stride + i] = make_double2(0.0, 0.0);
     }
+    // score buffers start as zeros; E tasks only ever write the p_stride slots of their row, so the pads between rows
+    // stay zero for the life of the kernel
+    for (size_t i = tid; i < 2 * s.w_stride; i += FB_THREADS) s.w0[i] = 0.0;
     __syncthreads();
     if (tid < 5) {
         // initialize() only ever produces five different rows (figbird.cpp:1657-1673): compute them once
@@ -312,8 +288,9 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
         __syncthreads();
 
         const int nchunks = (nrec + CH - 1) / CH;
-        const int nrb = (gp + 127) >> 7;              // M-step row blocks of 128 rows
+        const int nrb = (gp + 63) >> 6;               // M-step row blocks of 64 rows (two per lane)
         const int nblk = (PS + 63) >> 6;              // E-step blocks of 64 placements per record
+        const int WS = PS + kPadW;                    // score-row stride: the pad after a row is the pad before the next
         const bool keep_staged = nchunks <= 3;        // every chunk owns one of the three stage buffers for the whole unit
         int round = 0;                                // global round counter: selects the queue slot
         for (int it = 0; it < p.num_iter; it++) {
@@ -339,22 +316,24 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
                     task = __shfl_sync(0xffffffffu, task, 0);
                     if (task >= ntask) break;
                     if (task < tM) {
-                        // ---- M-step: a lane owns four gap rows (32 apart), a warp one (128 rows, base class) cell block.  Within a
-                        // cell the CPU adds in (record asc, placement asc) order (figbird.cpp:1718, 1826, 1874): walking a record's
-                        // class list from high j to low j visits its placements in ascending order.
+                        // ---- M-step: a lane owns two gap rows (32 apart), a warp one (64 rows, base class) cell block.  Within a cell
+                        // the CPU adds in (record asc, placement asc) order (figbird.cpp:1718, 1826, 1874): walking a record's class
+                        // list from high j to low j visits its placements in ascending order.  Score rows are zero outside the
+                        // record's window (pads + zero-filled tail), so a row that is not inside the window for some entry adds
+                        // +0.0 — exact: the accumulators are sums of non-negative scores (or NaN), never -0.0 — and the loop
+                        // needs no predicates: per entry one list byte, and per row one LDS.64 + DADD.
                         const int c = task / nrb, rb = task - c * nrb;
-                        const int xg = rb * 128 + lane, x0 = D + rb * 128;
-                        const bool ok0 = xg < gp, ok1 = xg + 32 < gp, ok2 = xg + 64 < gp, ok3 = xg + 96 < gp;
+                        const int xg = rb * 64 + lane, x0 = D + rb * 64;
+                        const bool ok0 = xg < gp, ok1 = xg + 32 < gp;
                         double* cr = s.cnt + c * gps + xg;
-                        double a0 = ok0 ? cr[0] : 0.0, a1 = ok1 ? cr[32] : 0.0, a2 = ok2 ? cr[64] : 0.0, a3 = ok3 ? cr[96] : 0.0;
-                        const unsigned wM_s = (unsigned)__cvta_generic_to_shared(wM);
-                        // per-record set-up, one record per lane: window, and the exact sub-range [qs, qe) of its class list whose
-                        // positions put some row of this block inside the window (two popcounts)
-                        int v_lo = 0, v_len = 0, v_qs = 0, v_qe = 0;
+                        double a0 = ok0 ? cr[0] : 0.0, a1 = ok1 ? cr[32] : 0.0;     // rows past the gap accumulate junk that is never stored
+                        // per-record set-up, one record per lane: the exact sub-range [qs, qe) of its class list whose positions
+                        // put some row of this block inside the window (two popcounts)
+                        int v_lo = 0, v_qs = 0, v_qe = 0;
                         if (lane < n_m) {
                             const int lo = SM.rlo[lane], hi = SM.rhi[lane];
                             const int L2 = SM.rfl[lane] & 0xff;
-                            const int jhi = min(L2 - 1, x0 + 127 - lo), jlo = max(0, x0 - hi);
+                            const int jhi = min(L2 - 1, x0 + 63 - lo), jlo = max(0, x0 - hi);
                             if (hi >= lo && jhi >= jlo) {
                                 const uint32_t* mk = SM.mask + lane * 20 + c * 4;
                                 const uint8_t* cum = SM.cum + lane * 32;
@@ -362,62 +341,58 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
                                 v_qs = cum[c * 4 + wh] + __popc((mk[wh] >> (jhi & 31)) >> 1);
                                 v_qe = (wl == 0 ? cum[20 + c] : cum[c * 4 + wl - 1]) - __popc(mk[wl] & ((1u << (jlo & 31)) - 1u));
                                 v_lo = lo;
-                                v_len = hi - lo + 1;
                             }
                         }
+                        const double* wrow0 = wM + kPadW + x0 + lane;
                         for (int rl = 0; rl < n_m; rl++) {
                             const int qs = __shfl_sync(0xffffffffu, v_qs, rl), qe = __shfl_sync(0xffffffffu, v_qe, rl);
                             if (qs >= qe) continue;
                             const int lo = __shfl_sync(0xffffffffu, v_lo, rl);
-                            const unsigned len = (unsigned)__shfl_sync(0xffffffffu, v_len, rl);
                             const uint8_t* jl = SM.jl + rl * FB_MAX_READ;
-                            const unsigned l0 = ok0 ? len : 0u, l1 = ok1 ? len : 0u, l2 = ok2 ? len : 0u, l3 = ok3 ? len : 0u;
-                            const int xlo = x0 + lane - lo;
-                            const unsigned wbase = wM_s + (unsigned)(rl * PS + xlo) * 8u;
-                            // loads and adds are separate statements: with the loop unrolled, the list bytes and the score loads of
-                            // several entries are issued before the first add, so only the adds form the dependent chain
-#pragma unroll 4
+                            const double* wr = wrow0 + rl * WS - lo;              // wr[-j] = score of placement (row - j) of this record
+#pragma unroll 8
                             for (int q = qs; q < qe; q++) {
-                                const unsigned j = jl[q];
-                                double v0, v1, v2, v3;
-                                load4_in_window(v0, v1, v2, v3, wbase - j * 8u, (unsigned)xlo - j, l0, l1, l2, l3);
-                                a0 = dadd(a0, v0);   // figbird.cpp:1879
-                                a1 = dadd(a1, v1);
-                                a2 = dadd(a2, v2);
-                                a3 = dadd(a3, v3);
+                                const int j = jl[q];
+                                a0 = dadd(a0, wr[-j]);        // figbird.cpp:1879
+                                a1 = dadd(a1, wr[32 - j]);
                             }
                         }
                         if (ok0) cr[0] = a0;
                         if (ok1) cr[32] = a1;
-                        if (ok2) cr[64] = a2;
-                        if (ok3) cr[96] = a3;
                     } else if (task < tM + tE) {
-                        // ---- E-step: warp per (record, 64 placements); lanes over placements
+                        // ---- E-step: warp per (record, 64 placements); lanes over placements.  Every slot of the record's score row is
+                        // written: the score inside the window, 0.0 outside it (the M-step relies on those zeros).
                         const int te = task - tM;
                         const int rl = te / nblk, blk = te - rl * nblk;
                         const int lo = SE.rlo[rl], hi = SE.rhi[rl];
-                        if (lo + 64 * blk > hi) continue;
+                        double* wrow = wE + kPadW + rl * WS;                  // slot k holds placement lo + k
+                        const int ka = 64 * blk + lane, kb = ka + 32;
+                        if (lo + 64 * blk > hi) {                              // nothing of the window in this block (or no window at all)
+                            if (ka < PS) wrow[ka] = 0.0;
+                            if (kb < PS) wrow[kb] = 0.0;
+                            continue;
+                        }
                         const int fl2 = SE.rfl[rl], L2 = fl2 & 0xff, tb = SE.rtb[rl];
                         const bool rev = (fl2 >> 8) & 1, left = (fl2 >> 9) & 1;
-                        const int ua = lo + 64 * blk + lane, ub = ua + 32;
+                        const int ua = lo + ka, ub = ua + 32;
                         const bool va_ok = ua <= hi, vb_ok = ub <= hi;
                         const int uc = va_ok ? ua : lo;                      // invalid lanes shadow a valid placement
                         const int ta = left ? uc + tb : tb - uc;
                         const int tbb = vb_ok ? (left ? ub + tb : tb - ub) : ta;
                         double sa = s.ild[ta - p.thr_min], sb = s.ild[tbb - p.thr_min];
                         const unsigned char* pa = reinterpret_cast<const unsigned char*>(s.pq + (uc - R0));
-                        const uint32_t* off = SE.off + rl * FB_MAX_READ;
+                        const uint32_t* cls4 = SE.cls4 + rl * 16;
+                        const unsigned cstride = (unsigned)nrs * 16u;
                         const bool two = lo + 64 * blk + 32 <= hi;           // any lane with a second placement?
                         if (two) {
-                            if (rev) score_pair<true, true>(pa, off, p, L2, sa, sb);
-                            else score_pair<false, true>(pa, off, p, L2, sa, sb);
+                            if (rev) score_pair<true, true>(pa, cls4, cstride, p, L2, sa, sb);
+                            else score_pair<false, true>(pa, cls4, cstride, p, L2, sa, sb);
                         } else {
-                            if (rev) score_pair<true, false>(pa, off, p, L2, sa, sb);
-                            else score_pair<false, false>(pa, off, p, L2, sa, sb);
+                            if (rev) score_pair<true, false>(pa, cls4, cstride, p, L2, sa, sb);
+                            else score_pair<false, false>(pa, cls4, cstride, p, L2, sa, sb);
                         }
-                        double* wrow = wE + rl * PS - lo;
-                        if (va_ok) wrow[ua] = sa;
-                        if (vb_ok) wrow[ub] = sb;
+                        if (ka < PS) wrow[ka] = va_ok ? sa : 0.0;
+                        if (kb < PS) wrow[kb] = vb_ok ? sb : 0.0;
                         // tempProb > maxProb with maxProb starting at 0: NaN and non-positive scores never win
                         unsigned long long ba = (va_ok && sa > 0.0) ? (unsigned long long)__double_as_longlong(sa) : 0ull;
                         unsigned long long bb = (vb_ok && sb > 0.0) ? (unsigned long long)__double_as_longlong(sb) : 0ull;
@@ -435,12 +410,12 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
                         const int L2 = rm.flags & 0xff;
                         unsigned cls[4];
                         fetch_classes(p.codes, p.nmask, rec, L2, lane, cls);
-                        uint4 o;
-                        o.x = min(cls[0], 4u) * (unsigned)nrs * 16u;
-                        o.y = min(cls[1], 4u) * (unsigned)nrs * 16u;
-                        o.z = min(cls[2], 4u) * (unsigned)nrs * 16u;
-                        o.w = min(cls[3], 4u) * (unsigned)nrs * 16u;
-                        reinterpret_cast<uint4*>(SL.off + rl * FB_MAX_READ)[lane] = o;
+                        {
+                            // four classes of this lane -> 16 bits; two lanes make one 32-bit word (8 bases)
+                            const unsigned nib4 = min(cls[0], 4u) | (min(cls[1], 4u) << 4) | (min(cls[2], 4u) << 8) | (min(cls[3], 4u) << 12);
+                            const unsigned hi16 = __shfl_down_sync(0xffffffffu, nib4, 1);
+                            if ((lane & 1) == 0) SL.cls4[rl * 16 + (lane >> 1)] = nib4 | (hi16 << 16);
+                        }
                         const unsigned grp = 0xffu << (lane & 24);           // the 8 lanes sharing one 32-bit mask word
 #pragma unroll
                         for (int c = 0; c < 5; c++) {
