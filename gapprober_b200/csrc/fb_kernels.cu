@@ -70,7 +70,8 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
 // meet at ONE barrier per round.
 // ---------------------------------------------------------------------------------------------------
 constexpr int kPadRows = 32;   // a lane's second placement sits 32 rows further; invalid lanes may read (not use) past the end
-constexpr int kPadW = 64;      // zeros either side of every score row: the M-step reads up to 63 placements outside a window
+constexpr int kListBytes = FB_MAX_READ + 16;   // per record: class-sorted position lists, each class starting 4-aligned
+constexpr int kPadW = 32;      // zeros either side of every score row: the M-step reads up to 31 placements outside a window
 
 struct Stage {
     int* rlo;
@@ -80,7 +81,7 @@ struct Stage {
     unsigned long long* rmax;
     uint32_t* mask;   // [chunk][5][4] bit j of class c: base j of the record is c
     uint32_t* cls4;   // [chunk][16]  base classes, 4 bits each (8 per word), in scoring orientation
-    uint8_t* jl;      // [chunk][128] read positions sorted by (class asc, position DESC)
+    uint8_t* jl;      // [chunk][kListBytes] read positions sorted by (class asc, position DESC), class segments 4-aligned
     uint8_t* cum;     // [chunk][32]  cum[c*4+w] = index in jl of the first position of class c that lies in mask word <= w
                       //              (i.e. class start + number of class-c positions in words above w); cum[20+c] = class end
 };
@@ -109,7 +110,7 @@ __device__ __forceinline__ Stage stage_at(const EmSmem& s, int k) {
     t.mask = reinterpret_cast<uint32_t*>(t.rfl + s.chunk);
     t.cls4 = t.mask + 20 * s.chunk;
     t.jl = reinterpret_cast<uint8_t*>(t.cls4 + 16 * s.chunk);
-    t.cum = t.jl + FB_MAX_READ * s.chunk;
+    t.cum = t.jl + kListBytes * s.chunk;
     return t;
 }
 
@@ -135,7 +136,7 @@ __host__ __device__ inline size_t em_carve(unsigned char* base, EmSmem* s, int n
     if (s) { s->w0 = (double*)a; s->w_stride = wbytes / sizeof(double); }
     // one staged chunk: rmax[chunk] u64 | rlo, rhi, rtb, rfl [chunk] int | mask[chunk][20] u32 | cls4[chunk][16] u32 |
     //                   jl[chunk][128] u8 | cum[chunk][32] u8
-    const size_t sbytes = align16((size_t)chunk * (8 + 4 * 4 + 20 * 4 + 16 * 4 + FB_MAX_READ + 32));
+    const size_t sbytes = align16((size_t)chunk * (8 + 4 * 4 + 20 * 4 + 16 * 4 + kListBytes + 32));
     a = take(3 * sbytes);
     if (s) { s->st0 = a; s->st_stride = sbytes; s->chunk = chunk; }
     return off;
@@ -288,7 +289,7 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
         __syncthreads();
 
         const int nchunks = (nrec + CH - 1) / CH;
-        const int nrb = (gp + 63) >> 6;               // M-step row blocks of 64 rows (two per lane)
+        const int nrb = (gp + 31) >> 5;               // M-step row blocks of 32 rows
         const int nblk = (PS + 63) >> 6;              // E-step blocks of 64 placements per record
         const int WS = PS + kPadW;                    // score-row stride: the pad after a row is the pad before the next
         const bool keep_staged = nchunks <= 3;        // every chunk owns one of the three stage buffers for the whole unit
@@ -316,24 +317,24 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
                     task = __shfl_sync(0xffffffffu, task, 0);
                     if (task >= ntask) break;
                     if (task < tM) {
-                        // ---- M-step: a lane owns two gap rows (32 apart), a warp one (64 rows, base class) cell block.  Within a cell
-                        // the CPU adds in (record asc, placement asc) order (figbird.cpp:1718, 1826, 1874): walking a record's class
-                        // list from high j to low j visits its placements in ascending order.  Score rows are zero outside the
-                        // record's window (pads + zero-filled tail), so a row that is not inside the window for some entry adds
-                        // +0.0 — exact: the accumulators are sums of non-negative scores (or NaN), never -0.0 — and the loop
-                        // needs no predicates: per entry one list byte, and per row one LDS.64 + DADD.
+                        // ---- M-step: a lane owns one gap row, a warp one (32 rows, base class) cell block.  Within a cell the CPU adds in
+                        // (record asc, placement asc) order (figbird.cpp:1718, 1826, 1874): walking a record's class list from high j
+                        // to low j visits its placements in ascending order.  Score rows are zero outside the record's window (pads +
+                        // zero-filled tail), so a row that is not inside the window for some entry adds +0.0 — exact: the
+                        // accumulators are sums of non-negative scores (or NaN), never -0.0 — and the loop needs no predicates:
+                        // per entry one LDS.64 + DADD, list positions fetched four at a time.
                         const int c = task / nrb, rb = task - c * nrb;
-                        const int xg = rb * 64 + lane, x0 = D + rb * 64;
-                        const bool ok0 = xg < gp, ok1 = xg + 32 < gp;
+                        const int xg = rb * 32 + lane, x0 = D + rb * 32;
+                        const bool ok0 = xg < gp;
                         double* cr = s.cnt + c * gps + xg;
-                        double a0 = ok0 ? cr[0] : 0.0, a1 = ok1 ? cr[32] : 0.0;     // rows past the gap accumulate junk that is never stored
+                        double a0 = ok0 ? cr[0] : 0.0;                             // rows past the gap accumulate junk that is never stored
                         // per-record set-up, one record per lane: the exact sub-range [qs, qe) of its class list whose positions
                         // put some row of this block inside the window (two popcounts)
                         int v_lo = 0, v_qs = 0, v_qe = 0;
                         if (lane < n_m) {
                             const int lo = SM.rlo[lane], hi = SM.rhi[lane];
                             const int L2 = SM.rfl[lane] & 0xff;
-                            const int jhi = min(L2 - 1, x0 + 63 - lo), jlo = max(0, x0 - hi);
+                            const int jhi = min(L2 - 1, x0 + 31 - lo), jlo = max(0, x0 - hi);
                             if (hi >= lo && jhi >= jlo) {
                                 const uint32_t* mk = SM.mask + lane * 20 + c * 4;
                                 const uint8_t* cum = SM.cum + lane * 32;
@@ -348,17 +349,20 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
                             const int qs = __shfl_sync(0xffffffffu, v_qs, rl), qe = __shfl_sync(0xffffffffu, v_qe, rl);
                             if (qs >= qe) continue;
                             const int lo = __shfl_sync(0xffffffffu, v_lo, rl);
-                            const uint8_t* jl = SM.jl + rl * FB_MAX_READ;
+                            const uint8_t* jl = SM.jl + rl * kListBytes;
                             const double* wr = wrow0 + rl * WS - lo;              // wr[-j] = score of placement (row - j) of this record
-#pragma unroll 8
-                            for (int q = qs; q < qe; q++) {
-                                const int j = jl[q];
-                                a0 = dadd(a0, wr[-j]);        // figbird.cpp:1879
-                                a1 = dadd(a1, wr[32 - j]);
+                            int q = qs;
+                            for (; q < qe && (q & 3); q++) a0 = dadd(a0, wr[-(int)jl[q]]);        // figbird.cpp:1879
+#pragma unroll 2
+                            for (; q + 4 <= qe; q += 4) {
+                                const uint32_t j4 = *reinterpret_cast<const uint32_t*>(jl + q);
+                                const double w0 = wr[-(int)(j4 & 0xffu)], w1 = wr[-(int)((j4 >> 8) & 0xffu)];
+                                const double w2 = wr[-(int)((j4 >> 16) & 0xffu)], w3 = wr[-(int)(j4 >> 24)];
+                                a0 = dadd(dadd(dadd(dadd(a0, w0), w1), w2), w3);
                             }
+                            for (; q < qe; q++) a0 = dadd(a0, wr[-(int)jl[q]]);
                         }
                         if (ok0) cr[0] = a0;
-                        if (ok1) cr[32] = a1;
                     } else if (task < tM + tE) {
                         // ---- E-step: warp per (record, 64 placements); lanes over placements.  Every slot of the record's score row is
                         // written: the score inside the window, 0.0 outside it (the M-step relies on those zeros).
@@ -430,7 +434,7 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
                             // class-sorted, position-descending list: slot = class start + (positions of that class above j)
                             const uint32_t* mk = SL.mask + rl * 20;
                             uint8_t* cum = SL.cum + rl * 32;
-                            uint8_t* jl = SL.jl + rl * FB_MAX_READ;
+                            uint8_t* jl = SL.jl + rl * kListBytes;
                             int start = 0;
 #pragma unroll
                             for (int c = 0; c < 5; c++) {
@@ -451,7 +455,7 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
                                         jl[start + (w == 3 ? 0 : w == 2 ? n3 : w == 1 ? n3 + n2 : n3 + n2 + n1) + higher] = (uint8_t)j;
                                     }
                                 }
-                                start += n3 + n2 + n1 + n0;
+                                start = (start + n3 + n2 + n1 + n0 + 3) & ~3;     // next class starts on a 32-bit boundary
                             }
                         }
                         if (lane == 0) {
