@@ -72,9 +72,8 @@ struct HostGap {
     double best_lik = 0;
     int total_reads = 0, discarded = 0;
     long likelihoods = 0;
-    std::string filled, best_string;
+    std::string filled;
     std::vector<double> liks;
-    int unit_first = -1;   // index of the gmin unit in ctx->unit_of (by estimate order)
 };
 
 template <typename T>
