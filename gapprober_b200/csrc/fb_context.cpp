@@ -65,6 +65,8 @@ struct HostGap {
     int orig, gmin, gmax;
     int rec_off, nrec, lmax;
     bool owned = true;
+    std::vector<char> est_owned;        // estimate-level partition: which estimates this context scans (empty = all)
+    std::vector<long long> cons_off;    // per estimate: offset of its consensus on this device, -1 when scanned elsewhere
     double cost = 0;
     // results
     bool done = false;
@@ -163,7 +165,8 @@ struct fb_ctx {
     std::vector<FbUnit> h_units;
     std::vector<int> unit_nrec;
     std::vector<Bin> bins;
-    bool uploaded = false, ran = false;
+    bool uploaded = false, ran = false, scanned = false;
+    bool unit_mode = false;   // partition by (gap, estimate) instead of by gap
 
     // device
     DevBuf<FbGapMeta> d_gapmeta;
@@ -313,7 +316,7 @@ int fb_clear_gaps(fb_ctx* c) {
     if (!c) return FB_EINVAL;
     c->gaps.clear(); c->h_gapmeta.clear(); c->h_flank.clear(); c->h_codes.clear(); c->h_nmask.clear();
     c->h_rmeta.clear(); c->h_bytes.clear(); c->h_units.clear(); c->unit_nrec.clear(); c->bins.clear();
-    c->uploaded = c->ran = false;
+    c->uploaded = c->ran = c->scanned = false;
     return FB_OK;
 }
 
@@ -459,7 +462,7 @@ int append_gap(fb_ctx* c, PackedGap& pk) {
     gm.lmax = pk.g.lmax;
     c->h_gapmeta.push_back(gm);
     c->gaps.push_back(pk.g);
-    c->uploaded = c->ran = false;
+    c->uploaded = c->ran = c->scanned = false;
     return (int)c->gaps.size() - 1;
 }
 
@@ -586,8 +589,42 @@ int fb_set_partition(fb_ctx* c, int rank, int world) {
         cost[i] = c->gaps[i].cost;
     }
     fb_partition_plan(cost.data(), n, world, owner.data());
-    for (int i = 0; i < n; i++) c->gaps[i].owned = owner[i] == rank;
-    c->uploaded = c->ran = false;
+    for (int i = 0; i < n; i++) {
+        c->gaps[i].owned = owner[i] == rank;
+        c->gaps[i].est_owned.clear();
+    }
+    c->unit_mode = false;
+    c->uploaded = c->ran = c->scanned = false;
+    return FB_OK;
+}
+
+int fb_set_partition_units(fb_ctx* c, int rank, int world) {
+    if (!c || world < 1 || rank < 0 || rank >= world) return FB_EINVAL;
+    c->part_rank = rank;
+    c->part_world = world;
+    c->unit_mode = world > 1;
+    // every (gap, estimate) unit is an independent EM run (figbird.cpp:2468-2501): deal units, not gaps
+    std::vector<double> cost;
+    std::vector<std::pair<int, int>> id;
+    for (size_t gi = 0; gi < c->gaps.size(); gi++) {
+        HostGap& g = c->gaps[gi];
+        g.owned = true;
+        g.est_owned.assign(g.gmax - g.gmin + 1, 0);
+        for (int gp = g.gmin; gp <= g.gmax; gp++) {
+            double t = 2000.0;
+            for (int r = 0; r < g.nrec; r++) {
+                const FbRecMeta& m = c->h_rmeta[g.rec_off + r];
+                t += (double)placements(m, c->D, gp) * (m.flags & 0xff);
+            }
+            cost.push_back(t);
+            id.emplace_back((int)gi, gp);
+        }
+    }
+    std::vector<int> owner(cost.size());
+    fb_partition_plan(cost.data(), (int)cost.size(), world, owner.data());
+    for (size_t k = 0; k < id.size(); k++)
+        if (owner[k] == rank) c->gaps[id[k].first].est_owned[id[k].second - c->gaps[id[k].first].gmin] = 1;
+    c->uploaded = c->ran = c->scanned = false;
     return FB_OK;
 }
 
@@ -622,6 +659,7 @@ int fb_upload(fb_ctx* c) {
             rec_bytes += (L2 + 3) / 4 + (L2 + 7) / 8 + 8 + 8;
         }
         for (int gp = g.gmin; gp <= g.gmax; gp++) {
+            if (!g.est_owned.empty() && !g.est_owned[gp - g.gmin]) continue;
             long liks = 0, terms = 0;
             for (int r = 0; r < g.nrec; r++) {
                 const FbRecMeta& m = c->h_rmeta[g.rec_off + r];
@@ -772,7 +810,7 @@ int fb_upload(fb_ctx* c) {
     tr.lap("upload: alloc + H2D");
     st.h2d_bytes = h2d;
     c->uploaded = true;
-    c->ran = false;
+    c->ran = c->scanned = false;
     return FB_OK;
 }
 
@@ -805,16 +843,17 @@ void fill_em_params(fb_ctx* c, FbEmParams& p) {
 
 extern "C" {
 
-int fb_run_device(fb_ctx* c) {
+// EM scan of the units this context owns: launches, per-bin copies, host log sums (figbird.cpp:2468-2478, 1951-1955).
+int fb_run_scan(fb_ctx* c) {
     if (!c) return FB_EINVAL;
-    if (!c->uploaded) return c->fail(FB_ESTATE, "fb_run_device before fb_upload");
+    if (!c->uploaded) return c->fail(FB_ESTATE, "fb_run_scan before fb_upload");
     FB_CUDA(c, cudaSetDevice(c->device));
     fb_stats& st = c->stats;
-    const int D = c->D;
     long d2h = 0;
     Trace tr;
     st.em_launches = st.finalize_launches = 0;
     st.finalize_likelihoods = 0;
+    st.finalize_kernel_ms = 0;
 
     // ---- EM scan: one persistent launch per size bin
     FB_CUDA(c, cudaEventRecord(c->evs, c->stream));
@@ -857,14 +896,13 @@ int fb_run_device(fb_ctx* c) {
 
     // ---- likelihood per unit (figbird.cpp:1951-1955): the per-record maxima of a bin are copied back on a second
     // stream as soon as that bin's launch has finished, and the host sums glibc log() over them while later bins run.
+    // Estimates scanned by another rank stay NaN until fb_merge_liks.
     for (HostGap& g : c->gaps) {
+        g.done = false;
         if (!g.owned) continue;
-        g.liks.assign(g.gmax - g.gmin + 1, 0.0);
+        g.liks.assign(g.gmax - g.gmin + 1, std::nan(""));
+        g.cons_off.assign(g.gmax - g.gmin + 1, -1);
     }
-    std::vector<long long> cons_off_of_best(c->gaps.size(), 0);
-    std::vector<std::vector<long long>> cons_off(c->gaps.size());
-    for (size_t gi = 0; gi < c->gaps.size(); gi++)
-        if (c->gaps[gi].owned) cons_off[gi].assign(c->gaps[gi].gmax - c->gaps[gi].gmin + 1, 0);
     for (size_t bi = 0; bi < c->bins.size(); bi++) {
         const Bin& b = c->bins[bi];
         FB_CUDA(c, cudaEventSynchronize(c->bin_copied[bi]));
@@ -876,12 +914,31 @@ int fb_run_device(fb_ctx* c) {
             for (int r = 0; r < g.nrec; r++)
                 if (mp[r] > 0) lik += log(mp[r]);
             g.liks[u.gp - g.gmin] = lik;
-            cons_off[u.gap][u.gp - g.gmin] = u.cons_off;
+            g.cons_off[u.gp - g.gmin] = u.cons_off;
         }
     }
     FB_CUDA(c, cudaStreamSynchronize(c->stream));
     tr.lap("run: EM + host log sums");
-    // best estimate per gap (figbird.cpp:2479-2490)
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    st.em_kernel_ms = ms;
+    st.d2h_bytes = d2h;
+    c->scanned = true;
+    c->ran = false;
+    return FB_OK;
+}
+
+// Best estimate per gap (figbird.cpp:2479-2490) and finalize (figbird.cpp:2087-2393) for every gap whose winning
+// estimate was scanned by this context.
+int fb_run_finalize(fb_ctx* c) {
+    if (!c) return FB_EINVAL;
+    if (!c->scanned) return c->fail(FB_ESTATE, "fb_run_finalize before fb_run_scan");
+    FB_CUDA(c, cudaSetDevice(c->device));
+    fb_stats& st = c->stats;
+    const int D = c->D;
+    long d2h = st.d2h_bytes;
+    Trace tr;
+    std::vector<long long> cons_off_of_best(c->gaps.size(), 0);
     std::vector<int> gaplist, bestgp(c->gaps.size(), 0);
     for (size_t gi = 0; gi < c->gaps.size(); gi++) {
         HostGap& g = c->gaps[gi];
@@ -889,15 +946,18 @@ int fb_run_device(fb_ctx* c) {
         double best = -DBL_MAX;
         int be = g.gmin;
         for (int gp = g.gmin; gp <= g.gmax; gp++) {
-            if (g.liks[gp - g.gmin] >= best) {   // last estimate wins ties
-                best = g.liks[gp - g.gmin];
+            const double l = g.liks[gp - g.gmin];
+            if (std::isnan(l)) return c->fail(FB_ESTATE, "gap %zu: estimate %d was scanned by another rank and its likelihood has not been merged", gi, gp);
+            if (l >= best) {   // last estimate wins ties
+                best = l;
                 be = gp;
             }
         }
         g.best_lik = best;
         g.best_est = be;
         bestgp[gi] = be;
-        cons_off_of_best[gi] = cons_off[gi][be - g.gmin];
+        if (g.cons_off[be - g.gmin] < 0) continue;   // the winner lives on another rank: that rank finalizes this gap
+        cons_off_of_best[gi] = g.cons_off[be - g.gmin];
         gaplist.push_back((int)gi);
     }
 
@@ -985,8 +1045,6 @@ int fb_run_device(fb_ctx* c) {
     float ms = 0;
     cudaEventElapsedTime(&ms, c->evs, c->eve);
     st.step_ms = ms;
-    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
-    st.em_kernel_ms = ms;
     st.finalize_kernel_ms = 0;
     if (!gaplist.empty()) {
         cudaEventElapsedTime(&ms, c->ev2, c->ev3);
@@ -994,6 +1052,34 @@ int fb_run_device(fb_ctx* c) {
     }
     st.d2h_bytes = d2h;
     c->ran = true;
+    return FB_OK;
+}
+
+int fb_run_device(fb_ctx* c) {
+    int rc = fb_run_scan(c);
+    if (rc != FB_OK) return rc;
+    return fb_run_finalize(c);
+}
+
+int fb_scan_liks(fb_ctx* c, int gap, double* liks, int cap) {
+    if (!c || gap < 0 || gap >= (int)c->gaps.size() || !liks) return FB_EINVAL;
+    const HostGap& g = c->gaps[gap];
+    if (!c->scanned || !g.owned) return c->fail(FB_ESTATE, "gap %d has not been scanned in this context", gap);
+    if (cap < (int)g.liks.size()) return FB_EINVAL;
+    memcpy(liks, g.liks.data(), g.liks.size() * sizeof(double));
+    return (int)g.liks.size();
+}
+
+int fb_merge_liks(fb_ctx* c, int gap, const double* liks, int n) {
+    if (!c || gap < 0 || gap >= (int)c->gaps.size() || !liks) return FB_EINVAL;
+    HostGap& g = c->gaps[gap];
+    if (!c->scanned || !g.owned) return c->fail(FB_ESTATE, "gap %d has not been scanned in this context", gap);
+    if (n != (int)g.liks.size()) return c->fail(FB_EINVAL, "gap %d scans %zu estimates, %d given", gap, g.liks.size(), n);
+    for (int i = 0; i < n; i++) {
+        if (std::isnan(g.liks[i])) g.liks[i] = liks[i];
+        else if (!std::isnan(liks[i]) && liks[i] != g.liks[i])
+            return c->fail(FB_EINVAL, "gap %d estimate %d: merged likelihood differs from the one computed here", gap, g.gmin + i);
+    }
     return FB_OK;
 }
 

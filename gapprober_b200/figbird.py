@@ -81,7 +81,7 @@ class FbStats(C.Structure):
 
 # Every symbol include/figbird_cuda.h declares; tests check the library exports all of them.
 ABI_SYMBOLS = [
-    "fb_create", "fb_destroy", "fb_add_gap", "fb_add_gap_file", "fb_add_gap_files", "fb_set_partition", "fb_owns_gap", "fb_partition_plan", "fb_gap_cost", "fb_run", "fb_upload",
+    "fb_create", "fb_destroy", "fb_add_gap", "fb_add_gap_file", "fb_add_gap_files", "fb_set_partition", "fb_set_partition_units", "fb_run_scan", "fb_run_finalize", "fb_scan_liks", "fb_merge_liks", "fb_owns_gap", "fb_partition_plan", "fb_gap_cost", "fb_run", "fb_upload",
     "fb_run_device", "fb_result", "fb_estimate_liks", "fb_best_string", "fb_dump_profile", "fb_get_stats",
     "fb_clear_gaps", "fb_gap_range", "fb_last_error", "fb_status_str", "fb_abi_version",
 ]
@@ -106,6 +106,11 @@ def load_library():
     L.fb_add_gap_file.argtypes = [vp, C.c_int, C.c_long, C.c_int, C.c_char_p, C.c_long, C.c_char_p]
     L.fb_add_gap_files.argtypes = [vp, C.POINTER(_FbGapDesc), C.c_int, C.POINTER(C.c_int), C.c_int]
     L.fb_set_partition.argtypes = [vp, C.c_int, C.c_int]
+    L.fb_set_partition_units.argtypes = [vp, C.c_int, C.c_int]
+    L.fb_run_scan.argtypes = [vp]
+    L.fb_run_finalize.argtypes = [vp]
+    L.fb_scan_liks.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.c_int]
+    L.fb_merge_liks.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.c_int]
     L.fb_owns_gap.argtypes = [vp, C.c_int]
     L.fb_partition_plan.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int, C.POINTER(C.c_int)]
     L.fb_gap_cost.argtypes = [vp, C.c_int]
@@ -376,6 +381,31 @@ class FigbirdContext:
 
     def setPartition(self, rank, world):
         self._check(self._L.fb_set_partition(self._h, rank, world))
+
+    def setPartitionUnits(self, rank, world):
+        """Deal (gap, estimate) units instead of gaps (for gap sets dominated by few gaps)."""
+        self._check(self._L.fb_set_partition_units(self._h, rank, world))
+
+    def runScan(self):
+        self._check(self._L.fb_run_scan(self._h))
+
+    def runFinalize(self):
+        self._check(self._L.fb_run_finalize(self._h))
+
+    def scanLiks(self, index):
+        a, b = gap_range(self._gaps[index].originalGap)
+        out = np.zeros(b - a + 1)
+        n = self._check(self._L.fb_scan_liks(self._h, index, out.ctypes.data_as(C.POINTER(C.c_double)), out.size))
+        return out[:n]
+
+    def mergeLiks(self, index, liks):
+        liks = np.ascontiguousarray(liks, dtype=np.float64)
+        self._check(self._L.fb_merge_liks(self._h, index, liks.ctypes.data_as(C.POINTER(C.c_double)), liks.size))
+
+    def hasResult(self, index):
+        """True when this context finalized gap `index` (it scanned the winning estimate)."""
+        r = _FbGapResult()
+        return self._L.fb_result(self._h, index, C.byref(r), None, 0) == FB_OK
 
     def ownsGap(self, index):
         return bool(self._L.fb_owns_gap(self._h, index))

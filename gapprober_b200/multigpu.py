@@ -23,10 +23,44 @@ def gather_results(local_results, group=None):
     return merged
 
 
-def fill_partitioned(ctx, gap_fillers, rank, world, group=None):
-    """setPartition + fillGaps + gather: returns {gap_index: result dict} for ALL gaps on every rank."""
-    if world > 1:
+def merge_liks(parts):
+    """Per-estimate likelihood arrays of all ranks (NaN = not scanned there) -> one array; ranks must agree where they overlap."""
+    import numpy as np
+    out = np.array(parts[0], dtype=np.float64, copy=True)
+    for p in parts[1:]:
+        p = np.asarray(p, dtype=np.float64)
+        take = np.isnan(out) & ~np.isnan(p)
+        both = ~np.isnan(out) & ~np.isnan(p)
+        if np.any(out[both] != p[both]):
+            raise RuntimeError("two ranks computed different likelihoods for one estimate")
+        out[take] = p[take]
+    if np.any(np.isnan(out)):
+        raise RuntimeError("an estimate was scanned by no rank")
+    return out
+
+
+def fill_partitioned(ctx, gap_fillers, rank, world, group=None, by="gap"):
+    """Partition + fill + gather: returns {gap_index: result dict} for ALL gaps on every rank.
+
+    by="gap": gaps are dealt to ranks (fb_set_partition); no exchange before the final gather.
+    by="estimate": (gap, estimate) units are dealt (fb_set_partition_units) — for gap sets dominated by few gaps; the
+    per-estimate likelihoods (a few doubles per gap) are all-gathered between the scan and the finalize."""
+    if world == 1:
+        ctx.fillGaps()
+        return {i: gf.result() for i, gf in enumerate(gap_fillers)}
+    if by == "gap":
         ctx.setPartition(rank, world)
-    ctx.fillGaps()
-    local = {i: gf.result() for i, gf in enumerate(gap_fillers) if world == 1 or ctx.ownsGap(i)}
+        ctx.fillGaps()
+        local = {i: gf.result() for i, gf in enumerate(gap_fillers) if ctx.ownsGap(i)}
+        return gather_results(local, group)
+    ctx.setPartitionUnits(rank, world)
+    ctx.upload()
+    ctx.runScan()
+    mine = [ctx.scanLiks(i) for i in range(len(gap_fillers))]
+    parts = [None] * world
+    dist.all_gather_object(parts, mine, group=group)
+    for i in range(len(gap_fillers)):
+        ctx.mergeLiks(i, merge_liks([parts[r][i] for r in range(world)]))
+    ctx.runFinalize()
+    local = {i: gf.result() for i, gf in enumerate(gap_fillers) if ctx.hasResult(i)}
     return gather_results(local, group)

@@ -118,6 +118,19 @@ int fb_add_gap_files(fb_ctx* ctx, const fb_gap_desc* descs, int n, int* handles,
  * context runs those of `rank`.  Results of other ranks' gaps are absent (fb_result -> FB_ESTATE).
  * Call after the last fb_add_gap and before fb_upload/fb_run.  No data-path collective is involved. */
 int fb_set_partition(fb_ctx* ctx, int rank, int world);
+/* Estimate-level variant, for gap sets dominated by few gaps: the independent units are (gap, estimate) pairs
+ * (figbird.cpp:2468-2501 scans estimates without any cross-estimate dependence until the final arg-max), so the
+ * units are dealt instead of the gaps.  Every rank registers every gap, then runs
+ *     fb_upload; fb_run_scan;  [exchange: fb_scan_liks -> all-gather -> fb_merge_liks];  fb_run_finalize
+ * and the rank that scanned a gap's winning estimate finalizes that gap (fb_result elsewhere: FB_ESTATE).
+ * The exchange is a few doubles per gap and is the caller's (gapprober_b200/multigpu.py: torch.distributed). */
+int fb_set_partition_units(fb_ctx* ctx, int rank, int world);
+int fb_run_scan(fb_ctx* ctx);        /* EM scan of the owned units + their likelihoods                       */
+int fb_run_finalize(fb_ctx* ctx);    /* selection + finalize; needs every estimate's likelihood (own or merged) */
+/* Likelihood per estimate after fb_run_scan; NaN where another rank scans the estimate.  Returns the count. */
+int fb_scan_liks(fb_ctx* ctx, int gap, double* liks, int cap);
+/* Fill in likelihoods scanned elsewhere (NaN entries of `liks` are ignored; values computed here are kept). */
+int fb_merge_liks(fb_ctx* ctx, int gap, const double* liks, int n);
 /* 1 if gap `gap` is run by this context under the current partition. */
 int fb_owns_gap(fb_ctx* ctx, int gap);
 /* The dealing rule itself, as pure host code (no GPU needed): items by descending cost, each to the least loaded

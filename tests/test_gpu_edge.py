@@ -129,6 +129,57 @@ def test_partition_invariance_and_idempotence(built):
         assert [seen[i] for i in range(len(gfs))] == full
 
 
+def test_estimate_level_partition(built):
+    """(gap, estimate) units dealt to three emulated ranks: each scans its share, the per-estimate likelihoods are merged
+    (what multigpu.fill_partitioned all-gathers), and the rank holding the winning estimate finalizes the gap."""
+    from gapprober_b200 import FigbirdContext, multigpu
+    for name in ("plateau_1000bp", "multi_gap_err1pct"):
+        case = G.Case(name)
+        world = 3
+        ctxs = [FigbirdContext(case.figbird_model()) for _ in range(world)]
+        try:
+            gfs = []
+            for rank, fb in enumerate(ctxs):
+                gfs.append([fb.GapFiller().initGapFiller(0, case.D, g["orig"], g["recs"], g["window"]) for g in case.gaps])
+                fb.setPartitionUnits(rank, world)
+                fb.upload()
+                fb.runScan()
+            total_units = sum(fb.stats()["n_units"] for fb in ctxs)
+            assert total_units == sum(len(g["liks"]) for g in case.gaps)          # every unit scanned exactly once
+            assert all(fb.stats()["n_units"] > 0 for fb in ctxs)
+            for gi, g in enumerate(case.gaps):
+                parts = [fb.scanLiks(gi) for fb in ctxs]
+                assert np.array_equal(np.sum([~np.isnan(p) for p in parts], axis=0), np.ones(len(g["liks"])))
+                merged = multigpu.merge_liks(parts)
+                assert np.array_equal(merged, g["liks"])
+                for fb in ctxs:
+                    fb.mergeLiks(gi, merged)
+            for fb in ctxs:
+                fb.runFinalize()
+            for gi, g in enumerate(case.gaps):
+                owners = [r for r, fb in enumerate(ctxs) if fb.hasResult(gi)]
+                assert len(owners) == 1
+                r = gfs[owners[0]][gi].result()
+                assert r["filled"] == g["filled"] and r["best_estimate"] == g["best_est"] and r["best_lik"] == g["best_lik"]
+        finally:
+            for fb in ctxs:
+                fb.close()
+
+
+def test_finalize_needs_merged_likelihoods(built):
+    from gapprober_b200 import FigbirdContext, FigbirdError
+    case = G.Case("lib180_100bp_60x")
+    g = case.gaps[0]
+    with FigbirdContext(case.figbird_model()) as fb:
+        fb.GapFiller().initGapFiller(0, case.D, g["orig"], g["recs"], g["window"])
+        fb.setPartitionUnits(0, 2)
+        fb.upload()
+        fb.runScan()
+        with pytest.raises(FigbirdError) as e:
+            fb.runFinalize()
+        assert e.value.status == -5
+
+
 def test_error_contract(built):
     from gapprober_b200 import FigbirdContext, FigbirdError
     case = G.Case("lib180_100bp_60x")

@@ -56,3 +56,15 @@ def test_two_rank_partition_and_gather(built):
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res), res
     assert sum(n for _, _, n in res) == 5 and all(n > 0 for _, _, n in res)     # every gap filled once, both ranks used
+
+
+def test_merge_liks_rules():
+    import pytest
+    from gapprober_b200.multigpu import merge_liks
+    nan = float("nan")
+    assert list(merge_liks([[1.0, nan, nan], [nan, 2.0, nan], [nan, nan, -0.5]])) == [1.0, 2.0, -0.5]
+    assert list(merge_liks([[1.0, 2.0], [1.0, nan]])) == [1.0, 2.0]
+    with pytest.raises(RuntimeError):
+        merge_liks([[1.0, nan], [nan, nan]])            # an estimate nobody scanned
+    with pytest.raises(RuntimeError):
+        merge_liks([[1.0, 2.0], [1.5, nan]])            # two ranks disagree
