@@ -256,8 +256,9 @@ def run_ours(a):
 
     # strong scaling: ownership is planned from cheap proxies (estimates scanned x gap-file bytes) with the library's
     # dealing rule, identically on every rank, so a rank parses, packs and uploads only the gaps it fills
+    by_estimate = world > 1 and not weak and a.partition == "estimate"
     mine = list(range(len(gaps)))
-    if world > 1 and not weak:
+    if world > 1 and not weak and not by_estimate:
         from gapprober_b200.figbird import gap_range, partition_plan
         proxy = []
         for (c, s, l), path in zip(gaps, gap_files):
@@ -269,6 +270,34 @@ def run_ours(a):
     def register():
         fb.clearGaps()
         fb.add_gap_files([(gaps[i][0], gaps[i][1], gaps[i][2], gap_files[i], seqs[gaps[i][0]]) for i in mine])
+        if by_estimate:
+            fb.setPartitionUnits(rank, world)
+
+    def exchange_and_finalize():
+        """estimate-level partition: all-gather the per-estimate likelihoods (a few doubles per gap), then finalize"""
+        from gapprober_b200.multigpu import merge_liks
+        local = [fb.scanLiks(i) for i in range(len(mine))]
+        parts = [None] * world
+        dist.all_gather_object(parts, local)
+        for i in range(len(mine)):
+            fb.mergeLiks(i, merge_liks([parts[r][i] for r in range(world)]))
+        fb.runFinalize()
+
+    def run_device():
+        if by_estimate:
+            fb.runScan()
+            exchange_and_finalize()
+        else:
+            fb.runDevice()
+
+    def run_e2e():
+        register()
+        if by_estimate:
+            fb.upload()
+            fb.runScan()
+            exchange_and_finalize()
+        else:
+            fb.fillGaps()
 
     def allmax(x):
         if world == 1:
@@ -290,7 +319,7 @@ def run_ours(a):
     register()
     fb.upload()
     for _ in range(a.warmup):
-        fb.runDevice()
+        run_device()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -300,10 +329,12 @@ def run_ours(a):
     for _ in range(a.steps):
         flush.fill_(1)                      # evict L2 between steps
         torch.cuda.synchronize()
-        fb.runDevice()                      # synchronous: returns after the last device->host copy
+        t_step = time.perf_counter()
+        run_device()                        # synchronous: returns after the last device->host copy
         st = fb.stats()
         em_ms += st["em_kernel_ms"]
-        step_ms += st["step_ms"]
+        # CUDA-event time of the step; with the likelihood exchange in the middle the events do not span it, use the host clock
+        step_ms += st["step_ms"] if not by_estimate else 1e3 * (time.perf_counter() - t_step)
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
@@ -315,16 +346,14 @@ def run_ours(a):
 
     # ---- end-to-end arm: host gap files -> library parse/pack -> H2D -> kernels -> D2H ------------------
     for _ in range(min(a.warmup, 2)):
-        register()
-        fb.fillGaps()
+        run_e2e()
     barrier()
     t0 = time.perf_counter()
     h2d = d2h = 0
     for _ in range(a.steps):
         flush.fill_(1)
         torch.cuda.synchronize()
-        register()
-        fb.fillGaps()
+        run_e2e()
         s2 = fb.stats()
         h2d, d2h = s2["h2d_bytes"], s2["d2h_bytes"]
     barrier()
@@ -333,8 +362,9 @@ def run_ours(a):
 
     # a result checksum so the step cannot be optimised away: total filled length over owned gaps
     filled_total = 0
-    for gf in fb._gaps:
-        filled_total += gf.result()["filled_len"]
+    for i, gf in enumerate(fb._gaps):
+        if not by_estimate or fb.hasResult(i):
+            filled_total += gf.result()["filled_len"]
     filled_total = int(allsum(float(filled_total)))
 
     if rank == 0:
@@ -359,6 +389,7 @@ def run_ours(a):
             "config": {"workload": a.config, "seed": a.seed, "gaps": len(gaps), "gaps_this_rank": len(mine), "units": st["n_units"], "records": st["n_records"],
                        "likelihoods_per_step_this_rank": st["likelihoods"], "l2": "flushed between steps (256 MiB write)",
                        "partition": ("rank r fills the gap set of seed+r (gap-partitioned, no data-path collective)" if weak else
+                                     "(gap, estimate) units dealt to ranks by cost; per-estimate likelihoods all-gathered before finalize" if by_estimate else
                                      "one gap set dealt to ranks by descending (estimates x gap-file bytes), no data-path collective"),
                        "filled_bases_total": filled_total, "host_wall_s": wall},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -408,6 +439,8 @@ def main():
     ap.add_argument("--ref-liks", type=float, default=4.0e6, help="likelihoods per process per step in the reference arm")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--partition", default="gap", choices=["gap", "estimate"],
+                    help="strong scaling only: deal gaps, or (gap, estimate) units when few gaps dominate")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":
