@@ -7,8 +7,8 @@
 //     repeat num_iter times
 //       placeReads                    figbird.cpp:1677-1965
 //         E-step  (1826-1872/1889-1938): score = ILD[t] * prod_j (P*(1-e) + e*Q)
-//                                                           -> warp per (record, 32 placements), lanes over
-//                                                              placements, j sequential in each lane
+//                                                           -> warp per (record, 64 placements), lanes over
+//                                                              placements (two per lane), j sequential per lane
 //         M-step  (1874-1881/1940-1947): counts[row][base] += score
 //                                                           -> ordered gather: lane per gap row, warp per
 //                                                              (32 rows, base class); adds arrive in the
@@ -24,8 +24,9 @@
 // scores to a cell in exactly the order the CPU's scatter loop does.  Likelihood plateaus therefore
 // tie exactly as they do on the CPU.  No tensor cores: the path is not a contraction.
 //
-// Roofs: ~3 HBM bytes per likelihood vs ~1.6 KB of shared-memory reads and ~400 FP64 instructions, so
-// shared-memory bandwidth (then the FP64 pipe) binds; DESIGN.md has the arithmetic.
+// Roofs: ~6.5 algorithmic HBM bytes per likelihood (1.65 MB of real DRAM traffic per bench step) vs ~1.6 KB of
+// shared-memory reads and ~400 FP64 instructions per likelihood, so shared-memory bandwidth (then the FP64 pipe)
+// binds; DESIGN.md has the arithmetic, profiles/README.md the measurements.
 
 #include "fb_device.h"
 
@@ -60,13 +61,13 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
 
 // ---------------------------------------------------------------------------------------------------
 // Shared-memory plan of the EM kernel.  Per CTA:
-//   eo, ild          model tables (read-position error rates, insert-length window)
+//   ild              insert-length window ({1-e,e} per read position comes through the kernel-parameter constant bank)
 //   pq[5][nrs+pad]   {P[row][c], Q[row][c]} per base class, class 4 = {0, Q[row][4]}          (E-step reads)
 //   cnt[5][gps]      counts of the gap rows                                                  (M-step accumulates)
-//   w[2][chunk][ps]  placement scores of two in-flight record chunks
-//   st[3]            staged record chunks: window, flags, class bit-masks, per-position table offsets
+//   w[2]             placement scores of two in-flight record chunks: rows of p_stride slots separated by kPadW zeros
+//   st[3]            staged record chunks: window, flags, class bit-masks, 4-bit packed classes, class-sorted position lists
 // One unit runs as a software pipeline over chunks of records: in round r the CTA's warps pull, from one
-// dynamic queue, M-step tasks of chunk r-2, E-step tasks of chunk r-1 and staging tasks of chunk r, and
+// dynamic queue, M-step tasks of chunk r-1, E-step tasks of chunk r and staging tasks of chunk r+1, and
 // meet at ONE barrier per round.
 // ---------------------------------------------------------------------------------------------------
 constexpr int kPadRows = 32;   // a lane's second placement sits 32 rows further; invalid lanes may read (not use) past the end
