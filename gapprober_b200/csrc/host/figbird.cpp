@@ -10,6 +10,8 @@
 // Library lookup: $FIGBIRD_CUDA_LIB, then next to the executable, then its parent directory, then the
 // dynamic loader's search path.  Optional environment:
 //   FIGBIRD_DEVICE=<n>       CUDA device (default 0)
+//   FIGBIRD_GPUS=<n>         fill the gaps on n GPUs (devices FIGBIRD_DEVICE .. +n-1): one context and one host thread per
+//                            GPU, gaps dealt by fb_set_partition, no exchange between them
 //   FIGBIRD_MODEL_OUT=<path> also write the learned model ("FBM1" file)
 //   FIGBIRD_PREAMBLE_ONLY=1  stop after the preamble (used by the benchmark to build its model)
 //   FIGBIRD_FROM_SAM=<path>  in-memory hand-off: split <path> (bowtie2's result.sam) in this process the way
@@ -20,12 +22,14 @@
 #include <dlfcn.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
 #include <iostream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/figbird_cuda.h"
@@ -41,6 +45,8 @@ struct Api {
     decltype(&fb_destroy) destroy = nullptr;
     decltype(&fb_add_gap) add_gap = nullptr;
     decltype(&fb_run) run = nullptr;
+    decltype(&fb_set_partition) set_partition = nullptr;
+    decltype(&fb_owns_gap) owns_gap = nullptr;
     decltype(&fb_result) result = nullptr;
     decltype(&fb_last_error) last_error = nullptr;
     decltype(&fb_status_str) status_str = nullptr;
@@ -77,6 +83,8 @@ bool load_api(Api& a, std::string& why) {
     FB_SYM(destroy, "fb_destroy")
     FB_SYM(add_gap, "fb_add_gap")
     FB_SYM(run, "fb_run")
+    FB_SYM(set_partition, "fb_set_partition")
+    FB_SYM(owns_gap, "fb_owns_gap")
     FB_SYM(result, "fb_result")
     FB_SYM(last_error, "fb_last_error")
     FB_SYM(status_str, "fb_status_str")
@@ -181,13 +189,16 @@ int main(int argc, char* argv[]) {
     m.max_distance = 200;   // maxDistance, figbird.cpp:103
     m.num_iter = 5;         // num_itr, figbird.cpp:2466
     m.f_mode = f_mode;
-    fb_ctx* ctx = nullptr;
     const int device = getenv("FIGBIRD_DEVICE") ? atoi(getenv("FIGBIRD_DEVICE")) : 0;
-    int rc = api.create(&m, device, &ctx);
-    if (rc != FB_OK) {
-        printf("figbird: fb_create failed: %s%s\n", api.status_str(rc),
-               rc == FB_EUNSUPPORTED ? " (only f=0, the mode GapProber.py uses, runs on the GPU)" : "");
-        return 1;
+    const int ngpu = getenv("FIGBIRD_GPUS") ? std::max(1, atoi(getenv("FIGBIRD_GPUS"))) : 1;
+    std::vector<fb_ctx*> ctxs(ngpu, nullptr);
+    for (int k = 0; k < ngpu; k++) {
+        int rc = api.create(&m, device + k, &ctxs[k]);
+        if (rc != FB_OK) {
+            printf("figbird: fb_create failed on device %d: %s%s\n", device + k, api.status_str(rc),
+                   rc == FB_EUNSUPPORTED ? " (only f=0, the mode GapProber.py uses, runs on the GPU)" : "");
+            return 1;
+        }
     }
 
     time_t t0, t1;
@@ -221,15 +232,30 @@ int main(int argc, char* argv[]) {
         const fbhost::GapInfo& gi = gaps[g];
         if (gi.contig_no < 0 || gi.contig_no >= (int)sc.seqs.size()) continue;
         const std::string& ctg = sc.seqs[gi.contig_no];
-        int h = api.add_gap(ctx, gi.contig_no, gi.start, gi.length, ctg.c_str(), (long)ctg.size(), rv.data(), (int)rv.size());
-        if (h < 0) fprintf(stderr, "figbird: gap %zu left unfilled: %s\n", g, api.last_error(ctx));
-        handle[g] = h;
+        for (int k = 0; k < ngpu; k++) {     // every context sees every gap; the partition decides who fills it
+            int h = api.add_gap(ctxs[k], gi.contig_no, gi.start, gi.length, ctg.c_str(), (long)ctg.size(), rv.data(), (int)rv.size());
+            if (h < 0 && k == 0) fprintf(stderr, "figbird: gap %zu left unfilled: %s\n", g, api.last_error(ctxs[k]));
+            handle[g] = h;
+        }
     }
-    rc = api.run(ctx);
-    if (rc != FB_OK) {
-        printf("figbird: fb_run failed: %s: %s\n", api.status_str(rc), api.last_error(ctx));
-        return 1;
+    std::vector<int> run_rc(ngpu, FB_OK);
+    if (ngpu == 1) {
+        run_rc[0] = api.run(ctxs[0]);
+    } else {
+        std::vector<std::thread> pool;
+        for (int k = 0; k < ngpu; k++)
+            pool.emplace_back([&, k]() {
+                int rc = api.set_partition(ctxs[k], k, ngpu);
+                run_rc[k] = rc == FB_OK ? api.run(ctxs[k]) : rc;
+            });
+        for (auto& t : pool) t.join();
     }
+    for (int k = 0; k < ngpu; k++)
+        if (run_rc[k] != FB_OK) {
+            printf("figbird: fb_run failed on device %d: %s: %s\n", device + k, api.status_str(run_rc[k]), api.last_error(ctxs[k]));
+            return 1;
+        }
+    int rc = FB_OK;
     FILE* gap_out = fopen("gapout.txt", "w");
     std::vector<std::string> filled(gaps.size());
     for (size_t g = 0; g < gaps.size(); g++) {
@@ -237,9 +263,12 @@ int main(int argc, char* argv[]) {
         if (handle[g] >= 0) {
             fb_gap_result res;
             std::vector<char> buf((size_t)2 * gi.length + 16);
-            rc = api.result(ctx, handle[g], &res, buf.data(), (int)buf.size());
+            fb_ctx* owner = ctxs[0];
+            for (int k = 0; k < ngpu; k++)
+                if (api.owns_gap(ctxs[k], handle[g])) owner = ctxs[k];
+            rc = api.result(owner, handle[g], &res, buf.data(), (int)buf.size());
             if (rc != FB_OK) {
-                printf("figbird: fb_result failed: %s\n", api.last_error(ctx));
+                printf("figbird: fb_result failed: %s\n", api.last_error(owner));
                 return 1;
             }
             filled[g] = buf.data();
@@ -252,7 +281,7 @@ int main(int argc, char* argv[]) {
         std::cout << "Gap " << g << " is done." << std::endl;
     }
     fclose(gap_out);
-    api.destroy(ctx);
+    for (fb_ctx* cx : ctxs) api.destroy(cx);
     time(&t1);
     std::cout << "Total time to fill gaps in seconds = " << difftime(t1, t0) << std::endl;
 

@@ -51,3 +51,22 @@ def test_in_memory_handoff_from_result_sam(built, tmp_path):
     assert not os.path.exists(os.path.join(a, "myout.sam")) and not os.path.exists(os.path.join(a, "Gaps"))
     strip = lambda s: [ln for ln in s.splitlines() if not ln.startswith("Total time to fill gaps")]
     assert strip(ours.stdout) == strip(ref.stdout)
+
+
+def test_dropin_two_gpus(built, tmp_path):
+    """FIGBIRD_GPUS=2: one context and host thread per GPU inside the drop-in binary, gaps dealt by fb_set_partition."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    if not refrun.have_ref():
+        pytest.skip("oracle/_ref binaries not built")
+    from gapprober_b200 import build, synth
+    a, b = str(tmp_path / "ours"), str(tmp_path / "ref")
+    synth.generate(a, ARGS, seed=35)
+    shutil.copytree(a, b)
+    ours = subprocess.run([build.build_host(), "scaffolds.fa", " 0", "250"], cwd=a, env=dict(os.environ, FIGBIRD_GPUS="2"),
+                          stdout=subprocess.PIPE, text=True)
+    assert ours.returncode == 0, ours.stdout
+    subprocess.run([refrun.REF_FIGBIRD, "scaffolds.fa", " 0", "250"], cwd=b, stdout=subprocess.DEVNULL, check=True)
+    for f in ("gapout.txt", "filledContigs.fa"):
+        assert filecmp.cmp(os.path.join(a, f), os.path.join(b, f), shallow=False), f
