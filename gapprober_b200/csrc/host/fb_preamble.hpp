@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace fbhost {
@@ -124,18 +125,63 @@ public:
 
     // Pass 1 over the file, then computeProbabilites, then pass 2 (computeLikelihood) and the cut-off.
     // With `mem` the same text is read from memory (the splitter's in-memory hand-off) instead of from myout_path.
+    // Both passes only accumulate integer counts, so large inputs are cut into chunks scanned by several host threads
+    // (FIGBIRD_THREADS, default one per hardware thread up to 16) and the counts are added up: same result, bit for bit.
     bool learn(const char* myout_path, Model& out, const std::string* mem = nullptr) {
-        mem_ = mem;
-        FILE* fp = open_input(myout_path);
-        if (!fp) return false;
-        std::vector<char> line(kMaxRecLen);
-        while (fgets(line.data(), kMaxRecLen, fp)) {
-            if (line[0] == '@') continue;
-            add_mapping(line.data());
+        std::string owned;
+        const std::string* text = mem;
+        if (!text) {
+            FILE* fp = fopen(myout_path, "rb");
+            if (!fp) return false;
+            fseek(fp, 0, SEEK_END);
+            long sz = ftell(fp);
+            fseek(fp, 0, SEEK_SET);
+            owned.resize(sz > 0 ? (size_t)sz : 0);
+            if (sz > 0 && fread(&owned[0], 1, (size_t)sz, fp) != (size_t)sz) { fclose(fp); return false; }
+            fclose(fp);
+            text = &owned;
         }
-        fclose(fp);
+        int threads = 1;
+        if (const char* e = getenv("FIGBIRD_THREADS")) threads = atoi(e);
+        else threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+        std::vector<size_t> cut1, cut2;
+        if (threads > 1 && text->size() >= (size_t)(4 << 20)) plan_chunks(*text, threads, cut1, cut2);
+        if (cut1.size() <= 2) {
+            cut1 = {0, text->size()};
+            cut2 = cut1;
+        }
+        const int T = (int)cut1.size() - 1;
+        // ---- pass 1
+        {
+            std::vector<Preamble> workers;
+            for (int t = 1; t < T; t++) workers.emplace_back(mrl_, hard_max_insert_, contig_len_);
+            std::vector<std::thread> pool;
+            for (int t = 1; t < T; t++)
+                pool.emplace_back([&, t]() { workers[t - 1].scan_range(text->data() + cut1[t], cut1[t + 1] - cut1[t]); });
+            scan_range(text->data() + cut1[0], cut1[1] - cut1[0]);
+            for (auto& th : pool) th.join();
+            for (Preamble& w : workers) absorb(w);
+        }
         derive_distributions();
-        if (!score_pairs(myout_path)) return false;
+        // ---- pass 2
+        {
+            gap_hist_.assign(1000, 0);
+            std::vector<std::vector<long>> hist(T, std::vector<long>(1000, 0)), mapped(T, std::vector<long>((size_t)max_insert_, 0));
+            std::vector<char> ok(T, 1);
+            std::vector<std::thread> pool;
+            auto work = [&](int t) {
+                std::vector<long> eff(eff_len_);
+                ok[t] = score_range(text->data() + cut2[t], cut2[t + 1] - cut2[t], hist[t], mapped[t], eff, /*flush_last_group=*/t != T - 1);
+            };
+            for (int t = 1; t < T; t++) pool.emplace_back(work, t);
+            work(0);
+            for (auto& th : pool) th.join();
+            for (int t = 0; t < T; t++) {
+                if (!ok[t]) return false;
+                for (int i = 0; i < 1000; i++) gap_hist_[i] += hist[t][i];
+                for (int i = 0; i < max_insert_; i++) inserts_mapped_[i] += mapped[t][i];
+            }
+        }
         // gapProbCutOff: first bin where the cumulative count reaches 99 % (figbird.cpp:2778-2794)
         long total = 0;
         for (long v : gap_hist_) total += v;
@@ -164,11 +210,106 @@ public:
     int thr_max() const { return thr_max_; }
 
 private:
-    FILE* open_input(const char* path) const {
-        if (mem_) return mem_->empty() ? fopen("/dev/null", "r") : fmemopen((void*)mem_->data(), mem_->size(), "r");
-        return fopen(path, "r");
+    static FILE* open_range(const char* p, size_t n) { return n ? fmemopen((void*)p, n, "r") : fopen("/dev/null", "r"); }
+
+    // pass 1 over a range of whole lines
+    void scan_range(const char* p, size_t n) {
+        FILE* fp = open_range(p, n);
+        if (!fp) return;
+        std::vector<char> line(kMaxRecLen);
+        while (fgets(line.data(), kMaxRecLen, fp)) {
+            if (line[0] == '@') continue;
+            add_mapping(line.data());
+        }
+        fclose(fp);
     }
-    const std::string* mem_ = nullptr;
+
+    // add another worker's pass-1 counts to this one (every counter starts from the same pseudo-count)
+    void absorb(const Preamble& w) {
+        if (w.insert_counts_.size() > insert_counts_.size()) insert_counts_.resize(w.insert_counts_.size(), 1);
+        for (size_t i = 0; i < w.insert_counts_.size(); i++) insert_counts_[i] += w.insert_counts_[i] - 1;
+        discarded_ += w.discarded_;
+        unique_reads_ += w.unique_reads_;
+        for (int i = 0; i < 5; i++) {
+            base_counts_[i] += w.base_counts_[i] - 1;
+            for (int j = 0; j < 5; j++) err_types_[i][j] += w.err_types_[i][j] - 1;
+        }
+        for (int i = 0; i < mrl_; i++) {
+            err_pos_[i] += w.err_pos_[i] - 1;
+            in_pos_[i] += w.in_pos_[i] - 1;
+            in_len_[i] += w.in_len_[i] - 1;
+            del_pos_[i] += w.del_pos_[i] - 1;
+            del_len_[i] += w.del_len_[i] - 1;
+            read_len_hist_[i] += w.read_len_hist_[i];
+        }
+    }
+
+    // Cut the text into about `parts` ranges.  cut1: at line starts (pass 1).  cut2: at the start of a line PAIR whose
+    // names differ from the pair before it, so that no multi-hit group of pass 2 straddles a cut.  Refuses (leaves the
+    // cuts empty -> single range) when the text has '@' lines or lines the reference's 1023-byte fgets would split.
+    static void plan_chunks(const std::string& text, int parts, std::vector<size_t>& cut1, std::vector<size_t>& cut2) {
+        const size_t n = text.size();
+        const char* d = text.data();
+        if (n == 0 || d[n - 1] != '\n') return;
+        std::vector<size_t> tentative;
+        for (int t = 1; t < parts; t++) {
+            size_t pos = n / parts * t;
+            const char* nl = (const char*)memchr(d + pos, '\n', n - pos);
+            if (!nl) break;
+            pos = (size_t)(nl - d) + 1;
+            if (pos < n && (tentative.empty() || pos > tentative.back())) tentative.push_back(pos);
+        }
+        // line parity of every tentative cut + sanity of the whole text, chunk by chunk in parallel
+        std::vector<size_t> bounds = {0};
+        bounds.insert(bounds.end(), tentative.begin(), tentative.end());
+        bounds.push_back(n);
+        const int C = (int)bounds.size() - 1;
+        std::vector<size_t> lines(C, 0);
+        std::vector<char> bad(C, 0);
+        std::vector<std::thread> pool;
+        for (int c = 0; c < C; c++)
+            pool.emplace_back([&, c]() {
+                const char* p = d + bounds[c];
+                const char* e = d + bounds[c + 1];
+                size_t cnt = 0;
+                while (p < e) {
+                    if (*p == '@') bad[c] = 1;
+                    const char* nl = (const char*)memchr(p, '\n', (size_t)(e - p));
+                    if (!nl) { bad[c] = 1; break; }
+                    if (nl - p >= kMaxRecLen - 1) bad[c] = 1;
+                    cnt++;
+                    p = nl + 1;
+                }
+                lines[c] = cnt;
+            });
+        for (auto& th : pool) th.join();
+        for (int c = 0; c < C; c++)
+            if (bad[c]) return;
+        cut1 = bounds;
+        // pass-2 cuts: move each cut forward to an even line, then further while the pair repeats the names of the pair before
+        auto next_line = [&](size_t pos) { const char* nl = (const char*)memchr(d + pos, '\n', n - pos); return nl ? (size_t)(nl - d) + 1 : n; };
+        auto name_at = [&](size_t pos) { size_t e = pos; while (e < n && d[e] != '\t' && d[e] != '\n') e++; return std::string(d + pos, e - pos); };
+        auto prev_line = [&](size_t pos) { size_t p = pos - 1; while (p > 0 && d[p - 1] != '\n') p--; return p; };   // pos = start of a line, > 0
+        cut2 = {0};
+        size_t seen = 0;
+        for (int c = 1; c < C; c++) {
+            seen += lines[c - 1];
+            size_t pos = bounds[c];
+            if (seen & 1) pos = next_line(pos);                  // an odd number of lines before: skip the pair's second line
+            while (pos < n) {
+                const size_t l2 = next_line(pos);
+                if (l2 >= n) { pos = n; break; }
+                const size_t p2 = prev_line(pos), p1 = prev_line(p2);
+                if (name_at(pos) != name_at(p1) || name_at(l2) != name_at(p2)) break;   // a new group starts here
+                pos = next_line(l2);
+            }
+            if (pos < n && pos > cut2.back()) cut2.push_back(pos);
+        }
+        cut2.push_back(n);
+        if (cut2.size() != cut1.size()) {       // keep the two cut lists the same length (one range per thread)
+            while (cut2.size() < cut1.size()) cut2.insert(cut2.end() - 1, cut2[cut2.size() - 2]);
+        }
+    }
 
     // updateInsertCounts, figbird.cpp:164-203
     void count_insert(int v) {
@@ -356,17 +497,17 @@ private:
     }
 
     // getEffectiveLength, figbird.cpp:902-929
-    long effective_length(int ins) {
+    long effective_length(int ins, std::vector<long>& cache) const {
         auto compute = [&](int v) {
             long e = 0;
             for (long l : contig_len_)
                 if (l >= v) e += (l - v + 1);
             return e;
         };
-        if (ins < 0) return eff_len_[0];
+        if (ins < 0) return cache[0];
         if (ins >= max_insert_) return compute(ins);
-        if (eff_len_[ins] == -1) eff_len_[ins] = compute(ins);
-        return eff_len_[ins];
+        if (cache[ins] == -1) cache[ins] = compute(ins);
+        return cache[ins];
     }
 
     // computeErrorProb, figbird.cpp:931-1132 (long double)
@@ -404,21 +545,24 @@ private:
     }
 
     // computeLikelihood, figbird.cpp:1135-1351: only its side effects (gapProbs histogram, insertCountsMapped) are used.
-    bool score_pairs(const char* path) {
-        FILE* fp = open_input(path);
+    // One range of line pairs.  The reference never flushes its last group (figbird.cpp:1339-1346 only adds the log);
+    // a range that is not the last one of the file does flush it, because the group is complete there.
+    bool score_range(const char* p, size_t n, std::vector<long>& hist, std::vector<long>& mapped, std::vector<long>& eff_cache,
+                     bool flush_last_group) {
+        FILE* fp = open_range(p, n);
         if (!fp) return false;
         std::vector<char> l1(kMaxRecLen), l2(kMaxRecLen);
         std::string pre1 = "*", pre2 = "*", md1, md2;
         long double sum = 0.0, logsum = 0.0, best = 0, gap_p = 0;
         int best_ins = 0;
-        gap_hist_.assign(1000, 0);
+        bool any = false;
         auto flush_hist = [&]() {
             long double v = -logl(gap_p);
             int idx = (std::isnan(v) || v >= 2147483648.0L || v <= -2147483649.0L) ? INT_MIN : (int)v;
-            if (idx < 1000 && idx >= 0) gap_hist_[idx]++;
-            else gap_hist_[999]++;
-            if (best_ins >= max_insert_) inserts_mapped_[max_insert_ - 1]++;
-            else inserts_mapped_[best_ins]++;
+            if (idx < 1000 && idx >= 0) hist[idx]++;
+            else hist[999]++;
+            if (best_ins >= max_insert_) mapped[max_insert_ - 1]++;
+            else mapped[best_ins]++;
         };
         while (fgets(l1.data(), kMaxRecLen, fp)) {
             if (l1[0] == '@') continue;
@@ -438,7 +582,8 @@ private:
             if (ins_p == 0) ins_p = 1 / (double)unique_reads_;
             const long double e1 = read_error_prob(a.cigar, md1.c_str(), a.seq, st1);
             const long double e2 = read_error_prob(b.cigar, md2.c_str(), b.seq, st2);
-            const long eff = effective_length(ins);
+            const long eff = effective_length(ins, eff_cache);
+            any = true;
             const long double prob = (1 / (long double)(eff)) * ins_p * e1 * e2;
             if (pre1 == a.qname && pre2 == b.qname) {
                 if (best < prob) {
@@ -466,6 +611,7 @@ private:
             if (std::isinf(logsum)) { fclose(fp); return false; }
         }
         fclose(fp);
+        if (flush_last_group && any) flush_hist();
         return true;
     }
 

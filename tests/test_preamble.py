@@ -34,3 +34,31 @@ def test_preamble_prints_the_threshold_line(built, tmp_path):
     out = subprocess.run([build.build_host(), "scaffolds.fa", " 0", "250"], cwd=wd, env=env, stdout=subprocess.PIPE, text=True, check=True).stdout
     m = FigbirdModel.load(os.path.join(wd, "m.bin"))
     assert out.strip() == f"insertThresholdMin = {m.thr_min}...insertThresholdMax = {m.thr_max}"   # figbird.cpp:2744
+
+
+def test_threaded_preamble_equals_serial_and_reference(built, tmp_path):
+    """Large myout.sam cut into chunks scanned by several host threads: the model must be byte-identical to the
+    single-thread scan and to the reference's (both passes only add integer counts).  Every pair is written three
+    times in a row (multi-hit groups, figbird.cpp:1268-1280) so that the pass-2 cuts have groups to respect."""
+    import refrun
+    from gapprober_b200 import build, synth
+    wd = str(tmp_path / "big")
+    synth.generate(wd, ["--genome", "400000", "--scaffolds", "2", "--gap-list", "120,300", "--cov", "45", "--ins-mean", "200", "--ins-sd", "25",
+                        "--err", "0.01", "--nrate", "0.002"], seed=51)
+    src = open(os.path.join(wd, "myout.sam")).read().splitlines(keepends=True)
+    with open(os.path.join(wd, "myout.sam"), "w") as f:
+        for k in range(0, len(src), 2):
+            f.write((src[k] + src[k + 1]) * 3)
+    assert os.path.getsize(os.path.join(wd, "myout.sam")) > (8 << 20)
+    models = {}
+    for threads in ("1", "3", "8"):
+        env = dict(os.environ, FIGBIRD_PREAMBLE_ONLY="1", FIGBIRD_MODEL_OUT=f"m{threads}.bin", FIGBIRD_THREADS=threads)
+        subprocess.run([build.build_host(), "scaffolds.fa", " 0", "250"], cwd=wd, env=env, check=True, stdout=subprocess.DEVNULL)
+        models[threads] = (open(os.path.join(wd, f"m{threads}.bin"), "rb").read(), open(os.path.join(wd, "mappedInserts.txt")).read())
+    assert models["1"] == models["3"] == models["8"]
+    if refrun.have_ref():
+        for k in range(2):                                           # preamble is what is compared: give the gaps no records
+            open(os.path.join(wd, "Gaps", f"gaps_{k}.sam"), "w").close()
+        subprocess.run([refrun.REF_DUMP, "scaffolds.fa", " 0", "250"], cwd=wd, check=True, stdout=subprocess.DEVNULL)
+        assert open(os.path.join(wd, "fb_model.bin"), "rb").read() == models["8"][0]
+        assert open(os.path.join(wd, "mappedInserts.txt")).read() == models["8"][1]
