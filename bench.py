@@ -274,13 +274,9 @@ def run_ours(a):
             fb.setPartitionUnits(rank, world)
 
     def exchange_and_finalize():
-        """estimate-level partition: all-gather the per-estimate likelihoods (a few doubles per gap), then finalize"""
-        from gapprober_b200.multigpu import merge_liks
-        local = [fb.scanLiks(i) for i in range(len(mine))]
-        parts = [None] * world
-        dist.all_gather_object(parts, local)
-        for i in range(len(mine)):
-            fb.mergeLiks(i, merge_liks([parts[r][i] for r in range(world)]))
+        """estimate-level partition: one NCCL all-reduce(MAX) of the per-estimate likelihoods (a few doubles per gap), then finalize"""
+        from gapprober_b200.multigpu import exchange_liks
+        exchange_liks(fb, len(mine), device=torch.device("cuda", local))
         fb.runFinalize()
 
     def run_device():

@@ -56,11 +56,29 @@ def fill_partitioned(ctx, gap_fillers, rank, world, group=None, by="gap"):
     ctx.setPartitionUnits(rank, world)
     ctx.upload()
     ctx.runScan()
-    mine = [ctx.scanLiks(i) for i in range(len(gap_fillers))]
-    parts = [None] * world
-    dist.all_gather_object(parts, mine, group=group)
-    for i in range(len(gap_fillers)):
-        ctx.mergeLiks(i, merge_liks([parts[r][i] for r in range(world)]))
+    exchange_liks(ctx, len(gap_fillers), group)
     ctx.runFinalize()
     local = {i: gf.result() for i, gf in enumerate(gap_fillers) if ctx.hasResult(i)}
     return gather_results(local, group)
+
+
+def exchange_liks(ctx, n_gaps, group=None, device=None):
+    """The one collective of the estimate-level partition: every rank holds the likelihoods of the estimates it scanned
+    (NaN elsewhere); one all-reduce(MAX) over the concatenated vector (NaN -> -inf) gives every rank all of them.  Each
+    estimate is scanned by exactly one rank, so MAX only ever picks between a value and -inf: the result is exact.
+    NCCL over NVLink when the ranks sit on GPUs (pass device), gloo on CPU."""
+    import numpy as np
+    import torch
+    mine = [ctx.scanLiks(i) for i in range(n_gaps)]
+    flat = np.concatenate(mine) if mine else np.zeros(0)
+    t = torch.from_numpy(np.where(np.isnan(flat), -np.inf, flat))
+    if device is not None:
+        t = t.to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    merged = t.cpu().numpy()
+    if np.any(np.isneginf(merged)):
+        raise RuntimeError("an estimate was scanned by no rank")
+    off = 0
+    for i, m in enumerate(mine):
+        ctx.mergeLiks(i, merged[off:off + m.size])
+        off += m.size

@@ -68,3 +68,54 @@ def test_merge_liks_rules():
         merge_liks([[1.0, nan], [nan, nan]])            # an estimate nobody scanned
     with pytest.raises(RuntimeError):
         merge_liks([[1.0, 2.0], [1.5, nan]])            # two ranks disagree
+
+
+class _FakeCtx:
+    """Stands in for FigbirdContext in the exchange test: holds per-gap likelihood arrays with NaN for foreign estimates."""
+
+    def __init__(self, liks):
+        self.liks = [l.copy() for l in liks]
+
+    def scanLiks(self, i):
+        return self.liks[i]
+
+    def mergeLiks(self, i, merged):
+        import numpy as np
+        own = ~np.isnan(self.liks[i])
+        assert np.array_equal(self.liks[i][own], merged[own])
+        self.liks[i] = np.array(merged, copy=True)
+
+
+def _exchange_worker(rank, world, port, q):
+    sys.path.insert(0, os.path.dirname(HERE))
+    from gapprober_b200 import multigpu
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    rng = np.random.default_rng(7)
+    full = [rng.normal(-3000, 50, size=n) for n in (51, 66, 7)]
+    mine = []
+    for g in full:
+        m = g.copy()
+        m[np.arange(g.size) % world != rank] = np.nan        # each estimate scanned by exactly one rank
+        mine.append(m)
+    ctx = _FakeCtx(mine)
+    multigpu.exchange_liks(ctx, len(full))
+    q.put((rank, all(np.array_equal(a, b) for a, b in zip(ctx.liks, full))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_likelihood_exchange_two_ranks():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_exchange_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res), res
