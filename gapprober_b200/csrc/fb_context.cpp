@@ -734,7 +734,8 @@ int fb_upload(fb_ctx* c) {
         b.global_tables = false;
         b.chunk = 0;
         int ctas = 2;
-        const int pref = getenv("FB_CHUNK") ? atoi(getenv("FB_CHUNK")) : 16;   // tuning knob: records per pipeline round
+        // tuning knob: records per pipeline round (the M-step sets up one record per lane, so at most 32)
+        const int pref = getenv("FB_CHUNK") ? std::max(1, std::min(32, atoi(getenv("FB_CHUNK")))) : 16;
         for (int want : {pref, 8, 4}) {
             if (want >= 1 && fb_em_smem_bytes(b.nr_stride, b.gp_stride, b.p_stride, want, pwin, false) <= two_cta) { b.chunk = want; break; }
         }
