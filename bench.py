@@ -257,8 +257,10 @@ def run_ours(a):
     # strong scaling: ownership is planned from cheap proxies (estimates scanned x gap-file bytes) with the library's
     # dealing rule, identically on every rank, so a rank parses, packs and uploads only the gaps it fills
     by_estimate = world > 1 and not weak and a.partition == "estimate"
+    by_record = not weak and a.partition == "record"      # every rank scans every unit over its block of the records
+    sess = [None]
     mine = list(range(len(gaps)))
-    if world > 1 and not weak and not by_estimate:
+    if world > 1 and not weak and not by_estimate and not by_record:
         from gapprober_b200.figbird import gap_range, partition_plan
         proxy = []
         for (c, s, l), path in zip(gaps, gap_files):
@@ -279,8 +281,17 @@ def run_ours(a):
         exchange_liks(fb, len(mine), device=torch.device("cuda", local))
         fb.runFinalize()
 
+    def open_session():
+        from gapprober_b200.multigpu import RecordShardSession
+        if sess[0] is not None:
+            sess[0].close()
+        sess[0] = RecordShardSession(fb, rank, world, device=torch.device("cuda", local), exchange=a.exchange)
+
     def run_device():
-        if by_estimate:
+        if by_record:
+            sess[0].scan()
+            fb.runFinalize()
+        elif by_estimate:
             fb.runScan()
             exchange_and_finalize()
         else:
@@ -288,7 +299,11 @@ def run_ours(a):
 
     def run_e2e():
         register()
-        if by_estimate:
+        if by_record:
+            open_session()                  # partition + upload + mapping of the peers' exchange buffers
+            sess[0].scan()
+            fb.runFinalize()
+        elif by_estimate:
             fb.upload()
             fb.runScan()
             exchange_and_finalize()
@@ -313,7 +328,10 @@ def run_ours(a):
 
     # ---- device-resident arm -------------------------------------------------------------------------
     register()
-    fb.upload()
+    if by_record:
+        open_session()
+    else:
+        fb.upload()
     for _ in range(a.warmup):
         run_device()
     sampler = ClockSampler(local)
@@ -330,7 +348,7 @@ def run_ours(a):
         st = fb.stats()
         em_ms += st["em_kernel_ms"]
         # CUDA-event time of the step; with the likelihood exchange in the middle the events do not span it, use the host clock
-        step_ms += st["step_ms"] if not by_estimate else 1e3 * (time.perf_counter() - t_step)
+        step_ms += st["step_ms"] if not (by_estimate or by_record) else 1e3 * (time.perf_counter() - t_step)
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
@@ -359,7 +377,7 @@ def run_ours(a):
     # a result checksum so the step cannot be optimised away: total filled length over owned gaps
     filled_total = 0
     for i, gf in enumerate(fb._gaps):
-        if not by_estimate or fb.hasResult(i):
+        if not (by_estimate or by_record) or fb.hasResult(i):
             filled_total += gf.result()["filled_len"]
     filled_total = int(allsum(float(filled_total)))
 
@@ -386,6 +404,7 @@ def run_ours(a):
                        "likelihoods_per_step_this_rank": st["likelihoods"], "l2": "flushed between steps (256 MiB write)",
                        "partition": ("rank r fills the gap set of seed+r (gap-partitioned, no data-path collective)" if weak else
                                      "(gap, estimate) units dealt to ranks by cost; per-estimate likelihoods all-gathered before finalize" if by_estimate else
+                                     f"record-sharded: every rank scans every unit over its block of the records; partial counts exchanged every iteration ({sess[0].exchange})" if by_record else
                                      "one gap set dealt to ranks by descending (estimates x gap-file bytes), no data-path collective"),
                        "filled_bases_total": filled_total, "host_wall_s": wall},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -418,6 +437,8 @@ def run_ours(a):
             else:
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": f"unavailable: {info}"}
         print(json.dumps(line))
+    if sess[0] is not None:
+        sess[0].close()
     fb.close()
     if world > 1:
         dist.destroy_process_group()
@@ -435,8 +456,11 @@ def main():
     ap.add_argument("--ref-liks", type=float, default=4.0e6, help="likelihoods per process per step in the reference arm")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
-    ap.add_argument("--partition", default="gap", choices=["gap", "estimate"],
-                    help="strong scaling only: deal gaps, or (gap, estimate) units when few gaps dominate")
+    ap.add_argument("--partition", default="gap", choices=["gap", "estimate", "record"],
+                    help="strong scaling only: deal gaps, (gap, estimate) units when few gaps dominate, or blocks of every gap's records "
+                         "(BASELINE config 3: partial counts exchanged every EM iteration)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="--partition record: peers' partial counts read over NVLink through CUDA IPC mappings (p2p) or all-gathered with NCCL")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":

@@ -64,6 +64,7 @@ struct HostGap {
     long gap_start;
     int orig, gmin, gmax;
     int rec_off, nrec, lmax;
+    int scan_off = 0, scan_n = -1;      // record-sharded scan: this context's block of the gap's records (-1 = all)
     bool owned = true;
     std::vector<char> est_owned;        // estimate-level partition: which estimates this context scans (empty = all)
     std::vector<long long> cons_off;    // per estimate: offset of its consensus on this device, -1 when scanned elsewhere
@@ -167,13 +168,18 @@ struct fb_ctx {
     std::vector<Bin> bins;
     bool uploaded = false, ran = false, scanned = false;
     bool unit_mode = false;   // partition by (gap, estimate) instead of by gap
+    bool rec_mode = false;    // record-sharded scan: every unit on every rank, records split in contiguous blocks
+    size_t shard_counts = 0, shard_maxprob = 0;   // doubles per partial-count buffer / per maxima buffer
 
     // device
     DevBuf<FbGapMeta> d_gapmeta;
     DevBuf<uint8_t> d_flank;
     DevBuf<uint4> d_codes, d_nmask;
     DevBuf<FbRecMeta> d_rmeta;
-    DevBuf<FbUnit> d_units;
+    DevBuf<FbUnit> d_units, d_units_scan;          // _scan: the units / gap metadata a record-sharded scan launches with
+    DevBuf<FbGapMeta> d_gapmeta_scan;
+    DevBuf<double> d_parts[2], d_sumcounts, d_maxmerge;
+    DevBuf<int> d_unit_nrec;
     DevBuf<int> d_counters;
     DevBuf<double> d_maxprob, d_gws, d_finprob, d_dump;
     DevBuf<char> d_cons;
@@ -297,6 +303,8 @@ void fb_destroy(fb_ctx* c) {
     c->d_units.release(); c->d_counters.release(); c->d_maxprob.release(); c->d_gws.release(); c->d_finprob.release();
     c->d_dump.release(); c->d_cons.release(); c->d_finpos.release(); c->d_gaplist.release(); c->d_bestgp.release();
     c->d_bestoff.release();
+    c->d_units_scan.release(); c->d_gapmeta_scan.release(); c->d_parts[0].release(); c->d_parts[1].release();
+    c->d_sumcounts.release(); c->d_maxmerge.release(); c->d_unit_nrec.release();
     c->h_maxprob.release(); c->h_finprob.release(); c->h_finpos.release(); c->h_stage.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -594,6 +602,8 @@ int fb_set_partition(fb_ctx* c, int rank, int world) {
         c->gaps[i].est_owned.clear();
     }
     c->unit_mode = false;
+    c->rec_mode = false;
+    for (HostGap& g : c->gaps) { g.scan_off = 0; g.scan_n = -1; }
     c->uploaded = c->ran = c->scanned = false;
     return FB_OK;
 }
@@ -603,6 +613,8 @@ int fb_set_partition_units(fb_ctx* c, int rank, int world) {
     c->part_rank = rank;
     c->part_world = world;
     c->unit_mode = world > 1;
+    c->rec_mode = false;
+    for (HostGap& g : c->gaps) { g.scan_off = 0; g.scan_n = -1; }
     // every (gap, estimate) unit is an independent EM run (figbird.cpp:2468-2501): deal units, not gaps
     std::vector<double> cost;
     std::vector<std::pair<int, int>> id;
@@ -628,8 +640,27 @@ int fb_set_partition_units(fb_ctx* c, int rank, int world) {
     return FB_OK;
 }
 
+int fb_set_partition_records(fb_ctx* c, int rank, int world) {
+    if (!c || world < 1 || world > FB_MAX_SHARDS || rank < 0 || rank >= world) return FB_EINVAL;
+    c->part_rank = rank;
+    c->part_world = world;
+    c->unit_mode = false;
+    c->rec_mode = true;
+    for (HostGap& g : c->gaps) {
+        g.owned = true;
+        g.est_owned.clear();
+        // contiguous blocks in file order: the rank-ordered sum of the partial counts then differs from the
+        // reference's record-by-record sum (figbird.cpp:1718, 1879) only in how the additions are grouped
+        g.scan_off = (int)((long)rank * g.nrec / world);
+        g.scan_n = (int)((long)(rank + 1) * g.nrec / world) - g.scan_off;
+    }
+    c->uploaded = c->ran = c->scanned = false;
+    return FB_OK;
+}
+
 int fb_owns_gap(fb_ctx* c, int gap) {
     if (!c || gap < 0 || gap >= (int)c->gaps.size()) return 0;
+    if (c->rec_mode) return gap % c->part_world == c->part_rank ? 1 : 0;   // who finalizes the gap
     return c->gaps[gap].owned ? 1 : 0;
 }
 
@@ -654,20 +685,29 @@ int fb_upload(fb_ctx* c) {
         if (!g.owned) return;
         GapUnits& out = per_gap[gi];
         long rec_bytes = 0;      // packed bases + mask + metadata in, per-record maximum out
-        for (int r = 0; r < g.nrec; r++) {
+        const int r0 = g.scan_off, r1 = g.scan_off + (g.scan_n < 0 ? g.nrec : g.scan_n);   // the records this context scans
+        for (int r = r0; r < r1; r++) {
             int L2 = c->h_rmeta[g.rec_off + r].flags & 0xff;
             rec_bytes += (L2 + 3) / 4 + (L2 + 7) / 8 + 8 + 8;
         }
         for (int gp = g.gmin; gp <= g.gmax; gp++) {
             if (!g.est_owned.empty() && !g.est_owned[gp - g.gmin]) continue;
             long liks = 0, terms = 0;
-            for (int r = 0; r < g.nrec; r++) {
+            for (int r = r0; r < r1; r++) {
                 const FbRecMeta& m = c->h_rmeta[g.rec_off + r];
                 long pl = placements(m, D, gp);
                 liks += pl;
                 terms += pl * (m.flags & 0xff);
             }
-            out.us.push_back({gi, gp, (double)terms + 2000.0, liks});
+            long order_terms = terms;
+            if (c->rec_mode) {      // the unit order fixes the layout of the exchange buffers: it must not depend on the rank
+                order_terms = 0;
+                for (int r = 0; r < g.nrec; r++) {
+                    const FbRecMeta& m = c->h_rmeta[g.rec_off + r];
+                    order_terms += placements(m, D, gp) * (m.flags & 0xff);
+                }
+            }
+            out.us.push_back({gi, gp, (double)order_terms + 2000.0, liks});
             out.liks += liks * c->num_iter;
             out.terms += terms * c->num_iter;
             out.bytes += (rec_bytes + 2L * 40 * gp) * c->num_iter;   // + counts out / profile in
@@ -678,7 +718,7 @@ int fb_upload(fb_ctx* c) {
     for (size_t gi = 0; gi < c->gaps.size(); gi++) {
         if (!c->gaps[gi].owned) continue;
         st.n_gaps++;
-        st.n_records += c->gaps[gi].nrec;
+        st.n_records += c->gaps[gi].scan_n < 0 ? c->gaps[gi].nrec : c->gaps[gi].scan_n;
         st.likelihoods += per_gap[gi].liks;
         st.base_terms += per_gap[gi].terms;
         st.algorithmic_bytes += per_gap[gi].bytes;
@@ -807,6 +847,32 @@ int fb_upload(fb_ctx* c) {
     FB_CUDA(c, up(c->d_nmask.p, c->h_nmask.data(), c->h_nmask.size() * sizeof(uint4)));
     FB_CUDA(c, up(c->d_rmeta.p, c->h_rmeta.data(), nr * sizeof(FbRecMeta)));
     FB_CUDA(c, up(c->d_units.p, c->h_units.data(), c->h_units.size() * sizeof(FbUnit)));
+    c->shard_counts = c->shard_maxprob = 0;
+    if (c->rec_mode) {
+        // the scan launches see only this rank's block of every gap; its maxima land at the block's place in the
+        // all-records layout so that the ranks' buffers merge element-wise
+        std::vector<FbGapMeta> gm_scan(c->h_gapmeta);
+        for (size_t gi = 0; gi < ng; gi++) {
+            gm_scan[gi].rec_off = c->gaps[gi].rec_off + c->gaps[gi].scan_off;
+            gm_scan[gi].nrec = c->gaps[gi].scan_n;
+        }
+        std::vector<FbUnit> u_scan(c->h_units);
+        for (FbUnit& u : u_scan) u.mp_off += c->gaps[u.gap].scan_off;
+        c->shard_counts = 5 * (size_t)co;
+        c->shard_maxprob = (size_t)mp;
+        FB_CUDA(c, c->d_gapmeta_scan.ensure(ng));
+        FB_CUDA(c, c->d_units_scan.ensure(u_scan.size()));
+        FB_CUDA(c, c->d_unit_nrec.ensure(c->unit_nrec.size()));
+        FB_CUDA(c, c->d_parts[0].ensure(c->shard_counts));
+        FB_CUDA(c, c->d_parts[1].ensure(c->shard_counts));
+        FB_CUDA(c, c->d_sumcounts.ensure(c->shard_counts));
+        FB_CUDA(c, c->d_maxmerge.ensure(c->shard_maxprob));
+        FB_CUDA(c, cudaMemcpyAsync(c->d_gapmeta_scan.p, gm_scan.data(), ng * sizeof(FbGapMeta), cudaMemcpyHostToDevice, c->stream));
+        FB_CUDA(c, cudaMemcpyAsync(c->d_units_scan.p, u_scan.data(), u_scan.size() * sizeof(FbUnit), cudaMemcpyHostToDevice, c->stream));
+        FB_CUDA(c, cudaMemcpyAsync(c->d_unit_nrec.p, c->unit_nrec.data(), c->unit_nrec.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        FB_CUDA(c, cudaStreamSynchronize(c->stream));   // the vectors above are pageable and local
+        h2d += (long)(ng * sizeof(FbGapMeta) + u_scan.size() * sizeof(FbUnit) + c->unit_nrec.size() * sizeof(int));
+    }
     FB_CUDA(c, cudaStreamSynchronize(c->stream));
     tr.lap("upload: alloc + H2D");
     st.h2d_bytes = h2d;
@@ -840,6 +906,20 @@ void fill_em_params(fb_ctx* c, FbEmParams& p) {
     p.gws = c->d_gws.p;
 }
 
+void fill_bin_params(fb_ctx* c, size_t bi, FbEmParams& p) {
+    const Bin& b = c->bins[bi];
+    fill_em_params(c, p);
+    p.units = c->d_units.p + b.first_unit;
+    p.n_units = b.n_units;
+    p.work_counter = c->d_counters.p + bi;
+    p.nr_stride = b.nr_stride;
+    p.gp_stride = b.gp_stride;
+    p.p_stride = b.p_stride;
+    p.chunk = b.chunk;
+    p.gws_stride = gws_stride_of(b.nr_stride, b.gp_stride);
+    p.gws = c->d_gws.p + b.gws_off;
+}
+
 }  // namespace
 
 extern "C" {
@@ -848,6 +928,7 @@ extern "C" {
 int fb_run_scan(fb_ctx* c) {
     if (!c) return FB_EINVAL;
     if (!c->uploaded) return c->fail(FB_ESTATE, "fb_run_scan before fb_upload");
+    if (c->rec_mode && c->part_world > 1) return c->fail(FB_ESTATE, "record-sharded partition: use fb_shard_scan_iter / fb_shard_scan_finish");
     FB_CUDA(c, cudaSetDevice(c->device));
     fb_stats& st = c->stats;
     long d2h = 0;
@@ -863,16 +944,7 @@ int fb_run_scan(fb_ctx* c) {
     for (size_t bi = 0; bi < c->bins.size(); bi++) {
         const Bin& b = c->bins[bi];
         FbEmParams p;
-        fill_em_params(c, p);
-        p.units = c->d_units.p + b.first_unit;
-        p.n_units = b.n_units;
-        p.work_counter = c->d_counters.p + bi;
-        p.nr_stride = b.nr_stride;
-        p.gp_stride = b.gp_stride;
-        p.p_stride = b.p_stride;
-        p.chunk = b.chunk;
-        p.gws_stride = gws_stride_of(b.nr_stride, b.gp_stride);
-        p.gws = c->d_gws.p + b.gws_off;
+        fill_bin_params(c, bi, p);
         // every bin runs on its own stream: as the persistent CTAs of one bin drain, CTAs of the next bin take over the
         // freed SMs, so only the last (smallest) bin has a tail
         cudaStream_t bs = c->bin_streams[bi];
@@ -958,6 +1030,7 @@ int fb_run_finalize(fb_ctx* c) {
         g.best_est = be;
         bestgp[gi] = be;
         if (g.cons_off[be - g.gmin] < 0) continue;   // the winner lives on another rank: that rank finalizes this gap
+        if (c->rec_mode && (int)(gi % c->part_world) != c->part_rank) continue;   // every rank could; the gaps are dealt round-robin
         cons_off_of_best[gi] = g.cons_off[be - g.gmin];
         gaplist.push_back((int)gi);
     }
@@ -1053,6 +1126,154 @@ int fb_run_finalize(fb_ctx* c) {
     }
     st.d2h_bytes = d2h;
     c->ran = true;
+    return FB_OK;
+}
+
+// ---- record-sharded scan (see include/figbird_cuda.h) ------------------------------------------------------------
+
+int fb_shard_sizes(fb_ctx* c, size_t* counts_doubles, size_t* maxprob_doubles) {
+    if (!c) return FB_EINVAL;
+    if (!c->uploaded || !c->rec_mode) return c->fail(FB_ESTATE, "fb_shard_sizes needs fb_set_partition_records + fb_upload");
+    if (counts_doubles) *counts_doubles = c->shard_counts;
+    if (maxprob_doubles) *maxprob_doubles = c->shard_maxprob;
+    return FB_OK;
+}
+
+int fb_shard_buffers(fb_ctx* c, double** counts_slot0, double** counts_slot1, double** maxprob) {
+    if (!c) return FB_EINVAL;
+    if (!c->uploaded || !c->rec_mode) return c->fail(FB_ESTATE, "fb_shard_buffers needs fb_set_partition_records + fb_upload");
+    if (counts_slot0) *counts_slot0 = c->d_parts[0].p;
+    if (counts_slot1) *counts_slot1 = c->d_parts[1].p;
+    if (maxprob) *maxprob = c->d_maxprob.p;
+    return FB_OK;
+}
+
+int fb_shard_scan_iter(fb_ctx* c, int it, const double* const* peer_counts, double* out_counts) {
+    if (!c || !out_counts) return FB_EINVAL;
+    if (!c->uploaded || !c->rec_mode) return c->fail(FB_ESTATE, "fb_shard_scan_iter needs fb_set_partition_records + fb_upload");
+    if (it < 0 || it >= c->num_iter || (it > 0 && !peer_counts)) return c->fail(FB_EINVAL, "iteration %d of %d", it, c->num_iter);
+    FB_CUDA(c, cudaSetDevice(c->device));
+    fb_stats& st = c->stats;
+    if (it == 0) {
+        st.em_launches = st.finalize_launches = 0;
+        st.finalize_likelihoods = 0;
+        st.finalize_kernel_ms = st.em_kernel_ms = 0;
+        st.d2h_bytes = 0;
+        c->scanned = c->ran = false;
+        FB_CUDA(c, cudaEventRecord(c->evs, c->stream));
+        // records scanned elsewhere keep 0 in this rank's maxima, so the ranks' buffers merge with max
+        FB_CUDA(c, cudaMemsetAsync(c->d_maxprob.p, 0, sizeof(double) * c->shard_maxprob, c->stream));
+    }
+    FB_CUDA(c, cudaMemsetAsync(c->d_counters.p, 0, sizeof(int) * (c->bins.size() + 1), c->stream));
+    FB_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    for (size_t bi = 0; bi < c->bins.size(); bi++) {
+        const Bin& b = c->bins[bi];
+        FbEmParams p;
+        fill_bin_params(c, bi, p);
+        p.units = c->d_units_scan.p + b.first_unit;
+        p.gaps = c->d_gapmeta_scan.p;
+        p.num_iter = 1;                       // one iteration per launch: the partial counts are exchanged in between
+        p.n_parts = it == 0 ? 0 : c->part_world;
+        for (int q = 0; q < p.n_parts; q++) {
+            if (!peer_counts[q]) return c->fail(FB_EINVAL, "peer_counts[%d] is null", q);
+            p.parts_in[q] = peer_counts[q];
+        }
+        p.part_out = out_counts;
+        cudaStream_t bs = c->bin_streams[bi];
+        FB_CUDA(c, cudaStreamWaitEvent(bs, c->ev0, 0));
+        FB_CUDA(c, fb_launch_em(p, b.grid, b.global_tables, b.smem, bs));
+        st.em_launches++;
+        FB_CUDA(c, cudaEventRecord(c->bin_done[bi], bs));
+        FB_CUDA(c, cudaStreamWaitEvent(c->stream, c->bin_done[bi], 0));
+    }
+    FB_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    FB_CUDA(c, cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    st.em_kernel_ms += ms;
+    return FB_OK;
+}
+
+int fb_shard_scan_finish(fb_ctx* c, const double* const* peer_counts, const double* const* peer_maxprob) {
+    if (!c || !peer_counts || !peer_maxprob) return FB_EINVAL;
+    if (!c->uploaded || !c->rec_mode) return c->fail(FB_ESTATE, "fb_shard_scan_finish needs fb_set_partition_records + fb_upload");
+    FB_CUDA(c, cudaSetDevice(c->device));
+    FbShardFinParams f;
+    memset(&f, 0, sizeof f);
+    f.units = c->d_units.p;
+    f.n_units = (int)c->h_units.size();
+    f.unit_nrec = c->d_unit_nrec.p;
+    f.n_parts = c->part_world;
+    for (int q = 0; q < f.n_parts; q++) {
+        if (!peer_counts[q] || !peer_maxprob[q]) return c->fail(FB_EINVAL, "peer buffer %d is null", q);
+        f.parts_in[q] = peer_counts[q];
+        f.maxprob_in[q] = peer_maxprob[q];
+    }
+    f.sum_counts = c->d_sumcounts.p;
+    f.maxprob_out = c->d_maxmerge.p;
+    f.unit_cons = c->d_cons.p;
+    FB_CUDA(c, fb_launch_shard_finish(f, c->stream));
+    FB_CUDA(c, cudaMemcpyAsync(c->h_maxprob.p, c->d_maxmerge.p, c->shard_maxprob * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    FB_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->stats.d2h_bytes = (long)(c->shard_maxprob * sizeof(double));
+    // likelihood per unit over ALL records of the gap, in record order (figbird.cpp:1951-1955): the same on every rank
+    for (HostGap& g : c->gaps) {
+        g.done = false;
+        g.liks.assign(g.gmax - g.gmin + 1, std::nan(""));
+        g.cons_off.assign(g.gmax - g.gmin + 1, -1);
+    }
+    for (const FbUnit& u : c->h_units) {
+        HostGap& g = c->gaps[u.gap];
+        const double* mp = c->h_maxprob.p + u.mp_off;
+        double lik = 0;
+        for (int r = 0; r < g.nrec; r++)
+            if (mp[r] > 0) lik += log(mp[r]);
+        g.liks[u.gp - g.gmin] = lik;
+        g.cons_off[u.gp - g.gmin] = u.cons_off;
+    }
+    c->scanned = true;
+    c->ran = false;
+    return FB_OK;
+}
+
+int fb_shard_counts(fb_ctx* c, int gap, int estimate, double* counts) {
+    if (!c || !counts || gap < 0 || gap >= (int)c->gaps.size()) return FB_EINVAL;
+    if (!c->scanned || !c->rec_mode) return c->fail(FB_ESTATE, "fb_shard_counts needs a finished record-sharded scan");
+    FB_CUDA(c, cudaSetDevice(c->device));
+    for (const FbUnit& u : c->h_units) {
+        if (u.gap != gap || u.gp != estimate) continue;
+        std::vector<double> cm((size_t)5 * u.gp);
+        FB_CUDA(c, cudaMemcpy(cm.data(), c->d_sumcounts.p + 5 * (size_t)u.cons_off, cm.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int x = 0; x < u.gp; x++)
+            for (int k = 0; k < 5; k++) counts[(size_t)x * 5 + k] = cm[(size_t)k * u.gp + x];
+        return FB_OK;
+    }
+    return c->fail(FB_EINVAL, "estimate %d is not in the scan range of gap %d", estimate, gap);
+}
+
+int fb_ipc_export(fb_ctx* c, const void* dev_ptr, unsigned char handle[64]) {
+    if (!c || !dev_ptr || !handle) return FB_EINVAL;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    FB_CUDA(c, cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    FB_CUDA(c, cudaIpcGetMemHandle(&h, const_cast<void*>(dev_ptr)));
+    memcpy(handle, &h, 64);
+    return FB_OK;
+}
+
+int fb_ipc_open(fb_ctx* c, const unsigned char handle[64], void** dev_ptr) {
+    if (!c || !handle || !dev_ptr) return FB_EINVAL;
+    FB_CUDA(c, cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    FB_CUDA(c, cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return FB_OK;
+}
+
+int fb_ipc_close(fb_ctx* c, void* dev_ptr) {
+    if (!c || !dev_ptr) return FB_EINVAL;
+    FB_CUDA(c, cudaSetDevice(c->device));
+    FB_CUDA(c, cudaIpcCloseMemHandle(dev_ptr));
     return FB_OK;
 }
 

@@ -8,6 +8,7 @@
 #define FB_MAX_READ 128          // longest mate the packed layout holds (2-bit codes in 2 x uint4)
 #define FB_THREADS 512           // CTA size of the EM kernel
 #define FB_FIN_THREADS 256       // CTA size of the finalize kernel
+#define FB_MAX_SHARDS 16         // ranks of a record-sharded scan
 
 // Per-record metadata, relative to the gap's profile window (row 0 = scaffold position gapStart - D).
 // u = row of the mate's first base for a placement.  Insert size of a placement:
@@ -64,6 +65,25 @@ struct FbEmParams {
     // global-memory tables for gaps too long for shared memory (one slice per CTA)
     double* gws;
     size_t gws_stride;      // doubles per CTA
+    // record-sharded scan (one launch per EM iteration, num_iter = 1): a unit's partial counts live at
+    // 5 * cons_off in every rank's exchange buffer, class-major [5][gp]
+    const double* parts_in[FB_MAX_SHARDS];   // last iteration's partial counts of every rank (own, peer-mapped or gathered)
+    int n_parts;                             // 0: first iteration, start from initialize()
+    double* part_out;                        // this rank's partial counts of this iteration (nullptr: not sharded)
+};
+
+// Closing step of a record-sharded scan: rank-ordered sum of the partial counts -> computeSequence(0); per-record
+// maxima merged over the ranks.
+struct FbShardFinParams {
+    const FbUnit* units;
+    int n_units;
+    const int* unit_nrec;                    // records of the unit's gap (all ranks' records)
+    const double* parts_in[FB_MAX_SHARDS];
+    const double* maxprob_in[FB_MAX_SHARDS]; // per rank: unit_maxprob in the global record layout, 0 where not owned
+    int n_parts;
+    double* sum_counts;                      // same layout as the partial counts
+    double* maxprob_out;
+    char* unit_cons;
 };
 
 struct FbFinParams {
@@ -89,4 +109,5 @@ struct FbFinParams {
 size_t fb_em_smem_bytes(int nr_stride, int gp_stride, int p_stride, int chunk, int pwin, bool global_tables);
 cudaError_t fb_launch_em(const FbEmParams& p, int grid, bool global_tables, size_t smem, cudaStream_t s);
 cudaError_t fb_launch_finalize(const FbFinParams& p, int n, size_t smem, cudaStream_t s);
+cudaError_t fb_launch_shard_finish(const FbShardFinParams& p, cudaStream_t s);
 cudaError_t fb_kernels_init(int* max_smem_optin, int* sm_count);

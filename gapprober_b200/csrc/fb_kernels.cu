@@ -280,6 +280,24 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
             int b = 4;
             if (x < D) b = fl[x];
             else if (x >= D + gp) b = fl[D + (x - D - gp)];
+            if (p.n_parts && b == 4) {
+                // record-sharded scan, iteration > 0: the counts of this gap row are the sum of every rank's partial
+                // counts of the previous iteration, always added in rank order
+                const size_t o = 5 * (size_t)unit.cons_off + (x - D);
+                double c[5];
+#pragma unroll
+                for (int k = 0; k < 5; k++) c[k] = p.parts_in[0][o + (size_t)k * gp];
+                for (int q = 1; q < p.n_parts; q++) {
+#pragma unroll
+                    for (int k = 0; k < 5; k++) c[k] = dadd(c[k], p.parts_in[q][o + (size_t)k * gp]);
+                }
+                double P[4], Q[5];
+                profile_row(c, sT, P, Q);
+#pragma unroll
+                for (int k = 0; k < 4; k++) s.pq[k * nrs + xr] = make_double2(P[k], Q[k]);
+                s.pq[4 * nrs + xr] = make_double2(0.0, Q[4]);
+                continue;
+            }
 #pragma unroll
             for (int k = 0; k < 5; k++) s.pq[k * nrs + xr] = sRow[b][k];
         }
@@ -486,6 +504,10 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
 #pragma unroll
                 for (int k = 0; k < 4; k++) s.pq[k * nrs + xr] = make_double2(P[k], Q[k]);
                 s.pq[4 * nrs + xr] = make_double2(0.0, Q[4]);
+                if (p.part_out) {
+#pragma unroll
+                    for (int k = 0; k < 5; k++) p.part_out[5 * (size_t)unit.cons_off + (size_t)k * gp + xg] = c[k];
+                }
                 if (last) {
                     // computeSequence(0), figbird.cpp:1991-2004: first strict maximum above 0, else index 0
                     double mx = 0.0;
@@ -601,6 +623,40 @@ __global__ void __launch_bounds__(FB_FIN_THREADS) fb_finalize_kernel(const FbFin
     }
 }
 
+// Closing step of a record-sharded scan.  Thread per gap row: the five counts summed over the ranks in rank order
+// (the same order the next iteration would have used), computeSequence(0) on the sum (figbird.cpp:1991-2004); thread
+// per record: the owner's per-record maximum (every other rank holds 0 there).
+__global__ void __launch_bounds__(256) fb_shard_finish_kernel(const FbShardFinParams p) {
+    for (int ui = blockIdx.x; ui < p.n_units; ui += gridDim.x) {
+        const FbUnit unit = p.units[ui];
+        const int gp = unit.gp;
+        for (int xg = threadIdx.x; xg < gp; xg += blockDim.x) {
+            const size_t o = 5 * (size_t)unit.cons_off + xg;
+            double c[5];
+#pragma unroll
+            for (int k = 0; k < 5; k++) c[k] = p.parts_in[0][o + (size_t)k * gp];
+            for (int q = 1; q < p.n_parts; q++) {
+#pragma unroll
+                for (int k = 0; k < 5; k++) c[k] = dadd(c[k], p.parts_in[q][o + (size_t)k * gp]);
+            }
+            double mx = 0.0;
+            int idx = 0;
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                p.sum_counts[o + (size_t)k * gp] = c[k];
+                if (c[k] > mx) { mx = c[k]; idx = k; }
+            }
+            p.unit_cons[unit.cons_off + xg] = "ACGTN"[idx];
+        }
+        const int nrec = p.unit_nrec[ui];
+        for (int r = threadIdx.x; r < nrec; r += blockDim.x) {
+            double m = p.maxprob_in[0][unit.mp_off + r];
+            for (int q = 1; q < p.n_parts; q++) m = fmax(m, p.maxprob_in[q][unit.mp_off + r]);
+            p.maxprob_out[unit.mp_off + r] = m;
+        }
+    }
+}
+
 }  // namespace
 
 size_t fb_em_smem_bytes(int nr_stride, int gp_stride, int p_stride, int chunk, int pwin, bool global_tables) {
@@ -630,5 +686,11 @@ cudaError_t fb_launch_em(const FbEmParams& p, int grid, bool global_tables, size
 
 cudaError_t fb_launch_finalize(const FbFinParams& p, int n, size_t smem, cudaStream_t s) {
     fb_finalize_kernel<<<n, FB_FIN_THREADS, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t fb_launch_shard_finish(const FbShardFinParams& p, cudaStream_t s) {
+    if (p.n_units < 1) return cudaSuccess;
+    fb_shard_finish_kernel<<<p.n_units < 4096 ? p.n_units : 4096, 256, 0, s>>>(p);
     return cudaGetLastError();
 }

@@ -84,6 +84,8 @@ ABI_SYMBOLS = [
     "fb_create", "fb_destroy", "fb_add_gap", "fb_add_gap_file", "fb_add_gap_files", "fb_set_partition", "fb_set_partition_units", "fb_run_scan", "fb_run_finalize", "fb_scan_liks", "fb_merge_liks", "fb_owns_gap", "fb_partition_plan", "fb_gap_cost", "fb_run", "fb_upload",
     "fb_run_device", "fb_result", "fb_estimate_liks", "fb_best_string", "fb_dump_profile", "fb_get_stats",
     "fb_clear_gaps", "fb_gap_range", "fb_last_error", "fb_status_str", "fb_abi_version",
+    "fb_set_partition_records", "fb_shard_sizes", "fb_shard_buffers", "fb_shard_scan_iter", "fb_shard_scan_finish",
+    "fb_shard_counts", "fb_ipc_export", "fb_ipc_open", "fb_ipc_close",
 ]
 
 _lib = None
@@ -131,6 +133,16 @@ def load_library():
     L.fb_status_str.argtypes = [C.c_int]
     L.fb_status_str.restype = C.c_char_p
     L.fb_abi_version.restype = C.c_int
+    dpp = C.POINTER(C.c_void_p)
+    L.fb_set_partition_records.argtypes = [vp, C.c_int, C.c_int]
+    L.fb_shard_sizes.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    L.fb_shard_buffers.argtypes = [vp, dpp, dpp, dpp]
+    L.fb_shard_scan_iter.argtypes = [vp, C.c_int, dpp, vp]
+    L.fb_shard_scan_finish.argtypes = [vp, dpp, dpp]
+    L.fb_shard_counts.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    L.fb_ipc_export.argtypes = [vp, vp, C.c_char_p]
+    L.fb_ipc_open.argtypes = [vp, C.c_char_p, dpp]
+    L.fb_ipc_close.argtypes = [vp, vp]
     _lib = L
     return L
 
@@ -385,6 +397,54 @@ class FigbirdContext:
     def setPartitionUnits(self, rank, world):
         """Deal (gap, estimate) units instead of gaps (for gap sets dominated by few gaps)."""
         self._check(self._L.fb_set_partition_units(self._h, rank, world))
+
+    def setPartitionRecords(self, rank, world):
+        """Record-sharded scan: every rank scans every unit over its block of each gap's records (include/figbird_cuda.h)."""
+        self._check(self._L.fb_set_partition_records(self._h, rank, world))
+        self._world = world
+
+    def shardSizes(self):
+        """(doubles per partial-count buffer, doubles of the per-record maxima buffer), after upload()."""
+        a, b = C.c_size_t(), C.c_size_t()
+        self._check(self._L.fb_shard_sizes(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def shardBuffers(self):
+        """Device addresses of this context's own exchange buffers: (counts slot 0, counts slot 1, maxima)."""
+        a, b, m = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(self._L.fb_shard_buffers(self._h, C.byref(a), C.byref(b), C.byref(m)))
+        return a.value, b.value, m.value
+
+    @staticmethod
+    def _ptr_array(ptrs):
+        return (C.c_void_p * len(ptrs))(*[int(x) for x in ptrs])
+
+    def shardScanIter(self, it, peer_counts, out_counts):
+        """One EM iteration over the local record blocks; peer_counts: device addresses of every rank's previous partial counts."""
+        arr = self._ptr_array(peer_counts) if peer_counts else None
+        self._check(self._L.fb_shard_scan_iter(self._h, int(it), arr, C.c_void_p(int(out_counts))))
+
+    def shardScanFinish(self, peer_counts, peer_maxprob):
+        self._check(self._L.fb_shard_scan_finish(self._h, self._ptr_array(peer_counts), self._ptr_array(peer_maxprob)))
+
+    def shardCounts(self, index, estimate):
+        """Summed counts of the gap rows of one unit after shardScanFinish, [estimate][5]."""
+        out = np.zeros((int(estimate), 5))
+        self._check(self._L.fb_shard_counts(self._h, index, int(estimate), out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def ipcExport(self, dev_ptr):
+        buf = C.create_string_buffer(64)
+        self._check(self._L.fb_ipc_export(self._h, C.c_void_p(int(dev_ptr)), buf))
+        return buf.raw
+
+    def ipcOpen(self, handle):
+        out = C.c_void_p()
+        self._check(self._L.fb_ipc_open(self._h, C.c_char_p(bytes(handle)), C.byref(out)))
+        return out.value
+
+    def ipcClose(self, dev_ptr):
+        self._check(self._L.fb_ipc_close(self._h, C.c_void_p(int(dev_ptr))))
 
     def runScan(self):
         self._check(self._L.fb_run_scan(self._h))

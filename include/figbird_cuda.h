@@ -12,6 +12,8 @@
 #ifndef FIGBIRD_CUDA_H
 #define FIGBIRD_CUDA_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -133,6 +135,39 @@ int fb_scan_liks(fb_ctx* ctx, int gap, double* liks, int cap);
 int fb_merge_liks(fb_ctx* ctx, int gap, const double* liks, int n);
 /* 1 if gap `gap` is run by this context under the current partition. */
 int fb_owns_gap(fb_ctx* ctx, int gap);
+
+/* Record-sharded scan — north_star's "by read where one gap dominates" and BASELINE config 3.  Every rank
+ * scans every (gap, estimate) unit, but only over its contiguous block of each gap's records (figbird.cpp:1718 reads
+ * them in file order; rank r takes records [r*R/world, (r+1)*R/world)).  The M-step sums of figbird.cpp:1874-1881 /
+ * 1940-1947 are then partial: after every one of the num_iter iterations the partial counts of all ranks are added, in
+ * rank order, by the kernel that starts the next iteration (it reads the peers' buffers directly: own memory,
+ * peer-mapped memory of the other GPUs over NVLink, or a gathered copy — the library only sees device pointers).
+ * The summation order inside a rank is the reference's; across ranks it is ((p0 + p1) + p2) + ...: counts and
+ * probabilities agree with the single-GPU path to rounding (1e-5 relative is the bar, observed ~1e-15), filled
+ * sequences are identical unless a cell ties to the last bit.  Call order, on every rank:
+ *     fb_set_partition_records; fb_upload;
+ *     for it in 0 .. num_iter-1:  fb_shard_scan_iter(it, peers' buffers of slot (it-1)&1, own buffer of slot it&1);  barrier
+ *     fb_shard_scan_finish(peers' buffers of slot (num_iter-1)&1, peers' maxima);  barrier;  fb_run_finalize
+ * fb_run_finalize then fills the gaps whose index is congruent to `rank` modulo `world` (fb_owns_gap tells).        */
+int fb_set_partition_records(fb_ctx* ctx, int rank, int world);
+/* Sizes (in doubles) of one partial-count buffer and of the per-record maxima buffer, valid after fb_upload. */
+int fb_shard_sizes(fb_ctx* ctx, size_t* counts_doubles, size_t* maxprob_doubles);
+/* This context's own exchange buffers (device memory from cudaMalloc, exportable with fb_ipc_export). */
+int fb_shard_buffers(fb_ctx* ctx, double** counts_slot0, double** counts_slot1, double** maxprob);
+/* One EM iteration over the local record blocks.  peer_counts: `world` device pointers (rank order, own included) to
+ * the previous iteration's partial counts, ignored for it == 0.  out_counts: where this iteration's partial counts
+ * go.  Returns when the iteration has finished on the device. */
+int fb_shard_scan_iter(fb_ctx* ctx, int it, const double* const* peer_counts, double* out_counts);
+/* Sum the last iteration's partial counts (rank order) -> consensus per unit; merge the per-record maxima of the
+ * ranks -> likelihood per estimate (identical on every rank).  Leaves the context as fb_run_scan does. */
+int fb_shard_scan_finish(fb_ctx* ctx, const double* const* peer_counts, const double* const* peer_maxprob);
+/* Parity tap: summed counts of the gap rows of one unit after fb_shard_scan_finish, laid out [estimate][5]. */
+int fb_shard_counts(fb_ctx* ctx, int gap, int estimate, double* counts);
+/* CUDA IPC plumbing for one-process-per-GPU runs: export a cudaMalloc'ed buffer as a 64-byte handle, map a peer's
+ * handle into this process (reads then go over NVLink), unmap it. */
+int fb_ipc_export(fb_ctx* ctx, const void* dev_ptr, unsigned char handle[64]);
+int fb_ipc_open(fb_ctx* ctx, const unsigned char handle[64], void** dev_ptr);
+int fb_ipc_close(fb_ctx* ctx, void* dev_ptr);
 /* The dealing rule itself, as pure host code (no GPU needed): items by descending cost, each to the least loaded
  * rank, ties to the lower rank; owner[i] receives the rank of item i.  fb_set_partition applies it to fb_gap_cost. */
 int fb_partition_plan(const double* cost, int n, int world, int* owner);
