@@ -44,7 +44,7 @@ def prepare_workload(cfg, seed):
     if not os.path.exists(done):
         if os.path.isdir(wd):
             shutil.rmtree(wd)
-        args = list(synth.CONFIGS[cfg])
+        args = synth.config_args(cfg)
         if "--model-pairs" not in args:
             args += ["--model-pairs", "200000"]   # the model is learned from a 200k-pair sample of the proper pairs
         synth.generate(wd, args, seed=seed)

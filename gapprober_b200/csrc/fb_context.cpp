@@ -129,8 +129,10 @@ struct Bin {
     int gpmax, lmax;
     int nr_stride, gp_stride, p_stride, chunk;
     bool global_tables;
+    int ctas_per_sm;
+    int cluster;      // CTAs per unit (thread-block cluster) when the launch has fewer units than the GPU has CTA slots; 1 = one CTA per unit
     size_t smem;
-    int grid;
+    int grid;         // CTAs, or clusters when cluster > 1
     size_t gws_off;   // doubles: this bin's slice of the global workspace (bins run concurrently)
 };
 
@@ -794,9 +796,38 @@ int fb_upload(fb_ctx* c) {
         }
         b.smem = fb_em_smem_bytes(b.nr_stride, b.gp_stride, b.p_stride, b.chunk, pwin, b.global_tables);
         b.grid = std::min(b.n_units, c->sm_count * ctas);
+        b.cluster = 1;
+        b.ctas_per_sm = ctas;
         b.gws_off = gws_need;
         if (b.global_tables) gws_need += (size_t)b.grid * gws_stride_of(b.nr_stride, b.gp_stride);
     }
+    // Few units (a single gap, the stress sweep): most SMs would idle with one CTA per unit.  Give every unit a
+    // thread-block cluster instead — as many CTAs as keep all units of all bins co-resident, at most 8 (the portable limit).
+    {
+        long cta_need = 0;      // SM-halves the launches would occupy with one CTA per unit
+        for (const Bin& b : c->bins) cta_need += (long)b.n_units * (b.ctas_per_sm == 2 ? 1 : 2);
+        int want = 1;
+        const char* force = getenv("FB_CLUSTER");        // tuning / test knob: 1 disables, 2/4/8 forces
+        if (force) want = std::max(1, std::min(8, atoi(force)));
+        else
+            while (want < 8 && cta_need * want * 2 <= 2L * c->sm_count) want *= 2;
+        for (Bin& b : c->bins) {
+            if (b.global_tables) continue;
+            for (int cl = want; cl > 1; cl >>= 1) {
+                int fit = 0;
+                if (fb_em_max_clusters(cl, b.smem, &fit) == cudaSuccess && fit > 0) {
+                    b.cluster = cl;
+                    b.grid = std::min(b.n_units, fit);
+                    break;
+                }
+                cudaGetLastError();
+            }
+        }
+    }
+    if (tr.on)
+        for (const Bin& b : c->bins)
+            fprintf(stderr, "[fb_trace] bin: %d units, estimates <= %d, chunk %d, smem %zu, %s, cluster %d, grid %d\n", b.n_units, b.gpmax,
+                    b.chunk, b.smem, b.global_tables ? "global tables" : b.ctas_per_sm == 2 ? "2 CTAs/SM" : "1 CTA/SM", b.cluster, b.grid);
     tr.lap("upload: units + bins");
     while (c->bin_done.size() < c->bins.size()) {
         cudaEvent_t a, b;
@@ -906,6 +937,11 @@ void fill_em_params(fb_ctx* c, FbEmParams& p) {
     p.gws = c->d_gws.p;
 }
 
+cudaError_t launch_bin(const Bin& b, const FbEmParams& p, cudaStream_t s) {
+    if (b.cluster > 1) return fb_launch_em_cluster(p, b.grid, b.cluster, b.smem, s);
+    return fb_launch_em(p, b.grid, b.global_tables, b.smem, s);
+}
+
 void fill_bin_params(fb_ctx* c, size_t bi, FbEmParams& p) {
     const Bin& b = c->bins[bi];
     fill_em_params(c, p);
@@ -949,7 +985,7 @@ int fb_run_scan(fb_ctx* c) {
         // freed SMs, so only the last (smallest) bin has a tail
         cudaStream_t bs = c->bin_streams[bi];
         FB_CUDA(c, cudaStreamWaitEvent(bs, c->ev0, 0));
-        FB_CUDA(c, fb_launch_em(p, b.grid, b.global_tables, b.smem, bs));
+        FB_CUDA(c, launch_bin(b, p, bs));
         st.em_launches++;
         // this bin's slice of unit_maxprob goes home on the copy stream while the other bins compute
         FB_CUDA(c, cudaEventRecord(c->bin_done[bi], bs));
@@ -1066,7 +1102,12 @@ int fb_run_finalize(fb_ctx* c) {
         f.gmax_stride = rows;
         if ((size_t)rows + 16 > (size_t)c->max_smem - 8192) return c->fail(FB_EINVAL, "gap estimate %d too long for finalize", rows);
         FB_CUDA(c, cudaEventRecord(c->ev2, c->stream));
-        FB_CUDA(c, fb_launch_finalize(f, (int)gaplist.size(), (size_t)rows + 16, c->stream));
+        // records are independent in finalize: enough CTAs per gap to fill the GPU, at least one record per warp
+        int max_nrec = 1;
+        for (int gi : gaplist) max_nrec = std::max(max_nrec, c->gaps[gi].nrec);
+        const int per_cta = FB_FIN_THREADS / 32;
+        const int slices = std::max(1, std::min((4 * c->sm_count + (int)gaplist.size() - 1) / (int)gaplist.size(), (max_nrec + per_cta - 1) / per_cta));
+        FB_CUDA(c, fb_launch_finalize(f, (int)gaplist.size(), slices, (size_t)rows + 16, c->stream));
         FB_CUDA(c, cudaEventRecord(c->ev3, c->stream));
         st.finalize_launches = 1;
         const size_t nr = c->h_rmeta.size();
@@ -1181,7 +1222,7 @@ int fb_shard_scan_iter(fb_ctx* c, int it, const double* const* peer_counts, doub
         p.part_out = out_counts;
         cudaStream_t bs = c->bin_streams[bi];
         FB_CUDA(c, cudaStreamWaitEvent(bs, c->ev0, 0));
-        FB_CUDA(c, fb_launch_em(p, b.grid, b.global_tables, b.smem, bs));
+        FB_CUDA(c, launch_bin(b, p, bs));
         st.em_launches++;
         FB_CUDA(c, cudaEventRecord(c->bin_done[bi], bs));
         FB_CUDA(c, cudaStreamWaitEvent(c->stream, c->bin_done[bi], 0));

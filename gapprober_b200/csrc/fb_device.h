@@ -108,6 +108,10 @@ struct FbFinParams {
 
 size_t fb_em_smem_bytes(int nr_stride, int gp_stride, int p_stride, int chunk, int pwin, bool global_tables);
 cudaError_t fb_launch_em(const FbEmParams& p, int grid, bool global_tables, size_t smem, cudaStream_t s);
-cudaError_t fb_launch_finalize(const FbFinParams& p, int n, size_t smem, cudaStream_t s);
+// cluster variant: n_clusters thread-block clusters of `cluster` CTAs, each cluster running one unit at a time
+cudaError_t fb_launch_em_cluster(const FbEmParams& p, int n_clusters, int cluster, size_t smem, cudaStream_t s);
+cudaError_t fb_em_max_clusters(int cluster, size_t smem, int* n);     // co-resident clusters of that size on this device
+// n gaps x `slices` CTAs per gap (a CTA takes every slices-th group of 8 records)
+cudaError_t fb_launch_finalize(const FbFinParams& p, int n, int slices, size_t smem, cudaStream_t s);
 cudaError_t fb_launch_shard_finish(const FbShardFinParams& p, cudaStream_t s);
 cudaError_t fb_kernels_init(int* max_smem_optin, int* sm_count);

@@ -30,6 +30,10 @@
 
 #include "fb_device.h"
 
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
+
 namespace {
 
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
@@ -217,9 +221,28 @@ __device__ __forceinline__ void score_pair(const unsigned char* pa, const uint32
     }
 }
 
-template <bool GT>
+// CLU: one unit is run by a thread-block cluster instead of one CTA — for launches with fewer units than the GPU has
+// CTA slots (single gaps, the stress sweep).  Nothing about the arithmetic changes, so results stay bit-exact:
+//   * every CTA keeps a full copy of the P/Q table and of the two score buffers in its own shared memory;
+//   * E tasks are dealt to the CTAs by record; a task writes its score row into every CTA's buffer (DSMEM stores:
+//     one row of scores per ~100 rows' worth of table reads, so the remote traffic is negligible);
+//   * M tasks are dealt by 32-row block: a CTA owns the counts of its row blocks and adds to them in the reference's
+//     order from its local copy of the scores;
+//   * the profile update of a row is done by the owner of its counts and broadcast to every CTA's table;
+//   * the per-round barrier becomes a cluster barrier.
+template <bool GT, bool CLU>
 __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __grid_constant__ FbEmParams p) {
+    static_assert(!(GT && CLU), "the cluster variant keeps its tables in shared memory");
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned crank = 0, csize = 1;
+    if (CLU) {
+        crank = cg::this_cluster().block_rank();
+        csize = cg::this_cluster().num_blocks();
+    }
+    auto sync_all = [&]() {
+        if (CLU) cg::this_cluster().sync();
+        else __syncthreads();
+    };
     EmSmem s;
     const int pwin = p.thr_max - p.thr_min + 1;
     em_carve(smem_raw, &s, p.nr_stride, p.gp_stride, p.p_stride, p.chunk, pwin, GT);
@@ -258,12 +281,17 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
     }
 
     for (;;) {
-        __syncthreads();
+        sync_all();
         if (tid == 0) {
-            s_unit = atomicAdd(p.work_counter, 1);
+            if (!CLU) {
+                s_unit = atomicAdd(p.work_counter, 1);
+            } else if (crank == 0) {
+                const int u = atomicAdd(p.work_counter, 1);
+                for (unsigned k = 0; k < csize; k++) *cg::this_cluster().map_shared_rank(&s_unit, k) = u;
+            }
             s_queue[0] = 0;
         }
-        __syncthreads();
+        sync_all();
         const int ui = s_unit;
         if (ui >= p.n_units) break;
         const FbUnit unit = p.units[ui];
@@ -325,9 +353,15 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
                 const Stage SL = stage_at(s, cl % 3), SE = stage_at(s, (ce + 3) % 3), SM = stage_at(s, (cm + 3) % 3);
                 double* wE = s.w0 + ((ce + 2) & 1) * s.w_stride;
                 const double* wM = s.w0 + ((cm + 2) & 1) * s.w_stride;
-                if (last && tid < n_m)   // per-record maximum of the last iteration (feeds figbird.cpp:1951-1955 on the host)
-                    p.unit_maxprob[unit.mp_off + cm * CH + tid] = __longlong_as_double((long long)SM.rmax[tid]);
-                const int tM = n_m ? nrb * 5 : 0, tE = n_e * nblk, tL = n_l;
+                if (last && tid < n_m) {   // per-record maximum of the last iteration (feeds figbird.cpp:1951-1955 on the host)
+                    if (!CLU) p.unit_maxprob[unit.mp_off + cm * CH + tid] = __longlong_as_double((long long)SM.rmax[tid]);
+                    else if ((unsigned)tid % csize == crank)   // all E tasks of a record run in one CTA: it holds the maximum
+                        p.unit_maxprob[unit.mp_off + cm * CH + tid] = __longlong_as_double((long long)SM.rmax[tid]);
+                }
+                // a cluster deals E tasks by record and M tasks by row block; staging is done by every CTA for itself
+                const int nrb_q = CLU ? (nrb + (int)csize - 1 - (int)crank) / (int)csize : nrb;
+                const int ne_q = CLU ? (n_e + (int)csize - 1 - (int)crank) / (int)csize : n_e;
+                const int tM = n_m ? nrb_q * 5 : 0, tE = ne_q * nblk, tL = n_l;
                 const int ntask = tM + tE + tL;
                 int* queue = &s_queue[round & 1];
                 for (;;) {
@@ -342,7 +376,7 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
                         // zero-filled tail), so a row that is not inside the window for some entry adds +0.0 — exact: the
                         // accumulators are sums of non-negative scores (or NaN), never -0.0 — and the loop needs no predicates:
                         // per entry one LDS.64 + DADD, list positions fetched four at a time.
-                        const int c = task / nrb, rb = task - c * nrb;
+                        const int c = task / nrb_q, rb = CLU ? (task - c * nrb_q) * (int)csize + (int)crank : task - c * nrb_q;
                         const int xg = rb * 32 + lane, x0 = D + rb * 32;
                         const bool ok0 = xg < gp;
                         double* cr = s.cnt + c * gps + xg;
@@ -386,13 +420,22 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
                         // ---- E-step: warp per (record, 64 placements); lanes over placements.  Every slot of the record's score row is
                         // written: the score inside the window, 0.0 outside it (the M-step relies on those zeros).
                         const int te = task - tM;
-                        const int rl = te / nblk, blk = te - rl * nblk;
+                        const int rq = te / nblk, blk = te - rq * nblk;
+                        const int rl = CLU ? rq * (int)csize + (int)crank : rq;
                         const int lo = SE.rlo[rl], hi = SE.rhi[rl];
                         double* wrow = wE + kPadW + rl * WS;                  // slot k holds placement lo + k
                         const int ka = 64 * blk + lane, kb = ka + 32;
                         if (lo + 64 * blk > hi) {                              // nothing of the window in this block (or no window at all)
-                            if (ka < PS) wrow[ka] = 0.0;
-                            if (kb < PS) wrow[kb] = 0.0;
+                            if (!CLU) {
+                                if (ka < PS) wrow[ka] = 0.0;
+                                if (kb < PS) wrow[kb] = 0.0;
+                            } else {
+                                for (unsigned k = 0; k < csize; k++) {
+                                    double* wr = cg::this_cluster().map_shared_rank(wrow, k);
+                                    if (ka < PS) wr[ka] = 0.0;
+                                    if (kb < PS) wr[kb] = 0.0;
+                                }
+                            }
                             continue;
                         }
                         const int fl2 = SE.rfl[rl], L2 = fl2 & 0xff, tb = SE.rtb[rl];
@@ -414,8 +457,16 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
                             if (rev) score_pair<true, false>(pa, cls4, cstride, p, L2, sa, sb);
                             else score_pair<false, false>(pa, cls4, cstride, p, L2, sa, sb);
                         }
-                        if (ka < PS) wrow[ka] = va_ok ? sa : 0.0;
-                        if (kb < PS) wrow[kb] = vb_ok ? sb : 0.0;
+                        if (!CLU) {
+                            if (ka < PS) wrow[ka] = va_ok ? sa : 0.0;
+                            if (kb < PS) wrow[kb] = vb_ok ? sb : 0.0;
+                        } else {
+                            for (unsigned k = 0; k < csize; k++) {   // the M tasks of every CTA read this row from their own copy
+                                double* wr = cg::this_cluster().map_shared_rank(wrow, k);
+                                if (ka < PS) wr[ka] = va_ok ? sa : 0.0;
+                                if (kb < PS) wr[kb] = vb_ok ? sb : 0.0;
+                            }
+                        }
                         // tempProb > maxProb with maxProb starting at 0: NaN and non-positive scores never win
                         unsigned long long ba = (va_ok && sa > 0.0) ? (unsigned long long)__double_as_longlong(sa) : 0ull;
                         unsigned long long bb = (vb_ok && sb > 0.0) ? (unsigned long long)__double_as_longlong(sb) : 0ull;
@@ -488,22 +539,32 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
                     }
                 }
                 if (tid == 0) s_queue[(round + 1) & 1] = 0;   // nobody touches the other slot during this round
-                __syncthreads();
+                sync_all();
             }
 
             // chunk 0 of a kept staging gets its per-record maxima reset here, a barrier ahead of the next iteration's E tasks
             if (keep_staged && !last && tid < min(CH, nrec)) stage_at(s, 0).rmax[tid] = 0ull;
             // ---- computeProbsGap + computeErrorProbsGap on the gap rows (flank rows never change)
             for (int xg = tid; xg < gp; xg += FB_THREADS) {
+                if (CLU && (unsigned)(xg >> 5) % csize != crank) continue;   // the counts of this row live in another CTA
                 double c[5];
 #pragma unroll
                 for (int k = 0; k < 5; k++) c[k] = s.cnt[k * gps + xg];
                 double P[4], Q[5];
                 profile_row(c, sT, P, Q);
                 const int xr = xg + lmax - 1;
+                if (!CLU) {
 #pragma unroll
-                for (int k = 0; k < 4; k++) s.pq[k * nrs + xr] = make_double2(P[k], Q[k]);
-                s.pq[4 * nrs + xr] = make_double2(0.0, Q[4]);
+                    for (int k = 0; k < 4; k++) s.pq[k * nrs + xr] = make_double2(P[k], Q[k]);
+                    s.pq[4 * nrs + xr] = make_double2(0.0, Q[4]);
+                } else {
+                    for (unsigned q = 0; q < csize; q++) {
+                        double2* pq = cg::this_cluster().map_shared_rank(s.pq, q);
+#pragma unroll
+                        for (int k = 0; k < 4; k++) pq[k * nrs + xr] = make_double2(P[k], Q[k]);
+                        pq[4 * nrs + xr] = make_double2(0.0, Q[4]);
+                    }
+                }
                 if (p.part_out) {
 #pragma unroll
                     for (int k = 0; k < 5; k++) p.part_out[5 * (size_t)unit.cons_off + (size_t)k * gp + xg] = c[k];
@@ -521,7 +582,7 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
                     for (int k = 0; k < 5; k++) s.cnt[k * gps + xg] = 0.0;   // placeReads zeroes the gap rows, :1708-1714
                 }
             }
-            __syncthreads();
+            sync_all();
         }
 
         // ---- parity tap: the whole profile of one unit, laid out like probsGap/countsGap
@@ -551,15 +612,15 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
 
 // finalize(), figbird.cpp:2239-2291 / 2310-2359: score every placement of every record against the
 // winning consensus (+ flanks) with the match/mismatch model and keep the best placement, lowest
-// position on ties.  One CTA per gap.  The cut-off test (-log(maxProb) <= gapProbCutOff), the +1
-// counting and computeSequence(1) are done by the host from (maxProb, maxPos).
+// position on ties.  The records of a gap are independent here: CTA (gap, slice) takes every
+// gridDim.y-th group of records, one record per warp, lanes over placements.  The cut-off test
+// (-log(maxProb) <= gapProbCutOff), the +1 counting and computeSequence(1) are done by the host
+// from (maxProb, maxPos).
 __global__ void __launch_bounds__(FB_FIN_THREADS) fb_finalize_kernel(const FbFinParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint8_t* gcode = smem_raw;                                     // [gmax_stride] codes of flank+best+flank window
-    __shared__ uint8_t cs[FB_MAX_READ];
+    __shared__ __align__(16) uint8_t cs_all[FB_FIN_THREADS / 32][FB_MAX_READ];
     __shared__ double sT[25];
-    __shared__ double red_v[FB_FIN_THREADS / 32];
-    __shared__ int red_u[FB_FIN_THREADS / 32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = p.gap_list[blockIdx.x];
@@ -581,17 +642,19 @@ __global__ void __launch_bounds__(FB_FIN_THREADS) fb_finalize_kernel(const FbFin
     }
     __syncthreads();
 
-    for (int r = 0; r < gm.nrec; r++) {
+    uint8_t* cs = cs_all[warp];
+    const int nwarp = FB_FIN_THREADS / 32;
+    for (int r = blockIdx.y * nwarp + warp; r < gm.nrec; r += gridDim.y * nwarp) {
         const int rec = gm.rec_off + r;
         const FbRecMeta rm = p.rmeta[rec];
         const int L2 = rm.flags & 0xff;
         const bool rev = (rm.flags >> 8) & 1, left = (rm.flags >> 9) & 1;
-        if (warp == 0) load_record_bytes(p.codes, p.nmask, rec, L2, cs, lane);
-        __syncthreads();
+        __syncwarp();
+        load_record_bytes(p.codes, p.nmask, rec, L2, cs, lane);
         const int lo = max(rm.a_lo, D - L2 + 1), hi = min(rm.a_hi, D + gb - 1);
         double bv = 0.0;
         int bu = 0x7fffffff;
-        for (int u = lo + tid; u <= hi; u += FB_FIN_THREADS) {
+        for (int u = lo + lane; u <= hi; u += 32) {
             const int t = left ? u + rm.tb : rm.tb - u;
             double sc = p.ild[t - p.thr_min];
             for (int j = 0; j < L2; j++) {
@@ -600,26 +663,19 @@ __global__ void __launch_bounds__(FB_FIN_THREADS) fb_finalize_kernel(const FbFin
                 if (from == to) sc = dmul(sc, p.match[k]);                          // figbird.cpp:2272
                 else sc = dmul(sc, dmul(p.epos[k], sT[from * 5 + to]));             // figbird.cpp:2276
             }
-            if (sc > bv) { bv = sc; bu = u; }   // ascending u per thread: first maximum kept
+            if (sc > bv) { bv = sc; bu = u; }   // ascending u per lane: first maximum kept
         }
-        // block arg-max, lowest placement wins ties (figbird.cpp:2280: strict '>' in ascending i)
+        // warp arg-max, lowest placement wins ties (figbird.cpp:2280: strict '>' in ascending i)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             double ov = __shfl_xor_sync(0xffffffffu, bv, o);
             int ou = __shfl_xor_sync(0xffffffffu, bu, o);
             if (ov > bv || (ov == bv && ou < bu)) { bv = ov; bu = ou; }
         }
-        if (lane == 0) { red_v[warp] = bv; red_u[warp] = bu; }
-        __syncthreads();
-        if (tid == 0) {
-            double v = 0.0;
-            int uu = 0x7fffffff;
-            for (int w = 0; w < FB_FIN_THREADS / 32; w++)
-                if (red_v[w] > v || (red_v[w] == v && red_u[w] < uu)) { v = red_v[w]; uu = red_u[w]; }
-            p.fin_maxprob[rec] = v;
-            p.fin_maxpos[rec] = v > 0.0 ? uu : 0;   // maxPos stays 0 when nothing scored above 0 (figbird.cpp:2235)
+        if (lane == 0) {
+            p.fin_maxprob[rec] = bv;
+            p.fin_maxpos[rec] = bv > 0.0 ? bu : 0;   // maxPos stays 0 when nothing scored above 0 (figbird.cpp:2235)
         }
-        __syncthreads();
     }
 }
 
@@ -671,21 +727,51 @@ cudaError_t fb_kernels_init(int* max_smem_optin, int* sm_count) {
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(fb_em_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, *max_smem_optin - 1024);
+    e = cudaFuncSetAttribute(fb_em_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, *max_smem_optin - 1024);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(fb_em_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, *max_smem_optin - 1024);
+    e = cudaFuncSetAttribute(fb_em_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, *max_smem_optin - 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(fb_em_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, *max_smem_optin - 1024);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(fb_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, *max_smem_optin - 8192);
 }
 
 cudaError_t fb_launch_em(const FbEmParams& p, int grid, bool global_tables, size_t smem, cudaStream_t s) {
-    if (global_tables) fb_em_kernel<true><<<grid, FB_THREADS, smem, s>>>(p);
-    else fb_em_kernel<false><<<grid, FB_THREADS, smem, s>>>(p);
+    if (global_tables) fb_em_kernel<true, false><<<grid, FB_THREADS, smem, s>>>(p);
+    else fb_em_kernel<false, false><<<grid, FB_THREADS, smem, s>>>(p);
     return cudaGetLastError();
 }
 
-cudaError_t fb_launch_finalize(const FbFinParams& p, int n, size_t smem, cudaStream_t s) {
-    fb_finalize_kernel<<<n, FB_FIN_THREADS, smem, s>>>(p);
+static void cluster_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, int grid, int cluster, size_t smem, cudaStream_t s) {
+    *cfg = cudaLaunchConfig_t{};
+    cfg->gridDim = dim3((unsigned)grid, 1, 1);
+    cfg->blockDim = dim3(FB_THREADS, 1, 1);
+    cfg->dynamicSmemBytes = smem;
+    cfg->stream = s;
+    attr->id = cudaLaunchAttributeClusterDimension;
+    attr->val.clusterDim.x = (unsigned)cluster;
+    attr->val.clusterDim.y = 1;
+    attr->val.clusterDim.z = 1;
+    cfg->attrs = attr;
+    cfg->numAttrs = 1;
+}
+
+cudaError_t fb_em_max_clusters(int cluster, size_t smem, int* n) {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr;
+    cluster_config(&cfg, &attr, cluster, cluster, smem, nullptr);
+    return cudaOccupancyMaxActiveClusters(n, fb_em_kernel<false, true>, &cfg);
+}
+
+cudaError_t fb_launch_em_cluster(const FbEmParams& p, int n_clusters, int cluster, size_t smem, cudaStream_t s) {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr;
+    cluster_config(&cfg, &attr, n_clusters * cluster, cluster, smem, s);
+    return cudaLaunchKernelEx(&cfg, fb_em_kernel<false, true>, p);
+}
+
+cudaError_t fb_launch_finalize(const FbFinParams& p, int n, int slices, size_t smem, cudaStream_t s) {
+    fb_finalize_kernel<<<dim3((unsigned)n, (unsigned)slices, 1), FB_FIN_THREADS, smem, s>>>(p);
     return cudaGetLastError();
 }
 

@@ -28,6 +28,23 @@ CONFIGS = {
 }
 
 
+def config_args(name):
+    """fb_synth arguments of a named configuration.  Besides the entries of CONFIGS, any point of the single-gap
+    stress sweep (BASELINE config 5) can be named cfg5_stress_g<gap>_c<coverage>_k<copies>."""
+    if name in CONFIGS:
+        return list(CONFIGS[name])
+    import re
+    m = re.fullmatch(r"cfg5_stress_g(\d+)_c(\d+)_k(\d+)", name)
+    if not m:
+        raise KeyError(f"unknown workload {name!r}")
+    g, cov, k = (int(x) for x in m.groups())
+    lib = ["--ins-mean", "180", "--ins-sd", "20"] if g < 500 else ["--ins-mean", "500", "--ins-sd", "50"]
+    args = ["--genome", "200000", "--gap-list", str(g), "--cov", str(cov), "--err", "0.01"] + lib
+    if k > 1:
+        args += ["--multihit", str(k)]
+    return args + ["--model-pairs", "200000"]
+
+
 def fb_synth_path():
     exe = os.path.join(_build.BIN, "fb_synth")
     if not os.path.exists(exe):
