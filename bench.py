@@ -356,7 +356,7 @@ def run_ours(a):
     dev_seconds = allmax(step_ms / 1e3)     # CUDA-event time of the steps, max over ranks
     liks_all = allsum(float(st["likelihoods"]))
     value = liks_all * a.steps / dev_seconds
-    launches = (st["em_launches"] + st["finalize_launches"]) * a.steps
+    launches = (st["em_launches"] + st["finalize_launches"] + st["aux_launches"]) * a.steps
 
     # ---- end-to-end arm: host gap files -> library parse/pack -> H2D -> kernels -> D2H ------------------
     for _ in range(min(a.warmup, 2)):

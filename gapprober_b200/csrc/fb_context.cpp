@@ -178,6 +178,8 @@ struct fb_ctx {
     DevBuf<uint8_t> d_flank;
     DevBuf<uint4> d_codes, d_nmask;
     DevBuf<FbRecMeta> d_rmeta;
+    DevBuf<uint32_t> d_st_mask, d_st_cls4;           // per-record tables built on the device by fb_stage_kernel
+    DevBuf<uint8_t> d_st_jl, d_st_cum;
     DevBuf<FbUnit> d_units, d_units_scan;          // _scan: the units / gap metadata a record-sharded scan launches with
     DevBuf<FbGapMeta> d_gapmeta_scan;
     DevBuf<double> d_parts[2], d_sumcounts, d_maxmerge;
@@ -305,6 +307,7 @@ void fb_destroy(fb_ctx* c) {
     c->d_units.release(); c->d_counters.release(); c->d_maxprob.release(); c->d_gws.release(); c->d_finprob.release();
     c->d_dump.release(); c->d_cons.release(); c->d_finpos.release(); c->d_gaplist.release(); c->d_bestgp.release();
     c->d_bestoff.release();
+    c->d_st_mask.release(); c->d_st_cls4.release(); c->d_st_jl.release(); c->d_st_cum.release();
     c->d_units_scan.release(); c->d_gapmeta_scan.release(); c->d_parts[0].release(); c->d_parts[1].release();
     c->d_sumcounts.release(); c->d_maxmerge.release(); c->d_unit_nrec.release();
     c->h_maxprob.release(); c->h_finprob.release(); c->h_finpos.release(); c->h_stage.release();
@@ -802,7 +805,7 @@ int fb_upload(fb_ctx* c) {
         if (b.global_tables) gws_need += (size_t)b.grid * gws_stride_of(b.nr_stride, b.gp_stride);
     }
     // Few units (a single gap, the stress sweep): most SMs would idle with one CTA per unit.  Give every unit a
-    // thread-block cluster instead — as many CTAs as keep all units of all bins co-resident, at most 8 (the portable limit).
+    // thread-block cluster instead — as many CTAs as keep all units of all bins co-resident, at most 4.
     {
         long cta_need = 0;      // SM-halves the launches would occupy with one CTA per unit
         for (const Bin& b : c->bins) cta_need += (long)b.n_units * (b.ctas_per_sm == 2 ? 1 : 2);
@@ -810,7 +813,7 @@ int fb_upload(fb_ctx* c) {
         const char* force = getenv("FB_CLUSTER");        // tuning / test knob: 1 disables, 2/4/8 forces
         if (force) want = std::max(1, std::min(8, atoi(force)));
         else
-            while (want < 8 && cta_need * want * 2 <= 2L * c->sm_count) want *= 2;
+            while (want < 4 && cta_need * want * 2 <= 2L * c->sm_count) want *= 2;   // 8 measured slower than 4: too few tasks per CTA and round
         for (Bin& b : c->bins) {
             if (b.global_tables) continue;
             for (int cl = want; cl > 1; cl >>= 1) {
@@ -846,6 +849,10 @@ int fb_upload(fb_ctx* c) {
     FB_CUDA(c, c->d_codes.ensure(c->h_codes.size()));
     FB_CUDA(c, c->d_nmask.ensure(c->h_nmask.size()));
     FB_CUDA(c, c->d_rmeta.ensure(nr));
+    FB_CUDA(c, c->d_st_mask.ensure(nr * 20));
+    FB_CUDA(c, c->d_st_cls4.ensure(nr * 16));
+    FB_CUDA(c, c->d_st_jl.ensure(nr * (FB_MAX_READ + 16)));
+    FB_CUDA(c, c->d_st_cum.ensure(nr * 32));
     FB_CUDA(c, c->d_units.ensure(c->h_units.size()));
     FB_CUDA(c, c->d_counters.ensure(c->bins.size() + 1));
     FB_CUDA(c, c->d_maxprob.ensure((size_t)mp));
@@ -931,10 +938,28 @@ void fill_em_params(fb_ctx* c, FbEmParams& p) {
     p.codes = c->d_codes.p;
     p.nmask = c->d_nmask.p;
     p.rmeta = c->d_rmeta.p;
+    p.st_mask = c->d_st_mask.p;
+    p.st_cls4 = c->d_st_cls4.p;
+    p.st_jl = c->d_st_jl.p;
+    p.st_cum = c->d_st_cum.p;
     p.unit_maxprob = c->d_maxprob.p;
     p.unit_cons = c->d_cons.p;
     p.dump_unit = -1;
     p.gws = c->d_gws.p;
+}
+
+// The per-record tables of the EM kernel, rebuilt on the device at the start of every pass.
+cudaError_t launch_stage(fb_ctx* c, cudaStream_t s) {
+    FbStageParams sp;
+    sp.codes = c->d_codes.p;
+    sp.nmask = c->d_nmask.p;
+    sp.rmeta = c->d_rmeta.p;
+    sp.n_records = (int)c->h_rmeta.size();
+    sp.st_mask = c->d_st_mask.p;
+    sp.st_cls4 = c->d_st_cls4.p;
+    sp.st_jl = c->d_st_jl.p;
+    sp.st_cum = c->d_st_cum.p;
+    return fb_launch_stage(sp, s);
 }
 
 cudaError_t launch_bin(const Bin& b, const FbEmParams& p, cudaStream_t s) {
@@ -976,6 +1001,8 @@ int fb_run_scan(fb_ctx* c) {
     // ---- EM scan: one persistent launch per size bin
     FB_CUDA(c, cudaEventRecord(c->evs, c->stream));
     FB_CUDA(c, cudaMemsetAsync(c->d_counters.p, 0, sizeof(int) * (c->bins.size() + 1), c->stream));
+    FB_CUDA(c, launch_stage(c, c->stream));
+    st.aux_launches = 1;
     FB_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     for (size_t bi = 0; bi < c->bins.size(); bi++) {
         const Bin& b = c->bins[bi];
@@ -1204,6 +1231,8 @@ int fb_shard_scan_iter(fb_ctx* c, int it, const double* const* peer_counts, doub
         FB_CUDA(c, cudaEventRecord(c->evs, c->stream));
         // records scanned elsewhere keep 0 in this rank's maxima, so the ranks' buffers merge with max
         FB_CUDA(c, cudaMemsetAsync(c->d_maxprob.p, 0, sizeof(double) * c->shard_maxprob, c->stream));
+        FB_CUDA(c, launch_stage(c, c->stream));
+        st.aux_launches = 1;
     }
     FB_CUDA(c, cudaMemsetAsync(c->d_counters.p, 0, sizeof(int) * (c->bins.size() + 1), c->stream));
     FB_CUDA(c, cudaEventRecord(c->ev0, c->stream));
@@ -1254,6 +1283,7 @@ int fb_shard_scan_finish(fb_ctx* c, const double* const* peer_counts, const doub
     f.maxprob_out = c->d_maxmerge.p;
     f.unit_cons = c->d_cons.p;
     FB_CUDA(c, fb_launch_shard_finish(f, c->stream));
+    c->stats.aux_launches++;
     FB_CUDA(c, cudaMemcpyAsync(c->h_maxprob.p, c->d_maxmerge.p, c->shard_maxprob * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     FB_CUDA(c, cudaStreamSynchronize(c->stream));
     c->stats.d2h_bytes = (long)(c->shard_maxprob * sizeof(double));
@@ -1426,6 +1456,7 @@ int fb_dump_profile(fb_ctx* c, int gap, int estimate, double* probs, double* cou
             p.dump_counts = c->d_dump.p + n;
             p.dump_unit = 0;
             FB_CUDA(c, cudaMemsetAsync(p.work_counter, 0, sizeof(int), c->stream));
+            FB_CUDA(c, launch_stage(c, c->stream));
             FB_CUDA(c, fb_launch_em(p, 1, b.global_tables, b.smem, c->stream));
             FB_CUDA(c, cudaMemcpyAsync(probs, c->d_dump.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
             FB_CUDA(c, cudaMemcpyAsync(counts, c->d_dump.p + n, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));

@@ -47,6 +47,11 @@ struct FbEmParams {
     const uint4* codes;     // [n_records][2]  2-bit bases, 16 per 32-bit word, already in scoring orientation
     const uint4* nmask;     // [n_records]     bit j set: base j is not ACGT
     const FbRecMeta* rmeta; // [n_records]
+    // per-record tables built by fb_stage_kernel (the EM kernel bulk-copies them chunk by chunk into shared memory)
+    const uint32_t* st_mask;   // [n_records][20]
+    const uint32_t* st_cls4;   // [n_records][16]
+    const uint8_t* st_jl;      // [n_records][FB_MAX_READ + 16]
+    const uint8_t* st_cum;     // [n_records][32]
     // work list
     const FbUnit* units;
     int n_units;
@@ -70,6 +75,17 @@ struct FbEmParams {
     const double* parts_in[FB_MAX_SHARDS];   // last iteration's partial counts of every rank (own, peer-mapped or gathered)
     int n_parts;                             // 0: first iteration, start from initialize()
     double* part_out;                        // this rank's partial counts of this iteration (nullptr: not sharded)
+};
+
+struct FbStageParams {
+    const uint4* codes;
+    const uint4* nmask;
+    const FbRecMeta* rmeta;
+    int n_records;
+    uint32_t* st_mask;
+    uint32_t* st_cls4;
+    uint8_t* st_jl;
+    uint8_t* st_cum;
 };
 
 // Closing step of a record-sharded scan: rank-ordered sum of the partial counts -> computeSequence(0); per-record
@@ -113,5 +129,6 @@ cudaError_t fb_launch_em_cluster(const FbEmParams& p, int n_clusters, int cluste
 cudaError_t fb_em_max_clusters(int cluster, size_t smem, int* n);     // co-resident clusters of that size on this device
 // n gaps x `slices` CTAs per gap (a CTA takes every slices-th group of 8 records)
 cudaError_t fb_launch_finalize(const FbFinParams& p, int n, int slices, size_t smem, cudaStream_t s);
+cudaError_t fb_launch_stage(const FbStageParams& p, cudaStream_t s);
 cudaError_t fb_launch_shard_finish(const FbShardFinParams& p, cudaStream_t s);
 cudaError_t fb_kernels_init(int* max_smem_optin, int* sm_count);

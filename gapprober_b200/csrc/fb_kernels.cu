@@ -24,7 +24,7 @@
 // scores to a cell in exactly the order the CPU's scatter loop does.  Likelihood plateaus therefore
 // tie exactly as they do on the CPU.  No tensor cores: the path is not a contraction.
 //
-// Roofs: ~6.5 algorithmic HBM bytes per likelihood (1.65 MB of real DRAM traffic per bench step) vs ~1.6 KB of
+// Roofs: ~6.5 algorithmic HBM bytes per likelihood (5 MB of real DRAM traffic per bench step) vs ~1.6 KB of
 // shared-memory reads and ~400 FP64 instructions per likelihood, so shared-memory bandwidth (then the FP64 pipe)
 // binds; DESIGN.md has the arithmetic, profiles/README.md the measurements.
 
@@ -70,26 +70,27 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
 //   cnt[5][gps]      counts of the gap rows                                                  (M-step accumulates)
 //   w[2]             placement scores of two in-flight record chunks: rows of p_stride slots separated by kPadW zeros
 //   st[3]            staged record chunks: window, flags, class bit-masks, 4-bit packed classes, class-sorted position lists
-// One unit runs as a software pipeline over chunks of records: in round r the CTA's warps pull, from one
-// dynamic queue, M-step tasks of chunk r-1, E-step tasks of chunk r and staging tasks of chunk r+1, and
-// meet at ONE barrier per round.
+// One unit runs as a software pipeline over chunks of records: in round r the bulk copies that stage chunk r+1 are
+// in flight while the CTA's warps pull, from one dynamic queue, M-step tasks of chunk r-1 and E-step tasks of
+// chunk r; everything meets at ONE barrier per round.
 // ---------------------------------------------------------------------------------------------------
 constexpr int kPadRows = 32;   // a lane's second placement sits 32 rows further; invalid lanes may read (not use) past the end
 constexpr int kListBytes = FB_MAX_READ + 16;   // per record: class-sorted position lists, each class starting 4-aligned
 constexpr int kPadW = 32;      // zeros either side of every score row: the M-step reads up to 31 placements outside a window
 
+// Per-record tables of a staged chunk.  They depend on the record only, so fb_stage_kernel builds them once per pass in
+// HBM (same per-record layout) and the EM kernel brings a chunk in with bulk asynchronous copies (TMA engine, mbarrier
+// completion) while the previous chunks are being scored.
 struct Stage {
-    int* rlo;
-    int* rhi;
-    int* rtb;
-    int* rfl;
-    unsigned long long* rmax;
+    const FbRecMeta* meta;   // [chunk]      window, insert base, flags (the estimate-dependent clamps are applied by the readers)
     uint32_t* mask;   // [chunk][5][4] bit j of class c: base j of the record is c
     uint32_t* cls4;   // [chunk][16]  base classes, 4 bits each (8 per word), in scoring orientation
     uint8_t* jl;      // [chunk][kListBytes] read positions sorted by (class asc, position DESC), class segments 4-aligned
     uint8_t* cum;     // [chunk][32]  cum[c*4+w] = index in jl of the first position of class c that lies in mask word <= w
                       //              (i.e. class start + number of class-c positions in words above w); cum[20+c] = class end
+    unsigned long long* rmax;   // [chunk] running maximum score of the record in this iteration (bit pattern of a positive double)
 };
+constexpr int kStageCopyBytes = 16 + 80 + 64 + kListBytes + 32;   // per record, brought in by the bulk copies (all but rmax)
 
 struct EmSmem {
     double* ild;
@@ -102,20 +103,17 @@ struct EmSmem {
     int chunk;
 };
 
-// Carve one staged chunk out of its slab (same order as em_carve lays it out).
+// Carve one staged chunk out of its slab (same order as em_carve lays it out); every section starts 16-byte aligned.
 __device__ __forceinline__ Stage stage_at(const EmSmem& s, int k) {
     unsigned char* b = s.st0 + (size_t)k * s.st_stride;
     Stage t;
-    t.rmax = reinterpret_cast<unsigned long long*>(b);
-    b += sizeof(unsigned long long) * s.chunk;
-    t.rlo = reinterpret_cast<int*>(b);
-    t.rhi = t.rlo + s.chunk;
-    t.rtb = t.rhi + s.chunk;
-    t.rfl = t.rtb + s.chunk;
-    t.mask = reinterpret_cast<uint32_t*>(t.rfl + s.chunk);
+    t.meta = reinterpret_cast<const FbRecMeta*>(b);
+    b += sizeof(FbRecMeta) * s.chunk;
+    t.mask = reinterpret_cast<uint32_t*>(b);
     t.cls4 = t.mask + 20 * s.chunk;
     t.jl = reinterpret_cast<uint8_t*>(t.cls4 + 16 * s.chunk);
     t.cum = t.jl + kListBytes * s.chunk;
+    t.rmax = reinterpret_cast<unsigned long long*>(t.cum + 32 * s.chunk);
     return t;
 }
 
@@ -139,9 +137,9 @@ __host__ __device__ inline size_t em_carve(unsigned char* base, EmSmem* s, int n
     const size_t wbytes = align16(sizeof(double) * ((size_t)kPadW + (size_t)chunk * (p_stride + kPadW)));
     a = take(2 * wbytes);
     if (s) { s->w0 = (double*)a; s->w_stride = wbytes / sizeof(double); }
-    // one staged chunk: rmax[chunk] u64 | rlo, rhi, rtb, rfl [chunk] int | mask[chunk][20] u32 | cls4[chunk][16] u32 |
-    //                   jl[chunk][128] u8 | cum[chunk][32] u8
-    const size_t sbytes = align16((size_t)chunk * (8 + 4 * 4 + 20 * 4 + 16 * 4 + kListBytes + 32));
+    // one staged chunk: meta[chunk] 16 B | mask[chunk][20] u32 | cls4[chunk][16] u32 | jl[chunk][144] u8 | cum[chunk][32] u8 |
+    //                   rmax[chunk] u64
+    const size_t sbytes = align16((size_t)chunk * (kStageCopyBytes + 8));
     a = take(3 * sbytes);
     if (s) { s->st0 = a; s->st_stride = sbytes; s->chunk = chunk; }
     return off;
@@ -171,6 +169,33 @@ __device__ __forceinline__ void fetch_classes(const uint4* __restrict__ codes, c
         if (j >= L2) c = 5;
         cls[q] = c;
     }
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// Bulk asynchronous copy global -> this CTA's shared memory; bytes and both addresses are multiples of 16.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
 }
 
 // Byte-code form used by the finalize kernel.
@@ -221,6 +246,59 @@ __device__ __forceinline__ void score_pair(const unsigned char* pa, const uint32
     }
 }
 
+// Per-record tables of the EM kernel, one warp per record (they do not depend on the estimate, so every unit of the
+// gap reuses them): 4-bit packed classes, class bit-masks, class-sorted position lists and their prefix counts.
+__global__ void __launch_bounds__(256) fb_stage_kernel(const FbStageParams p) {
+    const int lane = threadIdx.x & 31;
+    const int rec = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (rec >= p.n_records) return;
+    const int L2 = p.rmeta[rec].flags & 0xff;
+    unsigned cls[4];
+    fetch_classes(p.codes, p.nmask, rec, L2, lane, cls);
+    {
+        // four classes of this lane -> 16 bits; two lanes make one 32-bit word (8 bases)
+        const unsigned nib4 = min(cls[0], 4u) | (min(cls[1], 4u) << 4) | (min(cls[2], 4u) << 8) | (min(cls[3], 4u) << 12);
+        const unsigned hi16 = __shfl_down_sync(0xffffffffu, nib4, 1);
+        if ((lane & 1) == 0) p.st_cls4[(size_t)rec * 16 + (lane >> 1)] = nib4 | (hi16 << 16);
+    }
+    uint8_t* cum = p.st_cum + (size_t)rec * 32;
+    uint8_t* jl = p.st_jl + (size_t)rec * kListBytes;
+    for (int i = lane; i < kListBytes / 4; i += 32) reinterpret_cast<uint32_t*>(jl)[i] = 0u;   // the gaps between class segments
+    if (lane >= 25) cum[lane] = 0;
+    __syncwarp();
+    const unsigned grp = 0xffu << (lane & 24);           // the 8 lanes sharing one 32-bit mask word
+    int start = 0;
+#pragma unroll
+    for (int c = 0; c < 5; c++) {
+        unsigned nib = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) nib |= (cls[q] == (unsigned)c ? 1u : 0u) << q;
+        const unsigned word = __reduce_or_sync(grp, nib << (4 * (lane & 7)));     // bit j of word w: base 32w+j is of class c
+        if ((lane & 7) == 0) p.st_mask[(size_t)rec * 20 + c * 4 + (lane >> 3)] = word;
+        const unsigned m0 = __shfl_sync(0xffffffffu, word, 0), m1 = __shfl_sync(0xffffffffu, word, 8);
+        const unsigned m2 = __shfl_sync(0xffffffffu, word, 16), m3 = __shfl_sync(0xffffffffu, word, 24);
+        // class-sorted, position-descending list: slot = class start + (positions of that class above j)
+        const int n3 = __popc(m3), n2 = __popc(m2), n1 = __popc(m1), n0 = __popc(m0);
+        if (lane == 0) {
+            cum[c * 4 + 0] = (uint8_t)(start + n3 + n2 + n1);      // positions in words above w
+            cum[c * 4 + 1] = (uint8_t)(start + n3 + n2);
+            cum[c * 4 + 2] = (uint8_t)(start + n3);
+            cum[c * 4 + 3] = (uint8_t)start;
+            cum[20 + c] = (uint8_t)(start + n3 + n2 + n1 + n0);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (cls[q] == (unsigned)c) {
+                const int j = lane * 4 + q, w = j >> 5;
+                const unsigned mw = w == 0 ? m0 : w == 1 ? m1 : w == 2 ? m2 : m3;
+                const int higher = __popc((mw >> (j & 31)) >> 1);
+                jl[start + (w == 3 ? 0 : w == 2 ? n3 : w == 1 ? n3 + n2 : n3 + n2 + n1) + higher] = (uint8_t)j;
+            }
+        }
+        start = (start + n3 + n2 + n1 + n0 + 3) & ~3;     // next class starts on a 32-bit boundary
+    }
+}
+
 // CLU: one unit is run by a thread-block cluster instead of one CTA — for launches with fewer units than the GPU has
 // CTA slots (single gaps, the stress sweep).  Nothing about the arithmetic changes, so results stay bit-exact:
 //   * every CTA keeps a full copy of the P/Q table and of the two score buffers in its own shared memory;
@@ -253,6 +331,8 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
     }
     __shared__ int s_unit;
     __shared__ int s_queue[2];
+    __shared__ __align__(8) uint64_t s_bar[3];   // one per stage buffer: completion of the bulk copies that fill it
+    uint32_t bar_phase = 0;                      // bit k: parity the next wait on s_bar[k] has to see (same in every thread)
     __shared__ double sT[25];
     __shared__ double2 sRow[5][5];   // {P,Q} per base class of a row whose counts are one-hot in base b (flanks, and b=4: untouched gap rows)
 
@@ -261,6 +341,10 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
 
     for (int i = tid; i < pwin; i += FB_THREADS) s.ild[i] = p.ild[i];
     if (tid < 25) sT[tid] = p.T[tid];
+    if (tid == 0) {
+        for (int k = 0; k < 3; k++) mbar_init(&s_bar[k], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     if (GT) {
         for (int i = tid; i < kPadRows; i += FB_THREADS) s.pq[5 * (size_t)p.nr_stride + i] = make_double2(0.0, 0.0);
     }
@@ -361,8 +445,23 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
                 // a cluster deals E tasks by record and M tasks by row block; staging is done by every CTA for itself
                 const int nrb_q = CLU ? (nrb + (int)csize - 1 - (int)crank) / (int)csize : nrb;
                 const int ne_q = CLU ? (n_e + (int)csize - 1 - (int)crank) / (int)csize : n_e;
-                const int tM = n_m ? nrb_q * 5 : 0, tE = ne_q * nblk, tL = n_l;
-                const int ntask = tM + tE + tL;
+                if (n_l) {
+                    // ---- stage chunk cl: bulk copies of the records' prepared tables (fb_stage_kernel), waited for at the end of the round
+                    if (full_stage && tid == 0) {
+                        uint64_t* bar = &s_bar[cl % 3];
+                        const size_t rec0 = (size_t)gm.rec_off + (size_t)cl * CH;
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the buffer was last read through the generic proxy
+                        mbar_expect_tx(bar, (uint32_t)n_l * kStageCopyBytes);
+                        bulk_g2s(const_cast<FbRecMeta*>(SL.meta), p.rmeta + rec0, (uint32_t)n_l * 16u, bar);
+                        bulk_g2s(SL.mask, p.st_mask + rec0 * 20, (uint32_t)n_l * 80u, bar);
+                        bulk_g2s(SL.cls4, p.st_cls4 + rec0 * 16, (uint32_t)n_l * 64u, bar);
+                        bulk_g2s(SL.jl, p.st_jl + rec0 * kListBytes, (uint32_t)n_l * kListBytes, bar);
+                        bulk_g2s(SL.cum, p.st_cum + rec0 * 32, (uint32_t)n_l * 32u, bar);
+                    }
+                    if (tid < n_l) SL.rmax[tid] = 0ull;          // new iteration (or new chunk), new maximum
+                }
+                const int tM = n_m ? nrb_q * 5 : 0, tE = ne_q * nblk;
+                const int ntask = tM + tE;
                 int* queue = &s_queue[round & 1];
                 for (;;) {
                     int task = 0;
@@ -385,8 +484,10 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
                         // put some row of this block inside the window (two popcounts)
                         int v_lo = 0, v_qs = 0, v_qe = 0;
                         if (lane < n_m) {
-                            const int lo = SM.rlo[lane], hi = SM.rhi[lane];
-                            const int L2 = SM.rfl[lane] & 0xff;
+                            const FbRecMeta rm = SM.meta[lane];
+                            const int L2 = rm.flags & 0xff;
+                            // placements i in [gapStart-L2+1, gapStart+gp) (figbird.cpp:1826) -> u in [D-L2+1, D+gp-1]
+                            const int lo = max(rm.a_lo, D - L2 + 1), hi = min(rm.a_hi, D + gp - 1);
                             const int jhi = min(L2 - 1, x0 + 31 - lo), jlo = max(0, x0 - hi);
                             if (hi >= lo && jhi >= jlo) {
                                 const uint32_t* mk = SM.mask + lane * 20 + c * 4;
@@ -416,13 +517,16 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
                             for (; q < qe; q++) a0 = dadd(a0, wr[-(int)jl[q]]);
                         }
                         if (ok0) cr[0] = a0;
-                    } else if (task < tM + tE) {
+                    } else {
                         // ---- E-step: warp per (record, 64 placements); lanes over placements.  Every slot of the record's score row is
                         // written: the score inside the window, 0.0 outside it (the M-step relies on those zeros).
                         const int te = task - tM;
                         const int rq = te / nblk, blk = te - rq * nblk;
                         const int rl = CLU ? rq * (int)csize + (int)crank : rq;
-                        const int lo = SE.rlo[rl], hi = SE.rhi[rl];
+                        const FbRecMeta rm = SE.meta[rl];
+                        const int fl2 = rm.flags, L2 = fl2 & 0xff, tb = rm.tb;
+                        // placements i in [gapStart-L2+1, gapStart+gp) (figbird.cpp:1826) -> u in [D-L2+1, D+gp-1]
+                        const int lo = max(rm.a_lo, D - L2 + 1), hi = min(rm.a_hi, D + gp - 1);
                         double* wrow = wE + kPadW + rl * WS;                  // slot k holds placement lo + k
                         const int ka = 64 * blk + lane, kb = ka + 32;
                         if (lo + 64 * blk > hi) {                              // nothing of the window in this block (or no window at all)
@@ -438,7 +542,6 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
                             }
                             continue;
                         }
-                        const int fl2 = SE.rfl[rl], L2 = fl2 & 0xff, tb = SE.rtb[rl];
                         const bool rev = (fl2 >> 8) & 1, left = (fl2 >> 9) & 1;
                         const int ua = lo + ka, ub = ua + 32;
                         const bool va_ok = ua <= hi, vb_ok = ub <= hi;
@@ -472,73 +575,13 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
                         unsigned long long bb = (vb_ok && sb > 0.0) ? (unsigned long long)__double_as_longlong(sb) : 0ull;
                         ba = warp_max_u64(ba > bb ? ba : bb);
                         if (lane == 0 && ba) atomicMax(&SE.rmax[rl], ba);
-                    } else {
-                        // ---- stage one record: placement window, class bit-masks, per-position table offsets
-                        const int rl = task - tM - tE;
-                        if (!full_stage) {               // the staged tables of this chunk are still in place: new iteration, new maximum
-                            if (lane == 0) SL.rmax[rl] = 0ull;
-                            continue;
-                        }
-                        const int rec = gm.rec_off + cl * CH + rl;
-                        const FbRecMeta rm = p.rmeta[rec];
-                        const int L2 = rm.flags & 0xff;
-                        unsigned cls[4];
-                        fetch_classes(p.codes, p.nmask, rec, L2, lane, cls);
-                        {
-                            // four classes of this lane -> 16 bits; two lanes make one 32-bit word (8 bases)
-                            const unsigned nib4 = min(cls[0], 4u) | (min(cls[1], 4u) << 4) | (min(cls[2], 4u) << 8) | (min(cls[3], 4u) << 12);
-                            const unsigned hi16 = __shfl_down_sync(0xffffffffu, nib4, 1);
-                            if ((lane & 1) == 0) SL.cls4[rl * 16 + (lane >> 1)] = nib4 | (hi16 << 16);
-                        }
-                        const unsigned grp = 0xffu << (lane & 24);           // the 8 lanes sharing one 32-bit mask word
-#pragma unroll
-                        for (int c = 0; c < 5; c++) {
-                            unsigned nib = 0;
-#pragma unroll
-                            for (int q = 0; q < 4; q++) nib |= (cls[q] == (unsigned)c ? 1u : 0u) << q;
-                            unsigned word = __reduce_or_sync(grp, nib << (4 * (lane & 7)));
-                            if ((lane & 7) == 0) SL.mask[rl * 20 + c * 4 + (lane >> 3)] = word;
-                        }
-                        __syncwarp();
-                        {
-                            // class-sorted, position-descending list: slot = class start + (positions of that class above j)
-                            const uint32_t* mk = SL.mask + rl * 20;
-                            uint8_t* cum = SL.cum + rl * 32;
-                            uint8_t* jl = SL.jl + rl * kListBytes;
-                            int start = 0;
-#pragma unroll
-                            for (int c = 0; c < 5; c++) {
-                                const int n3 = __popc(mk[c * 4 + 3]), n2 = __popc(mk[c * 4 + 2]), n1 = __popc(mk[c * 4 + 1]), n0 = __popc(mk[c * 4]);
-                                const int above[4] = {n3 + n2 + n1, n3 + n2, n3, 0};   // positions in words above w
-                                if (lane == 0) {
-                                    cum[c * 4 + 0] = (uint8_t)(start + above[0]);
-                                    cum[c * 4 + 1] = (uint8_t)(start + above[1]);
-                                    cum[c * 4 + 2] = (uint8_t)(start + above[2]);
-                                    cum[c * 4 + 3] = (uint8_t)(start + above[3]);
-                                    cum[20 + c] = (uint8_t)(start + n3 + n2 + n1 + n0);
-                                }
-#pragma unroll
-                                for (int q = 0; q < 4; q++) {
-                                    if (cls[q] == (unsigned)c) {
-                                        const int j = lane * 4 + q, w = j >> 5;
-                                        const int higher = __popc((mk[c * 4 + w] >> (j & 31)) >> 1);
-                                        jl[start + (w == 3 ? 0 : w == 2 ? n3 : w == 1 ? n3 + n2 : n3 + n2 + n1) + higher] = (uint8_t)j;
-                                    }
-                                }
-                                start = (start + n3 + n2 + n1 + n0 + 3) & ~3;     // next class starts on a 32-bit boundary
-                            }
-                        }
-                        if (lane == 0) {
-                            // placements i in [gapStart-L2+1, gapStart+gp) (figbird.cpp:1826) -> u in [D-L2+1, D+gp-1]
-                            SL.rlo[rl] = max(rm.a_lo, D - L2 + 1);
-                            SL.rhi[rl] = min(rm.a_hi, D + gp - 1);
-                            SL.rtb[rl] = rm.tb;
-                            SL.rfl[rl] = rm.flags;
-                            SL.rmax[rl] = 0ull;
-                        }
                     }
                 }
                 if (tid == 0) s_queue[(round + 1) & 1] = 0;   // nobody touches the other slot during this round
+                if (n_l && full_stage) {                      // chunk cl has landed (the copies had the whole round)
+                    mbar_wait(&s_bar[cl % 3], (bar_phase >> (cl % 3)) & 1u);
+                    bar_phase ^= 1u << (cl % 3);
+                }
                 sync_all();
             }
 
@@ -778,5 +821,11 @@ cudaError_t fb_launch_finalize(const FbFinParams& p, int n, int slices, size_t s
 cudaError_t fb_launch_shard_finish(const FbShardFinParams& p, cudaStream_t s) {
     if (p.n_units < 1) return cudaSuccess;
     fb_shard_finish_kernel<<<p.n_units < 4096 ? p.n_units : 4096, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t fb_launch_stage(const FbStageParams& p, cudaStream_t s) {
+    if (p.n_records < 1) return cudaSuccess;
+    fb_stage_kernel<<<(p.n_records + 7) / 8, 256, 0, s>>>(p);
     return cudaGetLastError();
 }

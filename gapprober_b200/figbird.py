@@ -73,6 +73,7 @@ class FbStats(C.Structure):
         ("em_kernel_ms", C.c_double), ("finalize_kernel_ms", C.c_double), ("step_ms", C.c_double),
         ("em_launches", C.c_int), ("finalize_launches", C.c_int),
         ("h2d_bytes", C.c_long), ("d2h_bytes", C.c_long), ("algorithmic_bytes", C.c_long),
+        ("aux_launches", C.c_int),
     ]
 
     def as_dict(self):

@@ -80,6 +80,7 @@ typedef struct fb_stats {
     int em_launches, finalize_launches;
     long h2d_bytes, d2h_bytes;  /* of the last fb_upload + fb_run_device                               */
     long algorithmic_bytes;     /* SURVEY §8(d) HBM byte model summed over (unit, iteration)            */
+    int aux_launches;           /* other kernels of the pass: record-table staging, record-shard closing step */
 } fb_stats;
 
 typedef struct fb_ctx fb_ctx;

@@ -1,0 +1,51 @@
+"""Per-launch extract of an `ncu --set full` report: the columns profiles/r1_ncu_full_summary.csv keeps, plus the DRAM
+traffic of the EM launches as JSON (feeds bench.py's roofline.traffic).
+    ncu -i report.ncu-rep --page raw --csv > raw.csv
+    python tools/ncu_summary.py raw.csv profiles/r1_ncu_full_summary.csv profiles/r1_traffic.json
+"""
+import csv
+import json
+import sys
+
+KEEP = [
+    "ID", "Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem", "launch__cluster_dim_x",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "smsp__inst_executed.sum", "sm__cycles_elapsed.max", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sector_hit_rate.pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+]
+
+
+def to_bytes(v, unit):
+    mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+    return float(v.replace(",", "")) * mult
+
+
+def main(raw, out_csv, out_json):
+    rows = list(csv.reader(open(raw)))
+    hdr = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
+    names, units = rows[hdr], rows[hdr + 1]
+    cols = [names.index(k) for k in KEEP if k in names]
+    with open(out_csv, "w", newline="") as f:
+        w = csv.writer(f, quoting=csv.QUOTE_ALL)
+        w.writerow([names[c] for c in cols])
+        w.writerow([units[c] for c in cols])
+        for r in rows[hdr + 2:]:
+            if len(r) == len(names):
+                w.writerow([r[c] for c in cols])
+    ki, ri, wi = names.index("Kernel Name"), names.index("dram__bytes_read.sum"), names.index("dram__bytes_write.sum")
+    rd = wr = n = 0
+    for r in rows[hdr + 2:]:
+        if len(r) == len(names) and "fb_em_kernel" in r[ki]:
+            rd += to_bytes(r[ri], units[ri])
+            wr += to_bytes(r[wi], units[wi])
+            n += 1
+    json.dump({"source": f"{out_csv} (ncu --set full, bench.py --steps 1 --warmup 3 --no-cpu, cfg2_rhodobacter seed 2)",
+               "kernel": "fb_em_kernel", "launches_per_step": n, "dram_bytes_read_per_step": rd, "dram_bytes_write_per_step": wr,
+               "dram_bytes_per_launch": (rd + wr) / max(n, 1)}, open(out_json, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main(*sys.argv[1:4])
