@@ -130,6 +130,7 @@ struct Bin {
     int nr_stride, gp_stride, p_stride, chunk;
     bool global_tables;
     int ctas_per_sm;
+    int threads;      // per CTA: 512, or 1024 when only one CTA fits an SM
     int cluster;      // CTAs per unit (thread-block cluster) when the launch has fewer units than the GPU has CTA slots; 1 = one CTA per unit
     size_t smem;
     int grid;         // CTAs, or clusters when cluster > 1
@@ -801,6 +802,14 @@ int fb_upload(fb_ctx* c) {
         b.grid = std::min(b.n_units, c->sm_count * ctas);
         b.cluster = 1;
         b.ctas_per_sm = ctas;
+        // one CTA per SM: give it 32 warps instead of 16 (tuning knob FB_THREADS1=512 keeps the small CTA)
+        {
+            const char* k1 = getenv("FB_THREADS1");
+            const char* kg = getenv("FB_THREADS_GT");
+            b.threads = ctas == 1 ? 1024 : FB_THREADS;
+            if (ctas == 1 && !b.global_tables && k1 && atoi(k1) == 512) b.threads = 512;
+            if (b.global_tables && kg && atoi(kg) == 512) b.threads = 512;
+        }
         b.gws_off = gws_need;
         if (b.global_tables) gws_need += (size_t)b.grid * gws_stride_of(b.nr_stride, b.gp_stride);
     }
@@ -831,6 +840,8 @@ int fb_upload(fb_ctx* c) {
         for (const Bin& b : c->bins)
             fprintf(stderr, "[fb_trace] bin: %d units, estimates <= %d, chunk %d, smem %zu, %s, cluster %d, grid %d\n", b.n_units, b.gpmax,
                     b.chunk, b.smem, b.global_tables ? "global tables" : b.ctas_per_sm == 2 ? "2 CTAs/SM" : "1 CTA/SM", b.cluster, b.grid);
+    if (tr.on)
+        for (const Bin& b : c->bins) fprintf(stderr, "[fb_trace]      threads %d\n", b.threads);
     tr.lap("upload: units + bins");
     while (c->bin_done.size() < c->bins.size()) {
         cudaEvent_t a, b;
@@ -964,7 +975,7 @@ cudaError_t launch_stage(fb_ctx* c, cudaStream_t s) {
 
 cudaError_t launch_bin(const Bin& b, const FbEmParams& p, cudaStream_t s) {
     if (b.cluster > 1) return fb_launch_em_cluster(p, b.grid, b.cluster, b.smem, s);
-    return fb_launch_em(p, b.grid, b.global_tables, b.smem, s);
+    return fb_launch_em(p, b.grid, b.threads, b.global_tables, b.smem, s);
 }
 
 void fill_bin_params(fb_ctx* c, size_t bi, FbEmParams& p) {
@@ -1457,7 +1468,7 @@ int fb_dump_profile(fb_ctx* c, int gap, int estimate, double* probs, double* cou
             p.dump_unit = 0;
             FB_CUDA(c, cudaMemsetAsync(p.work_counter, 0, sizeof(int), c->stream));
             FB_CUDA(c, launch_stage(c, c->stream));
-            FB_CUDA(c, fb_launch_em(p, 1, b.global_tables, b.smem, c->stream));
+            FB_CUDA(c, fb_launch_em(p, 1, b.threads, b.global_tables, b.smem, c->stream));
             FB_CUDA(c, cudaMemcpyAsync(probs, c->d_dump.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
             FB_CUDA(c, cudaMemcpyAsync(counts, c->d_dump.p + n, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
             FB_CUDA(c, cudaStreamSynchronize(c->stream));

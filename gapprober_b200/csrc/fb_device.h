@@ -6,7 +6,7 @@
 #include <cuda_runtime.h>
 
 #define FB_MAX_READ 128          // longest mate the packed layout holds (2-bit codes in 2 x uint4)
-#define FB_THREADS 512           // CTA size of the EM kernel
+#define FB_THREADS 512           // CTA size of the EM kernel (1024 where only one CTA fits an SM)
 #define FB_FIN_THREADS 256       // CTA size of the finalize kernel
 #define FB_MAX_SHARDS 16         // ranks of a record-sharded scan
 
@@ -123,7 +123,7 @@ struct FbFinParams {
 };
 
 size_t fb_em_smem_bytes(int nr_stride, int gp_stride, int p_stride, int chunk, int pwin, bool global_tables);
-cudaError_t fb_launch_em(const FbEmParams& p, int grid, bool global_tables, size_t smem, cudaStream_t s);
+cudaError_t fb_launch_em(const FbEmParams& p, int grid, int threads, bool global_tables, size_t smem, cudaStream_t s);   // threads: 512 or 1024
 // cluster variant: n_clusters thread-block clusters of `cluster` CTAs, each cluster running one unit at a time
 cudaError_t fb_launch_em_cluster(const FbEmParams& p, int n_clusters, int cluster, size_t smem, cudaStream_t s);
 cudaError_t fb_em_max_clusters(int cluster, size_t smem, int* n);     // co-resident clusters of that size on this device

@@ -308,8 +308,10 @@ __global__ void __launch_bounds__(256) fb_stage_kernel(const FbStageParams p) {
 //     order from its local copy of the scores;
 //   * the profile update of a row is done by the owner of its counts and broadcast to every CTA's table;
 //   * the per-round barrier becomes a cluster barrier.
-template <bool GT, bool CLU>
-__global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __grid_constant__ FbEmParams p) {
+// NT: threads per CTA — 512 with two CTAs per SM where the tables allow it, 1024 with one CTA per SM for the bigger
+// estimates, so that an SM always has 32 warps to hide the shared-memory (or, with GT, L2) latency.
+template <bool GT, bool CLU, int NT>
+__global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(const __grid_constant__ FbEmParams p) {
     static_assert(!(GT && CLU), "the cluster variant keeps its tables in shared memory");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned crank = 0, csize = 1;
@@ -339,18 +341,18 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
     const int tid = threadIdx.x, lane = tid & 31;
     const int D = p.D, CH = p.chunk, PS = p.p_stride;
 
-    for (int i = tid; i < pwin; i += FB_THREADS) s.ild[i] = p.ild[i];
+    for (int i = tid; i < pwin; i += NT) s.ild[i] = p.ild[i];
     if (tid < 25) sT[tid] = p.T[tid];
     if (tid == 0) {
         for (int k = 0; k < 3; k++) mbar_init(&s_bar[k], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (GT) {
-        for (int i = tid; i < kPadRows; i += FB_THREADS) s.pq[5 * (size_t)p.nr_stride + i] = make_double2(0.0, 0.0);
+        for (int i = tid; i < kPadRows; i += NT) s.pq[5 * (size_t)p.nr_stride + i] = make_double2(0.0, 0.0);
     }
     // score buffers start as zeros; E tasks only ever write the p_stride slots of their row, so the pads between rows
     // stay zero for the life of the kernel
-    for (size_t i = tid; i < 2 * s.w_stride; i += FB_THREADS) s.w0[i] = 0.0;
+    for (size_t i = tid; i < 2 * s.w_stride; i += NT) s.w0[i] = 0.0;
     __syncthreads();
     if (tid < 5) {
         // initialize() only ever produces five different rows (figbird.cpp:1657-1673): compute them once
@@ -387,7 +389,7 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
         const uint8_t* fl = p.flank + (size_t)unit.gap * 2 * D;
 
         // ---- initialize(gp): flanks one-hot from the scaffold, gap rows N=1 (figbird.cpp:1657-1673)
-        for (int xr = tid; xr < NR; xr += FB_THREADS) {
+        for (int xr = tid; xr < NR; xr += NT) {
             int x = xr + R0;
             int b = 4;
             if (x < D) b = fl[x];
@@ -413,7 +415,7 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
 #pragma unroll
             for (int k = 0; k < 5; k++) s.pq[k * nrs + xr] = sRow[b][k];
         }
-        for (int i = tid; i < gp; i += FB_THREADS) {
+        for (int i = tid; i < gp; i += NT) {
 #pragma unroll
             for (int k = 0; k < 5; k++) s.cnt[k * gps + i] = 0.0;
         }
@@ -588,7 +590,7 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
             // chunk 0 of a kept staging gets its per-record maxima reset here, a barrier ahead of the next iteration's E tasks
             if (keep_staged && !last && tid < min(CH, nrec)) stage_at(s, 0).rmax[tid] = 0ull;
             // ---- computeProbsGap + computeErrorProbsGap on the gap rows (flank rows never change)
-            for (int xg = tid; xg < gp; xg += FB_THREADS) {
+            for (int xg = tid; xg < gp; xg += NT) {
                 if (CLU && (unsigned)(xg >> 5) % csize != crank) continue;   // the counts of this row live in another CTA
                 double c[5];
 #pragma unroll
@@ -631,7 +633,7 @@ __global__ void __launch_bounds__(FB_THREADS, GT ? 1 : 2) fb_em_kernel(const __g
         // ---- parity tap: the whole profile of one unit, laid out like probsGap/countsGap
         if (p.dump_probs && ui == p.dump_unit) {
             const int rows = gp + 2 * D;
-            for (int x = tid; x < rows; x += FB_THREADS) {
+            for (int x = tid; x < rows; x += NT) {
                 double c[5];
                 if (x >= D && x < D + gp) {
 #pragma unroll
@@ -770,18 +772,27 @@ cudaError_t fb_kernels_init(int* max_smem_optin, int* sm_count) {
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(fb_em_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, *max_smem_optin - 1024);
+    e = cudaFuncSetAttribute(fb_em_kernel<false, false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, *max_smem_optin - 1024);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(fb_em_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, *max_smem_optin - 1024);
+    e = cudaFuncSetAttribute(fb_em_kernel<false, false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, *max_smem_optin - 1024);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(fb_em_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, *max_smem_optin - 1024);
+    e = cudaFuncSetAttribute(fb_em_kernel<false, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, *max_smem_optin - 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(fb_em_kernel<true, false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, *max_smem_optin - 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(fb_em_kernel<true, false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, *max_smem_optin - 1024);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(fb_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, *max_smem_optin - 8192);
 }
 
-cudaError_t fb_launch_em(const FbEmParams& p, int grid, bool global_tables, size_t smem, cudaStream_t s) {
-    if (global_tables) fb_em_kernel<true, false><<<grid, FB_THREADS, smem, s>>>(p);
-    else fb_em_kernel<false, false><<<grid, FB_THREADS, smem, s>>>(p);
+cudaError_t fb_launch_em(const FbEmParams& p, int grid, int threads, bool global_tables, size_t smem, cudaStream_t s) {
+    if (threads == 1024) {
+        if (global_tables) fb_em_kernel<true, false, 1024><<<grid, 1024, smem, s>>>(p);
+        else fb_em_kernel<false, false, 1024><<<grid, 1024, smem, s>>>(p);
+    } else {
+        if (global_tables) fb_em_kernel<true, false, 512><<<grid, FB_THREADS, smem, s>>>(p);
+        else fb_em_kernel<false, false, 512><<<grid, FB_THREADS, smem, s>>>(p);
+    }
     return cudaGetLastError();
 }
 
@@ -803,14 +814,14 @@ cudaError_t fb_em_max_clusters(int cluster, size_t smem, int* n) {
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr;
     cluster_config(&cfg, &attr, cluster, cluster, smem, nullptr);
-    return cudaOccupancyMaxActiveClusters(n, fb_em_kernel<false, true>, &cfg);
+    return cudaOccupancyMaxActiveClusters(n, fb_em_kernel<false, true, 512>, &cfg);
 }
 
 cudaError_t fb_launch_em_cluster(const FbEmParams& p, int n_clusters, int cluster, size_t smem, cudaStream_t s) {
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr;
     cluster_config(&cfg, &attr, n_clusters * cluster, cluster, smem, s);
-    return cudaLaunchKernelEx(&cfg, fb_em_kernel<false, true>, p);
+    return cudaLaunchKernelEx(&cfg, fb_em_kernel<false, true, 512>, p);
 }
 
 cudaError_t fb_launch_finalize(const FbFinParams& p, int n, int slices, size_t smem, cudaStream_t s) {
