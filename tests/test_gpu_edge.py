@@ -194,3 +194,40 @@ def test_error_contract(built):
         assert e.value.status == -5
         fb.fillGaps()
         assert gf.result()["filled"] == g["filled"]
+
+
+def _fill_with_env(case, gaps, env):
+    """Fill `gaps` in a fresh context with tuning knobs set (they are read when the gap set is uploaded)."""
+    from gapprober_b200 import FigbirdContext
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        with FigbirdContext(case.figbird_model()) as fb:
+            gfs = [fb.GapFiller().initGapFiller(0, case.D, g["orig"], g["recs"], g["window"]) for g in gaps]
+            fb.fillGaps()
+            out = []
+            for gf in gfs:
+                r = gf.result()
+                probs, counts = gf.dumpProfile(r["best_estimate"])
+                out.append((r["filled"], r["best_estimate"], gf.estimateLikelihoods().tobytes(), probs.tobytes(), counts.tobytes()))
+            return out
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def test_kernel_variants_agree_bit_for_bit(built):
+    """One CTA per unit, clusters of 2 and 4 CTAs per unit, 512- and 1024-thread CTAs, other chunk sizes: the same bits.
+    plateau_1000bp scans estimates up to 1 050 rows (one CTA per SM), the other cases fit two CTAs per SM."""
+    for name, n in (("multi_gap_err1pct", 3), ("plateau_1000bp", 1), ("lib180_100bp_60x", 1)):
+        case = G.Case(name)
+        gaps = case.gaps[:n]
+        ref = _fill_with_env(case, gaps, {"FB_CLUSTER": "1", "FB_THREADS1": "512"})
+        for g, r in zip(gaps, ref):
+            assert r[0] == g["filled"] and r[1] == g["best_est"] and r[2] == np.asarray(g["liks"]).tobytes()
+        for env in ({"FB_CLUSTER": "2"}, {"FB_CLUSTER": "4"}, {"FB_CLUSTER": "1"}, {"FB_CLUSTER": "4", "FB_CHUNK": "8"},
+                    {"FB_CLUSTER": "1", "FB_CHUNK": "32"}, {"FB_CLUSTER": "2", "FB_CHUNK": "5"}):
+            assert _fill_with_env(case, gaps, env) == ref, (name, env)
