@@ -459,8 +459,9 @@ def main():
     ap.add_argument("--partition", default="gap", choices=["gap", "estimate", "record"],
                     help="strong scaling only: deal gaps, (gap, estimate) units when few gaps dominate, or blocks of every gap's records "
                          "(BASELINE config 3: partial counts exchanged every EM iteration)")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
-                    help="--partition record: peers' partial counts read over NVLink through CUDA IPC mappings (p2p) or all-gathered with NCCL")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "p2p-host", "nccl"],
+                    help="--partition record: peers' partial counts read over NVLink through CUDA IPC mappings, iterations separated by a "
+                         "device-side barrier (p2p) or by a host barrier (p2p-host), or all-gathered with NCCL (nccl)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":

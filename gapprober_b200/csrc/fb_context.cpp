@@ -184,7 +184,9 @@ struct fb_ctx {
     DevBuf<FbUnit> d_units, d_units_scan;          // _scan: the units / gap metadata a record-sharded scan launches with
     DevBuf<FbGapMeta> d_gapmeta_scan;
     DevBuf<double> d_parts[2], d_sumcounts, d_maxmerge;
-    DevBuf<int> d_unit_nrec;
+    DevBuf<int> d_unit_nrec, d_shard_err;
+    DevBuf<unsigned long long> d_flags;   // device-side barrier of the record-sharded scan: one word per rank, written by the peers
+    unsigned long long shard_epoch = 0;   // passes run with the device-side barrier (the same on every rank)
     DevBuf<int> d_counters;
     DevBuf<double> d_maxprob, d_gws, d_finprob, d_dump;
     DevBuf<char> d_cons;
@@ -310,7 +312,7 @@ void fb_destroy(fb_ctx* c) {
     c->d_bestoff.release();
     c->d_st_mask.release(); c->d_st_cls4.release(); c->d_st_jl.release(); c->d_st_cum.release();
     c->d_units_scan.release(); c->d_gapmeta_scan.release(); c->d_parts[0].release(); c->d_parts[1].release();
-    c->d_sumcounts.release(); c->d_maxmerge.release(); c->d_unit_nrec.release();
+    c->d_sumcounts.release(); c->d_maxmerge.release(); c->d_unit_nrec.release(); c->d_shard_err.release(); c->d_flags.release();
     c->h_maxprob.release(); c->h_finprob.release(); c->h_finpos.release(); c->h_stage.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -916,6 +918,12 @@ int fb_upload(fb_ctx* c) {
         FB_CUDA(c, c->d_parts[1].ensure(c->shard_counts));
         FB_CUDA(c, c->d_sumcounts.ensure(c->shard_counts));
         FB_CUDA(c, c->d_maxmerge.ensure(c->shard_maxprob));
+        if (!c->d_flags.p) {     // allocated and zeroed once: the tokens the peers write only ever grow
+            FB_CUDA(c, c->d_flags.ensure(FB_MAX_SHARDS));
+            FB_CUDA(c, c->d_shard_err.ensure(1));
+            FB_CUDA(c, cudaMemset(c->d_flags.p, 0, sizeof(unsigned long long) * FB_MAX_SHARDS));
+            FB_CUDA(c, cudaMemset(c->d_shard_err.p, 0, sizeof(int)));
+        }
         FB_CUDA(c, cudaMemcpyAsync(c->d_gapmeta_scan.p, gm_scan.data(), ng * sizeof(FbGapMeta), cudaMemcpyHostToDevice, c->stream));
         FB_CUDA(c, cudaMemcpyAsync(c->d_units_scan.p, u_scan.data(), u_scan.size() * sizeof(FbUnit), cudaMemcpyHostToDevice, c->stream));
         FB_CUDA(c, cudaMemcpyAsync(c->d_unit_nrec.p, c->unit_nrec.data(), c->unit_nrec.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
@@ -1218,28 +1226,29 @@ int fb_shard_sizes(fb_ctx* c, size_t* counts_doubles, size_t* maxprob_doubles) {
     return FB_OK;
 }
 
-int fb_shard_buffers(fb_ctx* c, double** counts_slot0, double** counts_slot1, double** maxprob) {
+int fb_shard_buffers(fb_ctx* c, double** counts_slot0, double** counts_slot1, double** maxprob, unsigned long long** flags) {
     if (!c) return FB_EINVAL;
     if (!c->uploaded || !c->rec_mode) return c->fail(FB_ESTATE, "fb_shard_buffers needs fb_set_partition_records + fb_upload");
     if (counts_slot0) *counts_slot0 = c->d_parts[0].p;
     if (counts_slot1) *counts_slot1 = c->d_parts[1].p;
     if (maxprob) *maxprob = c->d_maxprob.p;
+    if (flags) *flags = c->d_flags.p;
     return FB_OK;
 }
 
-int fb_shard_scan_iter(fb_ctx* c, int it, const double* const* peer_counts, double* out_counts) {
-    if (!c || !out_counts) return FB_EINVAL;
-    if (!c->uploaded || !c->rec_mode) return c->fail(FB_ESTATE, "fb_shard_scan_iter needs fb_set_partition_records + fb_upload");
-    if (it < 0 || it >= c->num_iter || (it > 0 && !peer_counts)) return c->fail(FB_EINVAL, "iteration %d of %d", it, c->num_iter);
-    FB_CUDA(c, cudaSetDevice(c->device));
+}  // extern "C"
+
+namespace {
+
+// Enqueue one EM iteration of a record-sharded scan (all bins); the caller decides when to synchronise.
+int shard_enqueue_iter(fb_ctx* c, int it, const double* const* peer_counts, double* out_counts, bool first_of_pass) {
     fb_stats& st = c->stats;
-    if (it == 0) {
+    if (first_of_pass) {
         st.em_launches = st.finalize_launches = 0;
         st.finalize_likelihoods = 0;
         st.finalize_kernel_ms = st.em_kernel_ms = 0;
         st.d2h_bytes = 0;
         c->scanned = c->ran = false;
-        FB_CUDA(c, cudaEventRecord(c->evs, c->stream));
         // records scanned elsewhere keep 0 in this rank's maxima, so the ranks' buffers merge with max
         FB_CUDA(c, cudaMemsetAsync(c->d_maxprob.p, 0, sizeof(double) * c->shard_maxprob, c->stream));
         FB_CUDA(c, launch_stage(c, c->stream));
@@ -1267,18 +1276,11 @@ int fb_shard_scan_iter(fb_ctx* c, int it, const double* const* peer_counts, doub
         FB_CUDA(c, cudaEventRecord(c->bin_done[bi], bs));
         FB_CUDA(c, cudaStreamWaitEvent(c->stream, c->bin_done[bi], 0));
     }
-    FB_CUDA(c, cudaEventRecord(c->ev1, c->stream));
-    FB_CUDA(c, cudaStreamSynchronize(c->stream));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
-    st.em_kernel_ms += ms;
     return FB_OK;
 }
 
-int fb_shard_scan_finish(fb_ctx* c, const double* const* peer_counts, const double* const* peer_maxprob) {
-    if (!c || !peer_counts || !peer_maxprob) return FB_EINVAL;
-    if (!c->uploaded || !c->rec_mode) return c->fail(FB_ESTATE, "fb_shard_scan_finish needs fb_set_partition_records + fb_upload");
-    FB_CUDA(c, cudaSetDevice(c->device));
+// The closing reduction (enqueue + wait) and the host likelihoods.
+int shard_finish(fb_ctx* c, const double* const* peer_counts, const double* const* peer_maxprob) {
     FbShardFinParams f;
     memset(&f, 0, sizeof f);
     f.units = c->d_units.p;
@@ -1296,7 +1298,10 @@ int fb_shard_scan_finish(fb_ctx* c, const double* const* peer_counts, const doub
     FB_CUDA(c, fb_launch_shard_finish(f, c->stream));
     c->stats.aux_launches++;
     FB_CUDA(c, cudaMemcpyAsync(c->h_maxprob.p, c->d_maxmerge.p, c->shard_maxprob * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    FB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FB_OK;
+}
+
+void shard_host_liks(fb_ctx* c) {
     c->stats.d2h_bytes = (long)(c->shard_maxprob * sizeof(double));
     // likelihood per unit over ALL records of the gap, in record order (figbird.cpp:1951-1955): the same on every rank
     for (HostGap& g : c->gaps) {
@@ -1315,6 +1320,96 @@ int fb_shard_scan_finish(fb_ctx* c, const double* const* peer_counts, const doub
     }
     c->scanned = true;
     c->ran = false;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fb_shard_scan_iter(fb_ctx* c, int it, const double* const* peer_counts, double* out_counts) {
+    if (!c || !out_counts) return FB_EINVAL;
+    if (!c->uploaded || !c->rec_mode) return c->fail(FB_ESTATE, "fb_shard_scan_iter needs fb_set_partition_records + fb_upload");
+    if (it < 0 || it >= c->num_iter || (it > 0 && !peer_counts)) return c->fail(FB_EINVAL, "iteration %d of %d", it, c->num_iter);
+    FB_CUDA(c, cudaSetDevice(c->device));
+    if (it == 0) FB_CUDA(c, cudaEventRecord(c->evs, c->stream));
+    FB_CUDA(c, cudaEventRecord(c->ev2, c->stream));
+    int rc = shard_enqueue_iter(c, it, peer_counts, out_counts, it == 0);
+    if (rc != FB_OK) return rc;
+    FB_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    FB_CUDA(c, cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev2, c->ev1);
+    c->stats.em_kernel_ms += ms;
+    return FB_OK;
+}
+
+int fb_shard_scan_finish(fb_ctx* c, const double* const* peer_counts, const double* const* peer_maxprob) {
+    if (!c || !peer_counts || !peer_maxprob) return FB_EINVAL;
+    if (!c->uploaded || !c->rec_mode) return c->fail(FB_ESTATE, "fb_shard_scan_finish needs fb_set_partition_records + fb_upload");
+    FB_CUDA(c, cudaSetDevice(c->device));
+    int rc = shard_finish(c, peer_counts, peer_maxprob);
+    if (rc != FB_OK) return rc;
+    FB_CUDA(c, cudaStreamSynchronize(c->stream));
+    shard_host_liks(c);
+    return FB_OK;
+}
+
+int fb_shard_scan_all(fb_ctx* c, const double* const* peer_counts0, const double* const* peer_counts1, const double* const* peer_maxprob,
+                      unsigned long long* const* peer_flags) {
+    if (!c || !peer_counts0 || !peer_counts1 || !peer_maxprob || !peer_flags) return FB_EINVAL;
+    if (!c->uploaded || !c->rec_mode) return c->fail(FB_ESTATE, "fb_shard_scan_all needs fb_set_partition_records + fb_upload");
+    FB_CUDA(c, cudaSetDevice(c->device));
+    const int world = c->part_world, rank = c->part_rank, niter = c->num_iter;
+    if (peer_counts0[rank] != c->d_parts[0].p || peer_counts1[rank] != c->d_parts[1].p || peer_flags[rank] != c->d_flags.p)
+        return c->fail(FB_EINVAL, "entry %d of the peer arrays must be this context's own buffer", rank);
+    FbFlagParams fp;
+    memset(&fp, 0, sizeof fp);
+    for (int q = 0; q < world; q++) {
+        if (!peer_flags[q]) return c->fail(FB_EINVAL, "peer_flags[%d] is null", q);
+        fp.peer_flags[q] = peer_flags[q];
+    }
+    fp.own_flags = c->d_flags.p;
+    fp.rank = rank;
+    fp.world = world;
+    fp.error = c->d_shard_err.p;
+    const unsigned long long stride = (unsigned long long)niter + 2;
+    const unsigned long long epoch = ++c->shard_epoch, base = epoch * stride;
+    auto wait_for = [&](unsigned long long token) {
+        fp.token = token;
+        return fb_launch_flag_wait(fp, c->stream);
+    };
+    auto signal = [&](unsigned long long token) {
+        fp.token = token;
+        return fb_launch_flag_signal(fp, c->stream);
+    };
+    FB_CUDA(c, cudaEventRecord(c->evs, c->stream));
+    // nobody may still be reading what this pass is about to overwrite
+    if (epoch > 1) FB_CUDA(c, wait_for((epoch - 1) * stride + niter + 1));
+    const double* const* slots[2] = {peer_counts0, peer_counts1};
+    double* own[2] = {c->d_parts[0].p, c->d_parts[1].p};
+    for (int it = 0; it < niter; it++) {
+        if (it > 0) FB_CUDA(c, wait_for(base + it));          // every rank has written its partial counts of iteration it-1
+        int rc = shard_enqueue_iter(c, it, it ? slots[(it - 1) & 1] : nullptr, own[it & 1], it == 0);
+        if (rc != FB_OK) return rc;
+        FB_CUDA(c, signal(base + it + 1));
+    }
+    FB_CUDA(c, wait_for(base + niter));
+    int rc = shard_finish(c, slots[(niter - 1) & 1], peer_maxprob);
+    if (rc != FB_OK) return rc;
+    FB_CUDA(c, signal(base + niter + 1));                      // this rank is done reading the peers' buffers
+    c->stats.aux_launches += 2 * niter + 2;
+    int err = 0;
+    FB_CUDA(c, cudaMemcpyAsync(&err, c->d_shard_err.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    FB_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    FB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (err) {
+        cudaMemset(c->d_shard_err.p, 0, sizeof(int));
+        return c->fail(FB_ECUDA, "record-sharded scan: a peer did not reach the barrier in time");
+    }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->evs, c->ev1);
+    c->stats.em_kernel_ms = ms;            // the whole device-side sequence, barriers included
+    shard_host_liks(c);
     return FB_OK;
 }
 

@@ -129,6 +129,16 @@ cudaError_t fb_launch_em_cluster(const FbEmParams& p, int n_clusters, int cluste
 cudaError_t fb_em_max_clusters(int cluster, size_t smem, int* n);     // co-resident clusters of that size on this device
 // n gaps x `slices` CTAs per gap (a CTA takes every slices-th group of 8 records)
 cudaError_t fb_launch_finalize(const FbFinParams& p, int n, int slices, size_t smem, cudaStream_t s);
+// Flags of the record-sharded scan's device-side barrier (one 64-bit word per rank, in every rank's exchange memory).
+struct FbFlagParams {
+    unsigned long long* peer_flags[FB_MAX_SHARDS];   // signal: every rank's flag array (own included)
+    const unsigned long long* own_flags;             // wait: this rank's array, written by the peers
+    unsigned long long token;
+    int rank, world;
+    int* error;                                      // wait: set to 1 when a peer did not arrive in time
+};
+cudaError_t fb_launch_flag_signal(const FbFlagParams& p, cudaStream_t s);
+cudaError_t fb_launch_flag_wait(const FbFlagParams& p, cudaStream_t s);
 cudaError_t fb_launch_stage(const FbStageParams& p, cudaStream_t s);
 cudaError_t fb_launch_shard_finish(const FbShardFinParams& p, cudaStream_t s);
 cudaError_t fb_kernels_init(int* max_smem_optin, int* sm_count);

@@ -758,7 +758,44 @@ __global__ void __launch_bounds__(256) fb_shard_finish_kernel(const FbShardFinPa
     }
 }
 
+// Device-side barrier of the record-sharded scan.  Every rank owns an array of flags in its exchange memory; the peers
+// store into it over NVLink.  signal: after this rank's launches of a phase (stream order), tell every peer; wait: hold
+// the stream until every rank has reached `want`.  Tokens only grow.  A wait gives up after ~10^10 cycles and raises the
+// error word instead of hanging the GPU.
+__global__ void fb_flag_signal_kernel(FbFlagParams p) {
+    const int q = threadIdx.x;
+    if (q >= p.world) return;
+    __threadfence_system();          // the partial counts written by the preceding kernels are visible before the flag
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.peer_flags[q] + p.rank), "l"(p.token) : "memory");
+}
+
+__global__ void fb_flag_wait_kernel(FbFlagParams p) {
+    const int q = threadIdx.x;
+    if (q >= p.world) return;
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p.own_flags + q) : "memory");
+        if (v >= p.token) break;
+        if (clock64() - t0 > 10000000000ll) {
+            atomicExch(p.error, 1);
+            break;
+        }
+        __nanosleep(200);
+    }
+}
+
 }  // namespace
+
+cudaError_t fb_launch_flag_signal(const FbFlagParams& p, cudaStream_t s) {
+    fb_flag_signal_kernel<<<1, 32, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t fb_launch_flag_wait(const FbFlagParams& p, cudaStream_t s) {
+    fb_flag_wait_kernel<<<1, 32, 0, s>>>(p);
+    return cudaGetLastError();
+}
 
 size_t fb_em_smem_bytes(int nr_stride, int gp_stride, int p_stride, int chunk, int pwin, bool global_tables) {
     return em_carve(nullptr, nullptr, nr_stride, gp_stride, p_stride, chunk, pwin, global_tables);

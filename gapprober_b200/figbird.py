@@ -85,7 +85,7 @@ ABI_SYMBOLS = [
     "fb_create", "fb_destroy", "fb_add_gap", "fb_add_gap_file", "fb_add_gap_files", "fb_set_partition", "fb_set_partition_units", "fb_run_scan", "fb_run_finalize", "fb_scan_liks", "fb_merge_liks", "fb_owns_gap", "fb_partition_plan", "fb_gap_cost", "fb_run", "fb_upload",
     "fb_run_device", "fb_result", "fb_estimate_liks", "fb_best_string", "fb_dump_profile", "fb_get_stats",
     "fb_clear_gaps", "fb_gap_range", "fb_last_error", "fb_status_str", "fb_abi_version",
-    "fb_set_partition_records", "fb_shard_sizes", "fb_shard_buffers", "fb_shard_scan_iter", "fb_shard_scan_finish",
+    "fb_set_partition_records", "fb_shard_sizes", "fb_shard_buffers", "fb_shard_scan_iter", "fb_shard_scan_finish", "fb_shard_scan_all",
     "fb_shard_counts", "fb_ipc_export", "fb_ipc_open", "fb_ipc_close",
 ]
 
@@ -137,7 +137,8 @@ def load_library():
     dpp = C.POINTER(C.c_void_p)
     L.fb_set_partition_records.argtypes = [vp, C.c_int, C.c_int]
     L.fb_shard_sizes.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
-    L.fb_shard_buffers.argtypes = [vp, dpp, dpp, dpp]
+    L.fb_shard_buffers.argtypes = [vp, dpp, dpp, dpp, dpp]
+    L.fb_shard_scan_all.argtypes = [vp, dpp, dpp, dpp, dpp]
     L.fb_shard_scan_iter.argtypes = [vp, C.c_int, dpp, vp]
     L.fb_shard_scan_finish.argtypes = [vp, dpp, dpp]
     L.fb_shard_counts.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_double)]
@@ -411,10 +412,15 @@ class FigbirdContext:
         return a.value, b.value
 
     def shardBuffers(self):
-        """Device addresses of this context's own exchange buffers: (counts slot 0, counts slot 1, maxima)."""
-        a, b, m = C.c_void_p(), C.c_void_p(), C.c_void_p()
-        self._check(self._L.fb_shard_buffers(self._h, C.byref(a), C.byref(b), C.byref(m)))
-        return a.value, b.value, m.value
+        """Device addresses of this context's own exchange buffers: (counts slot 0, counts slot 1, maxima, barrier flags)."""
+        a, b, m, f = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(self._L.fb_shard_buffers(self._h, C.byref(a), C.byref(b), C.byref(m), C.byref(f)))
+        return a.value, b.value, m.value, f.value
+
+    def shardScanAll(self, peer_counts0, peer_counts1, peer_maxprob, peer_flags):
+        """The whole record-sharded scan in one call, ranks synchronised by flags in peer memory (one GPU per rank)."""
+        self._check(self._L.fb_shard_scan_all(self._h, self._ptr_array(peer_counts0), self._ptr_array(peer_counts1),
+                                              self._ptr_array(peer_maxprob), self._ptr_array(peer_flags)))
 
     @staticmethod
     def _ptr_array(ptrs):

@@ -105,10 +105,16 @@ class RecordShardSession:
 
     Every rank runs every (gap, estimate) unit over its block of the gap's records, one kernel launch per EM
     iteration; the launch of iteration k+1 starts each unit by adding up, in rank order, the partial counts all ranks
-    wrote in iteration k.  exchange="p2p": the ranks map each other's buffers with CUDA IPC and the kernel loads the
-    peers' partial counts straight over NVLink — no collective moves data, only a barrier separates the iterations.
+    wrote in iteration k.
+    exchange="p2p": the ranks map each other's buffers with CUDA IPC; the kernel loads the peers' partial counts
+      straight over NVLink and the iterations are separated by a device-side barrier (flags the ranks store into each
+      other's memory) — the whole scan is enqueued at once, no collective and no host round trip inside it.  Needs one
+      GPU per rank.
+    exchange="p2p-host": the same mappings, but the host synchronises and runs a barrier after every iteration (works
+      with several ranks on one GPU, which is how the single-GPU tests run it).
     exchange="nccl": the partial counts are all-gathered with NCCL into a local buffer the kernel reads.
-    exchange="auto": p2p, falling back to nccl when the IPC mapping is refused.
+    exchange="auto": p2p under an NCCL process group (one GPU per rank), p2p-host under gloo; nccl when the IPC mapping
+      is refused.
     The session keeps the mappings for repeated scans of the same uploaded gap set."""
 
     def __init__(self, ctx, rank, world, group=None, device=None, exchange="auto"):
@@ -119,26 +125,30 @@ class RecordShardSession:
         ctx.setPartitionRecords(rank, world)
         ctx.upload()
         self.nc, self.nm = ctx.shardSizes()
-        self.own = ctx.shardBuffers()                       # counts slot 0, counts slot 1, maxima
+        self.own = ctx.shardBuffers()                       # counts slot 0, counts slot 1, maxima, flags
         self._opened = []
-        self.exchange = exchange
         if world == 1:
             self.exchange = "p2p"
             self.peers = [[p] for p in self.own]
             return
-        if exchange in ("auto", "p2p"):
-            ok = self._map_peers()
-            if not ok:
-                if exchange == "p2p":
-                    raise RuntimeError("CUDA IPC mapping of the peers' exchange buffers failed")
-                self.exchange = "nccl"
-            else:
-                self.exchange = "p2p"
+        nccl_group = dist.get_backend(group) == "nccl"
+        if exchange == "auto":
+            exchange = "p2p" if nccl_group else "p2p-host"
+            fallback = nccl_group
+        else:
+            fallback = False
+        if exchange == "p2p" and not nccl_group:
+            raise RuntimeError("exchange='p2p' needs one GPU per rank (an NCCL process group); use 'p2p-host'")
+        self.exchange = exchange
+        if exchange in ("p2p", "p2p-host") and not self._map_peers():
+            if not fallback:
+                raise RuntimeError("CUDA IPC mapping of the peers' exchange buffers failed")
+            self.exchange = "nccl"
         if self.exchange == "nccl":
-            if dist.get_backend(group) != "nccl":
+            if not nccl_group:
                 raise RuntimeError("exchange='nccl' needs an NCCL process group")
             self._own_t = [torch.as_tensor(_DeviceDoubles(p, n), device=self.device)
-                           for p, n in zip(self.own, (self.nc, self.nc, self.nm))]
+                           for p, n in zip(self.own[:3], (self.nc, self.nc, self.nm))]
             self._gath_c = torch.empty(world * self.nc, dtype=torch.float64, device=self.device)
             self._gath_m = torch.empty(world * self.nm, dtype=torch.float64, device=self.device)
 
@@ -147,10 +157,10 @@ class RecordShardSession:
         handles = [self.ctx.ipcExport(p) for p in self.own]
         allh = [None] * self.world
         dist.all_gather_object(allh, handles, group=self.group)
-        peers, ok = [[None] * self.world for _ in range(3)], 1
+        peers, ok = [[None] * self.world for _ in range(4)], 1
         try:
             for q in range(self.world):
-                for k in range(3):
+                for k in range(4):
                     if q == self.rank:
                         peers[k][q] = self.own[k]
                     else:
@@ -185,7 +195,10 @@ class RecordShardSession:
         and consensus strings on every rank."""
         import torch
         ctx = self.ctx
-        if self.exchange == "p2p":
+        if self.exchange == "p2p" and self.world > 1:
+            ctx.shardScanAll(*self.peers)
+            return
+        if self.exchange in ("p2p", "p2p-host"):
             for it in range(self.num_iter):
                 ctx.shardScanIter(it, self.peers[(it - 1) & 1] if it else None, self.own[it & 1])
                 self._barrier()
@@ -232,7 +245,7 @@ def scan_record_sharded_local(ctxs):
         c.setPartitionRecords(r, world)
         c.upload()
     bufs = [c.shardBuffers() for c in ctxs]
-    peers = [[bufs[q][k] for q in range(world)] for k in range(3)]
+    peers = [[bufs[q][k] for q in range(world)] for k in range(3)]      # counts slot 0, counts slot 1, maxima
     num_iter = ctxs[0].model.num_iter
     for it in range(num_iter):
         for r, c in enumerate(ctxs):

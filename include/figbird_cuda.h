@@ -154,7 +154,7 @@ int fb_set_partition_records(fb_ctx* ctx, int rank, int world);
 /* Sizes (in doubles) of one partial-count buffer and of the per-record maxima buffer, valid after fb_upload. */
 int fb_shard_sizes(fb_ctx* ctx, size_t* counts_doubles, size_t* maxprob_doubles);
 /* This context's own exchange buffers (device memory from cudaMalloc, exportable with fb_ipc_export). */
-int fb_shard_buffers(fb_ctx* ctx, double** counts_slot0, double** counts_slot1, double** maxprob);
+int fb_shard_buffers(fb_ctx* ctx, double** counts_slot0, double** counts_slot1, double** maxprob, unsigned long long** flags);
 /* One EM iteration over the local record blocks.  peer_counts: `world` device pointers (rank order, own included) to
  * the previous iteration's partial counts, ignored for it == 0.  out_counts: where this iteration's partial counts
  * go.  Returns when the iteration has finished on the device. */
@@ -162,6 +162,13 @@ int fb_shard_scan_iter(fb_ctx* ctx, int it, const double* const* peer_counts, do
 /* Sum the last iteration's partial counts (rank order) -> consensus per unit; merge the per-record maxima of the
  * ranks -> likelihood per estimate (identical on every rank).  Leaves the context as fb_run_scan does. */
 int fb_shard_scan_finish(fb_ctx* ctx, const double* const* peer_counts, const double* const* peer_maxprob);
+/* The whole scan in one call with a device-side barrier (one GPU per rank, all buffers peer-mapped): every array holds
+ * `world` device pointers in rank order, entry `rank` being this context's own buffer from fb_shard_buffers.  All
+ * iterations, the waits between them (flags the ranks store into each other's memory over NVLink) and the closing
+ * reduction are enqueued at once; the host synchronises once at the end.  Every rank must call it the same number of
+ * times.  Equivalent to the fb_shard_scan_iter / barrier / fb_shard_scan_finish sequence. */
+int fb_shard_scan_all(fb_ctx* ctx, const double* const* peer_counts_slot0, const double* const* peer_counts_slot1,
+                      const double* const* peer_maxprob, unsigned long long* const* peer_flags);
 /* Parity tap: summed counts of the gap rows of one unit after fb_shard_scan_finish, laid out [estimate][5]. */
 int fb_shard_counts(fb_ctx* ctx, int gap, int estimate, double* counts);
 /* CUDA IPC plumbing for one-process-per-GPU runs: export a cudaMalloc'ed buffer as a 64-byte handle, map a peer's

@@ -75,7 +75,12 @@ def _run(world, exchange):
 
 @pytest.mark.parametrize("world", [2, 3])
 def test_record_sharded_ipc_exchange(built, world):
-    _run(world, "p2p")
+    """auto: device-side barrier with one GPU per rank, host barrier when the ranks share cuda:0."""
+    _run(world, "auto")
+
+
+def test_record_sharded_ipc_host_barrier(built):
+    _run(2, "p2p-host")
 
 
 def test_record_sharded_nccl_exchange(built):

@@ -92,7 +92,7 @@ def test_record_sharded_call_order(built):
         fb.upload()
         with pytest.raises(FigbirdError):
             fb.runScan()                         # the one-call scan cannot exchange
-        c0, c1, mp = fb.shardBuffers()
+        c0, c1, mp, flags = fb.shardBuffers()
         with pytest.raises(FigbirdError):
             fb.shardScanIter(1, None, c1)        # iterations after the first need the peers' counts
         with pytest.raises(FigbirdError):
