@@ -126,7 +126,8 @@ inline size_t gws_stride_of(int nr_stride, int gp_stride) { return (size_t)10 * 
 
 struct Bin {
     int first_unit, n_units;      // range in the sorted unit array
-    int gpmax, lmax;
+    int gpmax, lmax;   // gpmax: most gap rows the tables of a unit hold (estimate minus the rows nothing touches)
+    int gp_full;       // largest estimate
     int nr_stride, gp_stride, p_stride, chunk;
     bool global_tables;
     int ctas_per_sm;
@@ -681,7 +682,7 @@ int fb_upload(fb_ctx* c) {
     c->t_parse_ms = c->t_pack_ms = 0;
     // ---- units: every (owned gap, estimate); heaviest first so persistent CTAs balance (LPT).
     // The per-gap sums are independent: computed on several host threads, merged in gap order.
-    struct U { int gap, gp; double cost; long liks; };
+    struct U { int gap, gp; double cost; long liks; int hole_lo, hole_len; };
     struct GapUnits { std::vector<U> us; long liks = 0, terms = 0, bytes = 0; };
     fb_stats& st = c->stats;
     memset(&st, 0, sizeof st);
@@ -694,6 +695,25 @@ int fb_upload(fb_ctx* c) {
         GapUnits& out = per_gap[gi];
         long rec_bytes = 0;      // packed bases + mask + metadata in, per-record maximum out
         const int r0 = g.scan_off, r1 = g.scan_off + (g.scan_n < 0 ? g.nrec : g.scan_n);   // the records this context scans
+        // Rows of the gap that no placement of any record can touch, whatever the estimate: the largest hole in the union
+        // of the records' row intervals [lo, a_hi + L2 - 1] (estimate-independent: clamping to an estimate only shrinks
+        // them).  Long gaps are reached an insert length deep from either flank and nowhere else.
+        long hole0 = 0, hole1 = 0, reach = D;          // best internal hole [hole0, hole1), end of the last interval
+        if (!c->rec_mode && !getenv("FB_NO_COMPACT")) {
+            std::vector<std::pair<long, long>> iv;
+            iv.reserve(g.nrec);
+            for (int r = 0; r < g.nrec; r++) {
+                const FbRecMeta& m = c->h_rmeta[g.rec_off + r];
+                const int L2 = m.flags & 0xff;
+                const long lo = std::max(m.a_lo, D - L2 + 1);
+                if (m.a_hi >= lo) iv.emplace_back(lo, (long)m.a_hi + L2);      // rows [lo, a_hi + L2)
+            }
+            std::sort(iv.begin(), iv.end());
+            for (const auto& v : iv) {
+                if (v.first > reach && v.first - reach > hole1 - hole0) { hole0 = reach; hole1 = v.first; }
+                reach = std::max(reach, v.second);
+            }
+        }
         for (int r = r0; r < r1; r++) {
             int L2 = c->h_rmeta[g.rec_off + r].flags & 0xff;
             rec_bytes += (L2 + 3) / 4 + (L2 + 7) / 8 + 8 + 8;
@@ -715,7 +735,17 @@ int fb_upload(fb_ctx* c) {
                     order_terms += placements(m, D, gp) * (m.flags & 0xff);
                 }
             }
-            out.us.push_back({gi, gp, (double)order_terms + 2000.0, liks});
+            int hole_lo = 0, hole_len = 0;
+            if (!c->rec_mode && !getenv("FB_NO_COMPACT")) {
+                // this estimate's candidates: the internal hole, or everything behind the last interval; both end at the
+                // right flank at the latest; the start is rounded up to a multiple of 32 gap rows (M-step row blocks)
+                const long gap_end = (long)D + gp;
+                long a0 = hole0, a1 = std::min(hole1, gap_end), b0 = reach, b1 = gap_end;
+                if (b1 - b0 > a1 - a0) { a0 = b0; a1 = b1; }
+                a0 = D + ((a0 - D + 31) / 32) * 32;
+                if (a1 - a0 >= 64) { hole_lo = (int)a0; hole_len = (int)(a1 - a0); }
+            }
+            out.us.push_back({gi, gp, (double)order_terms + 2000.0, liks, hole_lo, hole_len});
             out.liks += liks * c->num_iter;
             out.terms += terms * c->num_iter;
             out.bytes += (rec_bytes + 2L * 40 * gp) * c->num_iter;   // + counts out / profile in
@@ -741,7 +771,7 @@ int fb_upload(fb_ctx* c) {
         return b;
     };
     std::stable_sort(us.begin(), us.end(), [&](const U& a, const U& b) {
-        int ba = bin_of(a.gp), bb = bin_of(b.gp);
+        int ba = bin_of(a.gp - a.hole_len), bb = bin_of(b.gp - b.hole_len);     // by the rows the tables hold
         if (ba != bb) return ba > bb;       // big bins first: they have the longest units
         return a.cost > b.cost;
     });
@@ -755,12 +785,14 @@ int fb_upload(fb_ctx* c) {
         u.gp = us[i].gp;
         u.mp_off = mp;
         u.cons_off = co;
+        u.hole_lo = us[i].hole_lo;
+        u.hole_len = us[i].hole_len;
         mp += c->gaps[u.gap].nrec;
         co += u.gp;
         c->h_units[i] = u;
         c->unit_nrec[i] = c->gaps[u.gap].nrec;
-        int b = bin_of(u.gp);
-        if (c->bins.empty() || bin_of(c->h_units[c->bins.back().first_unit].gp) != b) {
+        int b = bin_of(u.gp - u.hole_len);
+        if (c->bins.empty() || bin_of(c->h_units[c->bins.back().first_unit].gp - c->h_units[c->bins.back().first_unit].hole_len) != b) {
             Bin nb;
             memset(&nb, 0, sizeof nb);
             nb.first_unit = (int)i;
@@ -768,7 +800,8 @@ int fb_upload(fb_ctx* c) {
         }
         Bin& bn = c->bins.back();
         bn.n_units++;
-        bn.gpmax = std::max(bn.gpmax, u.gp);
+        bn.gpmax = std::max(bn.gpmax, u.gp - u.hole_len);
+        bn.gp_full = std::max(bn.gp_full, u.gp);
         bn.lmax = std::max(bn.lmax, c->gaps[u.gap].lmax);
     }
     // ---- shared-memory geometry per bin
@@ -776,7 +809,7 @@ int fb_upload(fb_ctx* c) {
     for (Bin& b : c->bins) {
         b.nr_stride = b.gpmax + 2 * b.lmax - 2;
         b.gp_stride = (b.gpmax + 1) & ~1;
-        b.p_stride = std::max(1, std::min(pwin, b.gpmax + b.lmax - 1));
+        b.p_stride = std::max(1, std::min(pwin, b.gp_full + b.lmax - 1));
         const size_t two_cta = (size_t)(c->max_smem + 1024) / 2 - 1024 - 512;   // two CTAs per SM incl. 1 KB system reserve each
         const size_t one_cta = (size_t)c->max_smem - 1024;
         b.global_tables = false;

@@ -32,6 +32,8 @@ struct FbUnit {
     int gp;          // gap-length estimate
     long long mp_off;    // offset of this unit's per-record maxima in unit_maxprob
     long long cons_off;  // offset of this unit's consensus string in unit_cons
+    int hole_lo;     // profile rows [hole_lo, hole_lo + hole_len) are touched by no placement of this unit and are left
+    int hole_len;    // out of the tables; hole_lo - D is a multiple of 32, the hole lies inside the gap rows; 0 = none
 };
 
 struct FbEmParams {

@@ -386,11 +386,17 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
         const int R0 = D - lmax + 1;                 // first profile row any placement can touch
         const int NR = gp + 2 * lmax - 2;            // rows [R0, R0+NR) cover every touched row
         const int nrs = p.nr_stride, gps = p.gp_stride;
+        // Long gaps: no placement of any record touches the rows [hl, hl + hn) in the middle of the gap (reads reach at
+        // most an insert length in from either flank), so the tables leave them out.  hl - D is a multiple of 32, so
+        // an M-step row block never straddles the hole; every record's rows lie entirely on one side of it.
+        const int hl = unit.hole_lo, hn = unit.hole_len;
+        const int gpc = gp - hn, NRc = NR - hn;       // rows the tables hold
         const uint8_t* fl = p.flank + (size_t)unit.gap * 2 * D;
 
         // ---- initialize(gp): flanks one-hot from the scaffold, gap rows N=1 (figbird.cpp:1657-1673)
-        for (int xr = tid; xr < NR; xr += NT) {
+        for (int xr = tid; xr < NRc; xr += NT) {
             int x = xr + R0;
+            if (x >= hl) x += hn;
             int b = 4;
             if (x < D) b = fl[x];
             else if (x >= D + gp) b = fl[D + (x - D - gp)];
@@ -415,14 +421,14 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
 #pragma unroll
             for (int k = 0; k < 5; k++) s.pq[k * nrs + xr] = sRow[b][k];
         }
-        for (int i = tid; i < gp; i += NT) {
+        for (int i = tid; i < gpc; i += NT) {
 #pragma unroll
             for (int k = 0; k < 5; k++) s.cnt[k * gps + i] = 0.0;
         }
         __syncthreads();
 
         const int nchunks = (nrec + CH - 1) / CH;
-        const int nrb = (gp + 31) >> 5;               // M-step row blocks of 32 rows
+        const int nrb = (gpc + 31) >> 5;              // M-step row blocks of 32 rows (of the rows the tables hold)
         const int nblk = (PS + 63) >> 6;              // E-step blocks of 64 placements per record
         const int WS = PS + kPadW;                    // score-row stride: the pad after a row is the pad before the next
         const bool keep_staged = nchunks <= 3;        // every chunk owns one of the three stage buffers for the whole unit
@@ -478,8 +484,8 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
                         // accumulators are sums of non-negative scores (or NaN), never -0.0 — and the loop needs no predicates:
                         // per entry one LDS.64 + DADD, list positions fetched four at a time.
                         const int c = task / nrb_q, rb = CLU ? (task - c * nrb_q) * (int)csize + (int)crank : task - c * nrb_q;
-                        const int xg = rb * 32 + lane, x0 = D + rb * 32;
-                        const bool ok0 = xg < gp;
+                        const int xg = rb * 32 + lane, x0 = D + rb * 32 + (D + rb * 32 >= hl ? hn : 0);   // table row, profile row of lane 0
+                        const bool ok0 = xg < gpc;
                         double* cr = s.cnt + c * gps + xg;
                         double a0 = ok0 ? cr[0] : 0.0;                             // rows past the gap accumulate junk that is never stored
                         // per-record set-up, one record per lane: the exact sub-range [qs, qe) of its class list whose positions
@@ -551,7 +557,7 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
                         const int ta = left ? uc + tb : tb - uc;
                         const int tbb = vb_ok ? (left ? ub + tb : tb - ub) : ta;
                         double sa = s.ild[ta - p.thr_min], sb = s.ild[tbb - p.thr_min];
-                        const unsigned char* pa = reinterpret_cast<const unsigned char*>(s.pq + (uc - R0));
+                        const unsigned char* pa = reinterpret_cast<const unsigned char*>(s.pq + (uc - R0 - (lo >= hl ? hn : 0)));
                         const uint32_t* cls4 = SE.cls4 + rl * 16;
                         const unsigned cstride = (unsigned)nrs * 16u;
                         const bool two = lo + 64 * blk + 32 <= hi;           // any lane with a second placement?
@@ -590,8 +596,9 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
             // chunk 0 of a kept staging gets its per-record maxima reset here, a barrier ahead of the next iteration's E tasks
             if (keep_staged && !last && tid < min(CH, nrec)) stage_at(s, 0).rmax[tid] = 0ull;
             // ---- computeProbsGap + computeErrorProbsGap on the gap rows (flank rows never change)
-            for (int xg = tid; xg < gp; xg += NT) {
+            for (int xg = tid; xg < gpc; xg += NT) {
                 if (CLU && (unsigned)(xg >> 5) % csize != crank) continue;   // the counts of this row live in another CTA
+                const int xa = xg + (D + xg >= hl ? hn : 0);                  // gap row in the reference's numbering
                 double c[5];
 #pragma unroll
                 for (int k = 0; k < 5; k++) c[k] = s.cnt[k * gps + xg];
@@ -612,7 +619,7 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
                 }
                 if (p.part_out) {
 #pragma unroll
-                    for (int k = 0; k < 5; k++) p.part_out[5 * (size_t)unit.cons_off + (size_t)k * gp + xg] = c[k];
+                    for (int k = 0; k < 5; k++) p.part_out[5 * (size_t)unit.cons_off + (size_t)k * gp + xa] = c[k];
                 }
                 if (last) {
                     // computeSequence(0), figbird.cpp:1991-2004: first strict maximum above 0, else index 0
@@ -621,11 +628,15 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
 #pragma unroll
                     for (int k = 0; k < 5; k++)
                         if (c[k] > mx) { mx = c[k]; idx = k; }
-                    p.unit_cons[unit.cons_off + xg] = "ACGTN"[idx];
+                    p.unit_cons[unit.cons_off + xa] = "ACGTN"[idx];
                 } else {
 #pragma unroll
                     for (int k = 0; k < 5; k++) s.cnt[k * gps + xg] = 0.0;   // placeReads zeroes the gap rows, :1708-1714
                 }
+            }
+            if (last && (!CLU || crank == 0)) {
+                // rows no placement touches keep all-zero counts: computeSequence(0) gives index 0 there
+                for (int i = tid; i < hn; i += NT) p.unit_cons[unit.cons_off + (hl - D) + i] = 'A';
             }
             sync_all();
         }
@@ -635,9 +646,12 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
             const int rows = gp + 2 * D;
             for (int x = tid; x < rows; x += NT) {
                 double c[5];
-                if (x >= D && x < D + gp) {
+                if (x >= hl && x < hl + hn) {
 #pragma unroll
-                    for (int k = 0; k < 5; k++) c[k] = s.cnt[k * gps + (x - D)];
+                    for (int k = 0; k < 5; k++) c[k] = 0.0;      // zeroed by placeReads, never touched
+                } else if (x >= D && x < D + gp) {
+#pragma unroll
+                    for (int k = 0; k < 5; k++) c[k] = s.cnt[k * gps + (x - D - (x >= hl ? hn : 0))];
                 } else {
                     const int b = x < D ? fl[x] : fl[D + (x - D - gp)];
 #pragma unroll
