@@ -53,9 +53,11 @@ def test_ragged_read_lengths_and_lower_case(built):
             _check_against_oracle(fb, gf, case.oracle_model(), g["window"], case.D, g["orig"], recs)
 
 
-def test_long_gap_uses_global_tables(built, tmp_path):
-    """A 3000 bp gap scans estimates 2850..3150: the profile no longer fits shared memory and the kernel variant that
-    keeps it in global memory runs.  Same answers as the oracle."""
+@pytest.mark.parametrize("compact", [True, False])
+def test_long_gap(built, tmp_path, compact):
+    """A 3000 bp gap scans estimates 2850..3149.  By default the middle rows that no placement can reach are left out
+    of the tables and the unit runs from shared memory; with FB_NO_COMPACT=1 the full profile no longer fits and the
+    kernel variant that keeps it in global memory runs.  Same answers as the oracle either way, NaN rows included."""
     from gapprober_b200 import FigbirdContext, FigbirdModel, build, synth
     wd = str(tmp_path / "long")
     synth.generate(wd, ["--genome", "60000", "--gap-list", "3000", "--cov", "10", "--ins-mean", "180", "--ins-sd", "20", "--err", "0.01"], seed=13)
@@ -64,14 +66,23 @@ def test_long_gap_uses_global_tables(built, tmp_path):
     _, seqs = O.read_fasta(os.path.join(wd, "scaffolds.fa"))
     c, s, l = O.read_gap_info(os.path.join(wd, "gapInfo.txt"))[0]
     recs = O.read_gap_file(os.path.join(wd, "Gaps", "gaps_0.sam"))
-    with FigbirdContext(model) as fb:
-        gf = fb.GapFiller().initGapFiller(c, s, l, os.path.join(wd, "Gaps", "gaps_0.sam"), seqs[c])
-        fb.fillGaps()
-        r, orc = _check_against_oracle(fb, gf, omodel, seqs[c], s, l, recs)
-        assert r["gap_max"] == O.gap_range(3000)[1] == 3149      # 3000*1.05f truncates (float arithmetic, figbird.cpp:2453)
-        probs, counts = gf.dumpProfile(r["best_estimate"])
-        o2 = O.fill_gap(omodel, seqs[c], s, l, recs, dump_estimate=r["best_estimate"])
-        assert np.array_equal(probs, o2["probs"], equal_nan=True) and np.array_equal(counts, o2["counts"], equal_nan=True)
+    old = os.environ.pop("FB_NO_COMPACT", None)
+    if not compact:
+        os.environ["FB_NO_COMPACT"] = "1"
+    try:
+        with FigbirdContext(model) as fb:
+            gf = fb.GapFiller().initGapFiller(c, s, l, os.path.join(wd, "Gaps", "gaps_0.sam"), seqs[c])
+            fb.fillGaps()
+            r, orc = _check_against_oracle(fb, gf, omodel, seqs[c], s, l, recs)
+            assert r["gap_max"] == O.gap_range(3000)[1] == 3149      # 3000*1.05f truncates (float arithmetic, figbird.cpp:2453)
+            probs, counts = gf.dumpProfile(r["best_estimate"])
+            o2 = O.fill_gap(omodel, seqs[c], s, l, recs, dump_estimate=r["best_estimate"])
+            assert np.array_equal(probs, o2["probs"], equal_nan=True) and np.array_equal(counts, o2["counts"], equal_nan=True)
+            assert np.isnan(probs[200 + 1500]).all()                 # the middle of the gap: 0/0 in the reference too
+    finally:
+        os.environ.pop("FB_NO_COMPACT", None)
+        if old is not None:
+            os.environ["FB_NO_COMPACT"] = old
 
 
 def test_multihit_duplicates_many_chunks(built, tmp_path):
@@ -229,5 +240,6 @@ def test_kernel_variants_agree_bit_for_bit(built):
         for g, r in zip(gaps, ref):
             assert r[0] == g["filled"] and r[1] == g["best_est"] and r[2] == np.asarray(g["liks"]).tobytes()
         for env in ({"FB_CLUSTER": "2"}, {"FB_CLUSTER": "4"}, {"FB_CLUSTER": "1"}, {"FB_CLUSTER": "4", "FB_CHUNK": "8"},
+                    {"FB_NO_COMPACT": "1"}, {"FB_NO_COMPACT": "1", "FB_CLUSTER": "2"},
                     {"FB_CLUSTER": "1", "FB_CHUNK": "32"}, {"FB_CLUSTER": "2", "FB_CHUNK": "5"}):
             assert _fill_with_env(case, gaps, env) == ref, (name, env)
