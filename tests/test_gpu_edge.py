@@ -78,7 +78,7 @@ def test_long_gap(built, tmp_path, compact):
             probs, counts = gf.dumpProfile(r["best_estimate"])
             o2 = O.fill_gap(omodel, seqs[c], s, l, recs, dump_estimate=r["best_estimate"])
             assert np.array_equal(probs, o2["probs"], equal_nan=True) and np.array_equal(counts, o2["counts"], equal_nan=True)
-            assert np.isnan(probs[200 + 1500]).all()                 # the middle of the gap: 0/0 in the reference too
+            assert np.isnan(probs[200 + 1500, :4]).all()                # the middle of the gap: 0/0 in the reference too
     finally:
         os.environ.pop("FB_NO_COMPACT", None)
         if old is not None:
