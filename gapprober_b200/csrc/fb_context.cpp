@@ -489,7 +489,12 @@ PackConsts consts_of(const fb_ctx* c) { return PackConsts{c->D, c->thr_min, c->t
 template <typename F>
 void parallel_for(int n, int threads, F fn) {
     int hw = (int)std::thread::hardware_concurrency();
-    if (threads <= 0) threads = std::max(1, std::min(hw > 0 ? hw : 1, 16));
+    if (threads <= 0) {
+        // one process per GPU shares the host cores with its siblings (torchrun exports LOCAL_WORLD_SIZE)
+        const char* lws = getenv("LOCAL_WORLD_SIZE");
+        const int procs = lws ? std::max(1, atoi(lws)) : 1;
+        threads = std::max(1, std::min((hw > 0 ? hw : 1) / procs, 16));
+    }
     threads = std::min(threads, n);
     if (threads <= 1) {
         for (int i = 0; i < n; i++) fn(i);
