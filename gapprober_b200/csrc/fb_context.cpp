@@ -21,6 +21,9 @@
 #include <cstring>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <string>
 #include <vector>
@@ -485,6 +488,81 @@ int append_gap(fb_ctx* c, PackedGap& pk) {
 
 PackConsts consts_of(const fb_ctx* c) { return PackConsts{c->D, c->thr_min, c->thr_max, c->max_read_len}; }
 
+// A small persistent pool of host threads: the library fans out three short loops per pass (parse + pack, unit
+// planning, host finalize) and spawning a dozen threads each time costs more than the loops themselves.
+class HostPool {
+    std::vector<std::thread> workers;
+    std::mutex m, run_m;
+    std::condition_variable cv, done_cv;
+    const std::function<void(int)>* fn = nullptr;
+    std::atomic<int> next{0};
+    int n = 0, limit = 0, pending = 0;
+    unsigned long gen = 0;
+    bool stop = false;
+
+    void drain() {
+        for (;;) {
+            int i = next.fetch_add(1);
+            if (i >= n) break;
+            (*fn)(i);
+        }
+    }
+    void loop(int id) {
+        unsigned long seen = 0;
+        std::unique_lock<std::mutex> lk(m);
+        for (;;) {
+            cv.wait(lk, [&] { return stop || gen != seen; });
+            if (stop) return;
+            seen = gen;
+            if (id >= limit) continue;          // this job wants fewer threads
+            lk.unlock();
+            drain();
+            lk.lock();
+            if (--pending == 0) done_cv.notify_all();
+        }
+    }
+
+public:
+    explicit HostPool(int nthreads) {
+        for (int t = 0; t < nthreads; t++) workers.emplace_back([this, t] { loop(t); });
+    }
+    ~HostPool() {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            stop = true;
+        }
+        cv.notify_all();
+        for (auto& w : workers) w.join();
+    }
+    int size() const { return (int)workers.size(); }
+    // false when another host thread is using the pool right now (the caller then runs the loop itself)
+    bool run(int count, int threads, const std::function<void(int)>& f) {
+        std::unique_lock<std::mutex> busy(run_m, std::try_to_lock);
+        if (!busy.owns_lock()) return false;
+        {
+            std::lock_guard<std::mutex> lk(m);
+            fn = &f;
+            n = count;
+            next.store(0);
+            limit = std::min(threads - 1, (int)workers.size());     // the caller works too
+            pending = limit;
+            gen++;
+        }
+        cv.notify_all();
+        drain();
+        std::unique_lock<std::mutex> lk(m);
+        done_cv.wait(lk, [&] { return pending == 0; });
+        fn = nullptr;
+        return true;
+    }
+};
+
+HostPool& host_pool() {      // one per process, created on first use
+    const int hw = (int)std::thread::hardware_concurrency();
+    static HostPool pool(std::max(1, std::min(hw > 0 ? hw : 1, 16) - 1));
+    return pool;
+}
+
 // Run fn(i) for i in [0, n) on up to `threads` host threads (0 = one per hardware thread, at most 16).
 template <typename F>
 void parallel_for(int n, int threads, F fn) {
@@ -500,17 +578,9 @@ void parallel_for(int n, int threads, F fn) {
         for (int i = 0; i < n; i++) fn(i);
         return;
     }
-    std::atomic<int> next(0);
-    std::vector<std::thread> pool;
-    for (int t = 0; t < threads; t++)
-        pool.emplace_back([&]() {
-            for (;;) {
-                int i = next.fetch_add(1);
-                if (i >= n) break;
-                fn(i);
-            }
-        });
-    for (auto& th : pool) th.join();
+    const std::function<void(int)> f = fn;
+    if (host_pool().run(n, threads, f)) return;
+    for (int i = 0; i < n; i++) fn(i);      // pool in use by another context's thread: do it here
 }
 
 }  // namespace
@@ -687,11 +757,12 @@ int fb_upload(fb_ctx* c) {
     c->t_parse_ms = c->t_pack_ms = 0;
     // ---- units: every (owned gap, estimate); heaviest first so persistent CTAs balance (LPT).
     // The per-gap sums are independent: computed on several host threads, merged in gap order.
-    struct U { int gap, gp; double cost; long liks; int hole_lo, hole_len; };
+    struct U { int gap, gp; double cost; long liks; int hole_lo, hole_len; int bin; };
     struct GapUnits { std::vector<U> us; long liks = 0, terms = 0, bytes = 0; };
     fb_stats& st = c->stats;
     memset(&st, 0, sizeof st);
     std::vector<GapUnits> per_gap(c->gaps.size());
+    const bool compact = !c->rec_mode && !getenv("FB_NO_COMPACT");
     parallel_for((int)c->gaps.size(), 0, [&](int gi) {
         HostGap& g = c->gaps[gi];
         g.done = false;
@@ -704,7 +775,7 @@ int fb_upload(fb_ctx* c) {
         // of the records' row intervals [lo, a_hi + L2 - 1] (estimate-independent: clamping to an estimate only shrinks
         // them).  Long gaps are reached an insert length deep from either flank and nowhere else.
         long hole0 = 0, hole1 = 0, reach = D;          // best internal hole [hole0, hole1), end of the last interval
-        if (!c->rec_mode && !getenv("FB_NO_COMPACT")) {
+        if (compact) {
             std::vector<std::pair<long, long>> iv;
             iv.reserve(g.nrec);
             for (int r = 0; r < g.nrec; r++) {
@@ -741,7 +812,7 @@ int fb_upload(fb_ctx* c) {
                 }
             }
             int hole_lo = 0, hole_len = 0;
-            if (!c->rec_mode && !getenv("FB_NO_COMPACT")) {
+            if (compact) {
                 // this estimate's candidates: the internal hole, or everything behind the last interval; both end at the
                 // right flank at the latest; the start is rounded up to a multiple of 32 gap rows (M-step row blocks)
                 const long gap_end = (long)D + gp;
@@ -750,7 +821,7 @@ int fb_upload(fb_ctx* c) {
                 a0 = D + ((a0 - D + 31) / 32) * 32;
                 if (a1 - a0 >= 64) { hole_lo = (int)a0; hole_len = (int)(a1 - a0); }
             }
-            out.us.push_back({gi, gp, (double)order_terms + 2000.0, liks, hole_lo, hole_len});
+            out.us.push_back({gi, gp, (double)order_terms + 2000.0, liks, hole_lo, hole_len, 0});
             out.liks += liks * c->num_iter;
             out.terms += terms * c->num_iter;
             out.bytes += (rec_bytes + 2L * 40 * gp) * c->num_iter;   // + counts out / profile in
@@ -775,11 +846,30 @@ int fb_upload(fb_ctx* c) {
         while (gp > edges[b]) b++;
         return b;
     };
-    std::stable_sort(us.begin(), us.end(), [&](const U& a, const U& b) {
-        int ba = bin_of(a.gp - a.hole_len), bb = bin_of(b.gp - b.hole_len);     // by the rows the tables hold
-        if (ba != bb) return ba > bb;       // big bins first: they have the longest units
-        return a.cost > b.cost;
-    });
+    // order: big bins first (they have the longest units), cost descending inside a bin, ties in (gap, estimate) order.
+    // A stable LSD radix sort on a 48-bit key — a gap set of chr14's size has several hundred thousand units.
+    {
+        const uint64_t kCostMax = (1ull << 44) - 1;
+        std::vector<uint64_t> key(us.size());
+        for (size_t i = 0; i < us.size(); i++) {
+            us[i].bin = bin_of(us[i].gp - us[i].hole_len);     // by the rows the tables hold
+            const uint64_t cst = std::min<uint64_t>(kCostMax, (uint64_t)us[i].cost);
+            key[i] = ((uint64_t)(15 - us[i].bin) << 44) | (kCostMax - cst);
+        }
+        std::vector<uint32_t> idx(us.size()), tmp(us.size());
+        for (size_t i = 0; i < us.size(); i++) idx[i] = (uint32_t)i;
+        for (int pass = 0; pass < 3; pass++) {
+            const int shift = 16 * pass;
+            std::vector<uint32_t> cnt(65537, 0);
+            for (uint32_t i : idx) cnt[((key[i] >> shift) & 0xffff) + 1]++;
+            for (int d = 0; d < 65536; d++) cnt[d + 1] += cnt[d];
+            for (uint32_t i : idx) tmp[cnt[(key[i] >> shift) & 0xffff]++] = i;
+            idx.swap(tmp);
+        }
+        std::vector<U> sorted(us.size());
+        for (size_t i = 0; i < us.size(); i++) sorted[i] = us[idx[i]];
+        us.swap(sorted);
+    }
     c->h_units.resize(us.size());
     c->unit_nrec.resize(us.size());
     c->bins.clear();
