@@ -757,12 +757,25 @@ int fb_upload(fb_ctx* c) {
     c->t_parse_ms = c->t_pack_ms = 0;
     // ---- units: every (owned gap, estimate); heaviest first so persistent CTAs balance (LPT).
     // The per-gap sums are independent: computed on several host threads, merged in gap order.
-    struct U { int gap, gp; double cost; long liks; int hole_lo, hole_len; int bin; };
+    struct U { int gap, gp; double cost; long liks; int hole_lo, hole_len; int key; };
     struct GapUnits { std::vector<U> us; long liks = 0, terms = 0, bytes = 0; };
     fb_stats& st = c->stats;
     memset(&st, 0, sizeof st);
     std::vector<GapUnits> per_gap(c->gaps.size());
     const bool compact = !c->rec_mode && !getenv("FB_NO_COMPACT");
+    // bins by the rows a unit's tables hold (the shared-memory footprint decides occupancy)
+    static const int edges[] = {96, 160, 256, 384, 544, 768, 1024, 1536, 2048, 3072, 4096, 6144, 8192, 1 << 30};
+    auto bin_of = [&](int gp) {
+        int b = 0;
+        while (gp > edges[b]) b++;
+        return b;
+    };
+    auto sort_key = [&](int bin, double cost) {          // ascending key = the launch order
+        const uint64_t cst = std::max<uint64_t>(8, (uint64_t)cost);
+        const int msb = 63 - __builtin_clzll(cst);
+        const int cls = std::min(383, msb * 8 + (int)((cst >> (msb - 3)) & 7));
+        return (15 - bin) * 384 + (383 - cls);
+    };
     parallel_for((int)c->gaps.size(), 0, [&](int gi) {
         HostGap& g = c->gaps[gi];
         g.done = false;
@@ -821,55 +834,41 @@ int fb_upload(fb_ctx* c) {
                 a0 = D + ((a0 - D + 31) / 32) * 32;
                 if (a1 - a0 >= 64) { hole_lo = (int)a0; hole_len = (int)(a1 - a0); }
             }
-            out.us.push_back({gi, gp, (double)order_terms + 2000.0, liks, hole_lo, hole_len, 0});
+            const double cost = (double)order_terms + 2000.0;
+            out.us.push_back({gi, gp, cost, liks, hole_lo, hole_len, sort_key(bin_of(gp - hole_len), cost)});
             out.liks += liks * c->num_iter;
             out.terms += terms * c->num_iter;
             out.bytes += (rec_bytes + 2L * 40 * gp) * c->num_iter;   // + counts out / profile in
         }
         g.likelihoods = out.liks;
     });
+    tr.lap("upload:   per-gap planning");
+    // Order: big bins first (they have the longest units), inside a bin by descending cost class (an eighth of a power
+    // of two: persistent CTAs pull the heaviest units first, finer than that does not change the balance), inside a
+    // class in (gap, estimate) order.  One counting sort over the units as the gaps planned them — a gap set of
+    // chr14's size has several hundred thousand units.
     std::vector<U> us;
-    for (size_t gi = 0; gi < c->gaps.size(); gi++) {
-        if (!c->gaps[gi].owned) continue;
-        st.n_gaps++;
-        st.n_records += c->gaps[gi].scan_n < 0 ? c->gaps[gi].nrec : c->gaps[gi].scan_n;
-        st.likelihoods += per_gap[gi].liks;
-        st.base_terms += per_gap[gi].terms;
-        st.algorithmic_bytes += per_gap[gi].bytes;
-        us.insert(us.end(), per_gap[gi].us.begin(), per_gap[gi].us.end());
+    {
+        const int kKeys = 16 * 384;
+        std::vector<size_t> start(kKeys + 1, 0);
+        for (size_t gi = 0; gi < c->gaps.size(); gi++) {
+            if (!c->gaps[gi].owned) continue;
+            st.n_gaps++;
+            st.n_records += c->gaps[gi].scan_n < 0 ? c->gaps[gi].nrec : c->gaps[gi].scan_n;
+            st.likelihoods += per_gap[gi].liks;
+            st.base_terms += per_gap[gi].terms;
+            st.algorithmic_bytes += per_gap[gi].bytes;
+            for (const U& u : per_gap[gi].us) start[u.key + 1]++;
+        }
+        for (int k = 0; k < kKeys; k++) start[k + 1] += start[k];
+        us.resize(start[kKeys]);
+        for (size_t gi = 0; gi < c->gaps.size(); gi++) {
+            if (!c->gaps[gi].owned) continue;
+            for (const U& u : per_gap[gi].us) us[start[u.key]++] = u;
+        }
     }
     st.n_units = (long)us.size();
-    // bins by estimate size (shared-memory footprint decides occupancy), then cost-descending inside a bin
-    static const int edges[] = {96, 160, 256, 384, 544, 768, 1024, 1536, 2048, 3072, 4096, 6144, 8192, 1 << 30};
-    auto bin_of = [&](int gp) {
-        int b = 0;
-        while (gp > edges[b]) b++;
-        return b;
-    };
-    // order: big bins first (they have the longest units), cost descending inside a bin, ties in (gap, estimate) order.
-    // A stable LSD radix sort on a 48-bit key — a gap set of chr14's size has several hundred thousand units.
-    {
-        const uint64_t kCostMax = (1ull << 44) - 1;
-        std::vector<uint64_t> key(us.size());
-        for (size_t i = 0; i < us.size(); i++) {
-            us[i].bin = bin_of(us[i].gp - us[i].hole_len);     // by the rows the tables hold
-            const uint64_t cst = std::min<uint64_t>(kCostMax, (uint64_t)us[i].cost);
-            key[i] = ((uint64_t)(15 - us[i].bin) << 44) | (kCostMax - cst);
-        }
-        std::vector<uint32_t> idx(us.size()), tmp(us.size());
-        for (size_t i = 0; i < us.size(); i++) idx[i] = (uint32_t)i;
-        for (int pass = 0; pass < 3; pass++) {
-            const int shift = 16 * pass;
-            std::vector<uint32_t> cnt(65537, 0);
-            for (uint32_t i : idx) cnt[((key[i] >> shift) & 0xffff) + 1]++;
-            for (int d = 0; d < 65536; d++) cnt[d + 1] += cnt[d];
-            for (uint32_t i : idx) tmp[cnt[(key[i] >> shift) & 0xffff]++] = i;
-            idx.swap(tmp);
-        }
-        std::vector<U> sorted(us.size());
-        for (size_t i = 0; i < us.size(); i++) sorted[i] = us[idx[i]];
-        us.swap(sorted);
-    }
+    tr.lap("upload:   sort");
     c->h_units.resize(us.size());
     c->unit_nrec.resize(us.size());
     c->bins.clear();
@@ -899,6 +898,7 @@ int fb_upload(fb_ctx* c) {
         bn.gp_full = std::max(bn.gp_full, u.gp);
         bn.lmax = std::max(bn.lmax, c->gaps[u.gap].lmax);
     }
+    tr.lap("upload:   unit array");
     // ---- shared-memory geometry per bin
     size_t gws_need = 0;
     for (Bin& b : c->bins) {
