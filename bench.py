@@ -269,9 +269,13 @@ def run_ours(a):
         owner = partition_plan(proxy, world)
         mine = [i for i in range(len(gaps)) if owner[i] == rank]
 
+    # the inputs of a step: scaffold sequences in host memory + the gap files on the host file system (descriptors laid out once)
+    from gapprober_b200 import GapBatch
+    batch = GapBatch([(gaps[i][0], gaps[i][1], gaps[i][2], gap_files[i], seqs[gaps[i][0]]) for i in mine])
+
     def register():
         fb.clearGaps()
-        fb.add_gap_files([(gaps[i][0], gaps[i][1], gaps[i][2], gap_files[i], seqs[gaps[i][0]]) for i in mine])
+        fb.add_gap_files(batch)                # the library reads, parses and packs the gap files (host threads)
         if by_estimate:
             fb.setPartitionUnits(rank, world)
 

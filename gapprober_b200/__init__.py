@@ -4,8 +4,8 @@ Scope (SURVEY.md §8): GapFiller::fillGap and what it calls.  csrc/ holds the CU
 (include/figbird_cuda.h); figbird.py mirrors the reference's GapFiller interface over that ABI;
 synth.py drives the seeded workload generator.  Nothing here runs the EM on the CPU.
 """
-from .figbird import (FigbirdContext, FigbirdError, FigbirdModel, GapFiller, gap_range, load_library,  # noqa: F401
+from .figbird import (FigbirdContext, FigbirdError, FigbirdModel, GapBatch, GapFiller, gap_range, load_library,  # noqa: F401
                       read_gap_file, read_gap_info, read_scaffolds)
 
-__all__ = ["FigbirdContext", "FigbirdError", "FigbirdModel", "GapFiller", "gap_range", "load_library",
+__all__ = ["FigbirdContext", "FigbirdError", "FigbirdModel", "GapBatch", "GapFiller", "gap_range", "load_library",
            "read_gap_file", "read_gap_info", "read_scaffolds"]

@@ -606,16 +606,62 @@ int fb_add_gap_files(fb_ctx* c, const fb_gap_desc* descs, int n, int* handles, i
     if (!c || n < 0 || (n > 0 && (!descs || !handles))) return FB_EINVAL;
     const PackConsts k = consts_of(c);
     std::vector<PackedGap> packed((size_t)n);
+    const auto t0 = std::chrono::steady_clock::now();
     parallel_for(n, threads, [&](int i) {
         const fb_gap_desc& d = descs[i];
         if (!d.contig) pack_fail(packed[i], FB_EINVAL, "gap %d: null contig", i);
         else parse_and_pack(k, d.contig_no, d.gap_start, d.orig_gap, d.contig, d.contig_len, d.gap_file, packed[i]);
     });
+    const auto t1 = std::chrono::steady_clock::now();
+    // appended in the order given (handles are dense and deterministic): sizes first, one resize per array, then the
+    // copies on the host threads
     int bad = 0;
-    for (int i = 0; i < n; i++) {        // appended in the order given: handles are dense and deterministic
-        handles[i] = append_gap(c, packed[i]);
-        if (handles[i] < 0) bad++;
+    std::vector<size_t> rec_at((size_t)n + 1, c->h_rmeta.size());
+    std::vector<int> slot((size_t)n, -1);
+    int ngood = 0;
+    for (int i = 0; i < n; i++) {
+        rec_at[i + 1] = rec_at[i];
+        if (packed[i].status != FB_OK) {
+            handles[i] = c->fail(packed[i].status, "%s", packed[i].err.c_str());
+            bad++;
+            continue;
+        }
+        slot[i] = (int)c->gaps.size() + ngood++;
+        handles[i] = slot[i];
+        rec_at[i + 1] += packed[i].rmeta.size();
     }
+    const size_t g0 = c->gaps.size(), nr_new = rec_at[n];
+    const size_t D2 = 2 * (size_t)c->D;
+    c->gaps.resize(g0 + ngood);
+    c->h_gapmeta.resize(g0 + ngood);
+    c->h_flank.resize((g0 + ngood) * D2);
+    c->h_rmeta.resize(nr_new);
+    c->h_nmask.resize(nr_new);
+    c->h_codes.resize(nr_new * 2);
+    c->h_bytes.resize(nr_new * FB_MAX_READ);
+    parallel_for(n, threads, [&](int i) {
+        if (slot[i] < 0) return;
+        PackedGap& pk = packed[i];
+        const size_t r0 = rec_at[i], nr = pk.rmeta.size();
+        pk.g.rec_off = (int)r0;
+        memcpy(&c->h_flank[(size_t)slot[i] * D2], pk.flank.data(), D2);
+        if (nr) {
+            memcpy(&c->h_bytes[r0 * FB_MAX_READ], pk.bytes.data(), nr * FB_MAX_READ);
+            memcpy(&c->h_codes[r0 * 2], pk.codes.data(), nr * 2 * sizeof(uint4));
+            memcpy(&c->h_nmask[r0], pk.nmask.data(), nr * sizeof(uint4));
+            memcpy(&c->h_rmeta[r0], pk.rmeta.data(), nr * sizeof(FbRecMeta));
+        }
+        FbGapMeta gm;
+        gm.rec_off = pk.g.rec_off;
+        gm.nrec = pk.g.nrec;
+        gm.orig = pk.g.orig;
+        gm.lmax = pk.g.lmax;
+        c->h_gapmeta[slot[i]] = gm;
+        c->gaps[slot[i]] = pk.g;
+    });
+    c->uploaded = c->ran = c->scanned = false;
+    c->t_parse_ms += std::chrono::duration<double, std::milli>(t1 - t0).count();                                  // FB_TRACE: parse + pack (threads)
+    c->t_pack_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();     // FB_TRACE: append (serial)
     if (!bad) return FB_OK;
     const std::string last = c->err;
     return c->fail(FB_EDOMAIN, "%d of %d gaps were refused (see handles); last: %s", bad, n, last.c_str());
@@ -753,7 +799,7 @@ int fb_upload(fb_ctx* c) {
     FB_CUDA(c, cudaSetDevice(c->device));
     const int D = c->D, pwin = c->thr_max - c->thr_min + 1;
     Trace tr;
-    if (tr.on) fprintf(stderr, "[fb_trace] add_gap_file: parse %.3f ms, pack %.3f ms\n", c->t_parse_ms, c->t_pack_ms);
+    if (tr.on) fprintf(stderr, "[fb_trace] add_gap_files: parse + pack %.3f ms, append %.3f ms\n", c->t_parse_ms, c->t_pack_ms);
     c->t_parse_ms = c->t_pack_ms = 0;
     // ---- units: every (owned gap, estimate); heaviest first so persistent CTAs balance (LPT).
     // The per-gap sums are independent: computed on several host threads, merged in gap order.

@@ -309,6 +309,27 @@ class GapFiller:
         return self._ctx._dump(self.index, estimate)
 
 
+class GapBatch:
+    """The descriptors of many gaps ([(contigNo, gapStart, originalGap, gapFilePath, contig bytes)]) laid out once for
+    fb_add_gap_files, for callers that register the same gap set repeatedly."""
+
+    def __init__(self, gaps):
+        n = len(gaps)
+        self.n = n
+        self.descs = (_FbGapDesc * max(1, n))()
+        self.handles = (C.c_int * max(1, n))()
+        self._keep = []
+        self.meta = []
+        self._fillers = None
+        for i, (c, s, l, path, contig) in enumerate(gaps):
+            p = os.fsencode(path)
+            self._keep.append((p, contig))
+            d = self.descs[i]
+            d.contig_no, d.gap_start, d.orig_gap = int(c), int(s), int(l)
+            d.contig, d.contig_len, d.gap_file = contig, len(contig), p
+            self.meta.append((int(c), int(s), int(l)))
+
+
 class FigbirdContext:
     """A model bound to one GPU; owns the registered gaps.  fillGaps() = GapFiller::fillGap for all of them."""
 
@@ -361,29 +382,32 @@ class FigbirdContext:
         return self._check(self._L.fb_add_gap_file(self._h, contig_no, gap_start, orig, contig, len(contig), path))
 
     def add_gap_files(self, gaps, threads=0):
-        """Register many gaps at once: gaps = [(contigNo, gapStart, originalGap, gapFilePath, contig bytes)].  The library
-        parses and packs the files on several host threads (fb_add_gap_files).  Returns the GapFiller objects."""
-        n = len(gaps)
-        descs = (_FbGapDesc * max(1, n))()
-        keep = []
-        for i, (c, s, l, path, contig) in enumerate(gaps):
-            p = os.fsencode(path)
-            keep.append(p)
-            descs[i].contig_no, descs[i].gap_start, descs[i].orig_gap = int(c), int(s), int(l)
-            descs[i].contig, descs[i].contig_len, descs[i].gap_file = contig, len(contig), p
-        handles = (C.c_int * max(1, n))()
-        rc = self._L.fb_add_gap_files(self._h, descs, n, handles, int(threads))
+        """Register many gaps at once: gaps = [(contigNo, gapStart, originalGap, gapFilePath, contig bytes)] or a GapBatch
+        prepared from such a list.  The library parses and packs the files on several host threads
+        (fb_add_gap_files).  Returns the GapFiller objects."""
+        batch = gaps if isinstance(gaps, GapBatch) else GapBatch(gaps)
+        n = batch.n
+        rc = self._L.fb_add_gap_files(self._h, batch.descs, n, batch.handles, int(threads))
+        handles = np.frombuffer(batch.handles, dtype=np.int32, count=n)
+        cached = batch._fillers
+        if (rc == FB_OK and cached is not None and cached[0] is self and len(self._gaps) == (int(handles[0]) if n else 0)
+                and np.array_equal(handles, cached[1])):
+            out = cached[2]                      # same context, same handles as last time: the objects are still right
+            self._gaps.extend(out)
+            return out
         out = []
-        for i, (c, s, l, path, contig) in enumerate(gaps):
-            if handles[i] < 0:
+        for (c, s, l), h in zip(batch.meta, handles.tolist()):
+            if h < 0:
                 continue
             g = GapFiller(self)
-            g.contigNo, g.gapStart, g.originalGap, g.index = int(c), int(s), int(l), handles[i]
-            while len(self._gaps) <= g.index:
+            g.contigNo, g.gapStart, g.originalGap, g.index = c, s, l, h
+            while len(self._gaps) <= h:
                 self._gaps.append(None)
-            self._gaps[g.index] = g
+            self._gaps[h] = g
             out.append(g)
         self._check(rc)
+        if n and len(out) == n and np.array_equal(handles, np.arange(handles[0], handles[0] + n)):
+            batch._fillers = (self, handles.copy(), out)
         return out
 
     def add_workdir(self, wd, scaffolds="scaffolds.fa", threads=0):
