@@ -24,7 +24,7 @@
 // scores to a cell in exactly the order the CPU's scatter loop does.  Likelihood plateaus therefore
 // tie exactly as they do on the CPU.  No tensor cores: the path is not a contraction.
 //
-// Roofs: ~6.5 algorithmic HBM bytes per likelihood (5 MB of real DRAM traffic per bench step) vs ~1.6 KB of
+// Roofs: ~6.5 algorithmic HBM bytes per likelihood (6.5 MB of real DRAM traffic per bench step) vs ~1.6 KB of
 // shared-memory reads and ~400 FP64 instructions per likelihood, so shared-memory bandwidth (then the FP64 pipe)
 // binds; DESIGN.md has the arithmetic, profiles/README.md the measurements.
 
