@@ -426,7 +426,7 @@ def run_ours(a):
                      "peak_gbs": smem_peak, "frac": smem_bytes / em_s / 1e9 / smem_peak,
                      "peak_source": "148 SMs x 128 B/clk x max SM clock (B300_MICROARCH.md: smem crossbar 128 B/clk/SM)",
                      "fp64_instr_per_step": st["base_terms"] * 5, "fp64_ginstr_s": st["base_terms"] * 5 / em_s / 1e9,
-                     "note": "useful bytes = 16 B per base term; ncu reports 76-84 % shared-memory pipe utilisation for the same launches "
+                     "note": "useful bytes = 16 B per base term; ncu reports 80-82 % shared-memory pipe utilisation for the same launches "
                              "(profiles/r1_ncu_full_summary.csv) — lane packing (81 %) and the M-step's reads account for the difference"},
         }
         if world == 1 and not a.no_cpu:
