@@ -33,6 +33,7 @@ int main(int argc, char** argv) {
     FILE* single = fopen("singletons.sam", "w");
     FILE* un = fopen("unmapped.txt", "w");
     sp.run("result.sam", myout, single, linking, un, true);
+    if (getenv("FB_TRACE")) fprintf(stderr, "[fb_trace] split: %ld stretches, %ld run again\n", sp.stretches, sp.reruns);
     fclose(myout);
     fclose(linking);
     fclose(single);

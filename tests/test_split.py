@@ -54,3 +54,70 @@ def test_in_memory_handoff_learns_the_same_model(built, tmp_path):
     subprocess.run([build.build_host(), "scaffolds.fa", " 0", "250"], cwd=wd, env=env, check=True, stdout=subprocess.DEVNULL)
     assert open(os.path.join(wd, "mem.bin"), "rb").read() == via_files
     assert not os.path.exists(os.path.join(wd, "myout.sam"))
+
+
+def _outputs(d):
+    names = SAME + ["singletons.sam"] + sorted(os.path.join("Gaps", f) for f in os.listdir(os.path.join(d, "Gaps")))
+    return {n: open(os.path.join(d, n), "rb").read() for n in names}
+
+
+def _mangle(path, seed):
+    """Make a SAM the parallel splitter cannot cut blindly: /1 /2 suffixes on some proper pairs (the name changes inside
+    a pair), mate lines dropped from some unpaired groups (the machine then pairs lines of different reads), an
+    over-long line (split by the reference's 1023-byte fgets) and a record whose name repeats after a gap."""
+    import random
+    rng = random.Random(seed)
+    lines = open(path, "rb").read().split(b"\n")
+    out = []
+    i = 0
+    while i < len(lines):
+        ln = lines[i]
+        f = ln.split(b"\t")
+        if len(f) > 10 and not ln.startswith(b"@"):
+            flag = int(f[1])
+            r = rng.random()
+            if flag & 2 and r < 0.15 and i + 1 < len(lines):
+                g = lines[i + 1].split(b"\t")
+                f[0] += b"/1"
+                g[0] += b"/2"
+                out += [b"\t".join(f), b"\t".join(g)]
+                i += 2
+                continue
+            if not flag & 2 and r < 0.05:
+                i += 1                      # drop this line: the groups behind it shift
+                continue
+            if r > 0.999:
+                f[9] = f[9] * 12            # > 1023 characters
+                f[10] = f[10] * 12
+                ln = b"\t".join(f)
+        out.append(ln)
+        i += 1
+    open(path, "wb").write(b"\n".join(out))
+
+
+@pytest.mark.parametrize("mangled", [False, True])
+def test_split_is_the_same_for_every_stretch_size(built, tmp_path, mangled):
+    """The file is cut into stretches that run on several threads; whatever the cut points, the outputs are those of
+    the one-stretch (= sequential) run, which test_split_equals_reference_main_out pins to main.out."""
+    from gapprober_b200 import build, synth
+    base = str(tmp_path / "base")
+    synth.generate(base, ARGS, seed=43, direct=False, sam=True)
+    if mangled:
+        _mangle(os.path.join(base, "result.sam"), 7)
+    want = None
+    for stretch, threads in (("4000000000", "1"), ("700", "3"), ("5000", "8"), ("65536", "2"), ("1000000", "4")):
+        d = str(tmp_path / f"s{stretch}")
+        shutil.copytree(base, d)
+        env = dict(os.environ, FIGBIRD_SPLIT_STRETCH=stretch, FIGBIRD_THREADS=threads, FB_TRACE="1")
+        r = subprocess.run([os.path.join(build.BIN, "fb_split"), "scaffolds.fa", "250"], cwd=d, env=env, check=True,
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+        got = dict(_outputs(d), stdout=r.stdout)
+        if want is None:
+            want = got
+            assert b"1 stretches, 0 run again" in r.stderr
+        else:
+            assert got.keys() == want.keys()
+            for k in want:
+                assert got[k] == want[k], (stretch, k)
+            if not mangled:
+                assert b" 0 run again" in r.stderr, r.stderr      # well-formed input: every speculative start was right
