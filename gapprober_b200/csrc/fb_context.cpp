@@ -25,6 +25,7 @@
 #include <functional>
 #include <mutex>
 #include <thread>
+#include <unistd.h>
 #include <string>
 #include <vector>
 
@@ -499,6 +500,7 @@ class HostPool {
     int n = 0, limit = 0, pending = 0;
     unsigned long gen = 0;
     bool stop = false;
+    const pid_t owner = getpid();
 
     void drain() {
         for (;;) {
@@ -527,6 +529,10 @@ public:
         for (int t = 0; t < nthreads; t++) workers.emplace_back([this, t] { loop(t); });
     }
     ~HostPool() {
+        if (getpid() != owner) {
+            for (auto& w : workers) w.detach();
+            return;
+        }
         {
             std::lock_guard<std::mutex> lk(m);
             stop = true;
@@ -537,6 +543,7 @@ public:
     int size() const { return (int)workers.size(); }
     // false when another host thread is using the pool right now (the caller then runs the loop itself)
     bool run(int count, int threads, const std::function<void(int)>& f) {
+        if (getpid() != owner) return false;      // a forked child has the object but not the threads
         std::unique_lock<std::mutex> busy(run_m, std::try_to_lock);
         if (!busy.owns_lock()) return false;
         {
