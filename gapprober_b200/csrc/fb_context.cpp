@@ -529,10 +529,6 @@ public:
         for (int t = 0; t < nthreads; t++) workers.emplace_back([this, t] { loop(t); });
     }
     ~HostPool() {
-        if (getpid() != owner) {
-            for (auto& w : workers) w.detach();
-            return;
-        }
         {
             std::lock_guard<std::mutex> lk(m);
             stop = true;
@@ -564,10 +560,10 @@ public:
     }
 };
 
-HostPool& host_pool() {      // one per process, created on first use
+HostPool& host_pool() {      // one per process, created on first use and never destroyed (its threads end with the process)
     const int hw = (int)std::thread::hardware_concurrency();
-    static HostPool pool(std::max(1, std::min(hw > 0 ? hw : 1, 16) - 1));
-    return pool;
+    static HostPool* pool = new HostPool(std::max(1, std::min(hw > 0 ? hw : 1, 16) - 1));
+    return *pool;
 }
 
 // Run fn(i) for i in [0, n) on up to `threads` host threads (0 = one per hardware thread, at most 16).
