@@ -144,6 +144,8 @@ struct Bin {
 
 }  // namespace
 
+void host_pool_warm();   // creates the library's host thread pool
+
 struct fb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
@@ -250,6 +252,18 @@ void fb_gap_range(int orig_gap, int* gap_min, int* gap_max) {
     else hi = 1.5;
     *gap_min = orig_gap * lo < 10 ? 1 : orig_gap * lo;
     *gap_max = orig_gap * hi;
+}
+
+int fb_warmup(int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || device < 0 || device >= ndev) return FB_ECUDA;
+    if (cudaSetDevice(device) != cudaSuccess || cudaFree(nullptr) != cudaSuccess) return FB_ECUDA;
+    int smem = 0, sms = 0;
+    if (fb_kernels_init(&smem, &sms) != cudaSuccess) return FB_ECUDA;
+    void* pin = nullptr;                       // the first pinned allocation sets up the host allocator
+    if (cudaMallocHost(&pin, 1 << 16) == cudaSuccess) cudaFreeHost(pin);
+    host_pool_warm();
+    return FB_OK;
 }
 
 int fb_create(const fb_model* m, int device, fb_ctx** out) {
@@ -565,6 +579,12 @@ HostPool& host_pool() {      // one per process, created on first use and never 
     static HostPool* pool = new HostPool(std::max(1, std::min(hw > 0 ? hw : 1, 16) - 1));
     return *pool;
 }
+
+}  // namespace
+
+void host_pool_warm() { host_pool(); }
+
+namespace {
 
 // Run fn(i) for i in [0, n) on up to `threads` host threads (0 = one per hardware thread, at most 16).
 template <typename F>

@@ -19,10 +19,17 @@
 //                            the GPU without writing myout.sam or Gaps/*.sam (gapInfo.txt and stat.txt are still written)
 // There is no CPU fallback: if the library or a GPU is missing the program prints why and exits 1.
 
+// GapProber.py builds this file without any flags, i.e. at -O0; the host stages (splitter, preamble) are text parsing
+// loops that run twice as fast optimised, so ask for it here.  No fast-math: the preamble stays bit-exact.
+#if defined(__GNUC__) && !defined(__clang__) && !defined(__OPTIMIZE__)
+#pragma GCC optimize("O2")
+#endif
+
 #include <dlfcn.h>
 #include <unistd.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -42,6 +49,7 @@ namespace {
 struct Api {
     void* h = nullptr;
     decltype(&fb_create) create = nullptr;
+    decltype(&fb_warmup) warmup = nullptr;
     decltype(&fb_destroy) destroy = nullptr;
     decltype(&fb_add_gap) add_gap = nullptr;
     decltype(&fb_run) run = nullptr;
@@ -80,6 +88,7 @@ bool load_api(Api& a, std::string& why) {
     a.field = reinterpret_cast<decltype(a.field)>(dlsym(a.h, name)); \
     if (!a.field) { why = std::string("missing symbol ") + name; return false; }
     FB_SYM(create, "fb_create")
+    FB_SYM(warmup, "fb_warmup")
     FB_SYM(destroy, "fb_destroy")
     FB_SYM(add_gap, "fb_add_gap")
     FB_SYM(run, "fb_run")
@@ -103,12 +112,38 @@ int main(int argc, char* argv[]) {
     }
     const char* contig_path = argv[1];
     const int f_mode = atoi(argv[2]);
+    const bool trace = getenv("FB_TRACE") != nullptr;      // phase wall times on stderr
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!trace) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[fb_trace] figbird: %-24s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     FILE* out_txt = fopen("out.txt", "w");   // the reference creates it and never writes to it
     fbhost::Scaffolds sc;
     if (!fbhost::read_scaffolds(contig_path, sc)) {
         printf("Can't open contig file\n");
         return 1;
     }
+    lap("scaffolds");
+    // The CUDA context and the kernels come up on a second thread while this one splits and learns the model.
+    Api api;
+    std::string why;
+    bool api_ok = false;
+    const int device = getenv("FIGBIRD_DEVICE") ? atoi(getenv("FIGBIRD_DEVICE")) : 0;
+    const int ngpu = getenv("FIGBIRD_GPUS") ? std::max(1, atoi(getenv("FIGBIRD_GPUS"))) : 1;
+    std::thread warm;
+    if (!getenv("FIGBIRD_PREAMBLE_ONLY"))
+        warm = std::thread([&]() {
+            api_ok = load_api(api, why);
+            if (api_ok)
+                for (int k = 0; k < ngpu; k++) api.warmup(device + k);     // failures are reported by fb_create below
+        });
+    struct Joiner {
+        std::thread& t;
+        ~Joiner() { if (t.joinable()) t.join(); }
+    } joiner{warm};
     const char* from_sam = getenv("FIGBIRD_FROM_SAM");
     fbhost::Splitter* split = nullptr;
     std::string myout_text;
@@ -149,6 +184,7 @@ int main(int argc, char* argv[]) {
         return 1;
     }
 
+    lap("split / stat.txt");
     // ---- preamble (host): model tables + gapProbCutOff
     fbhost::Preamble pre(max_read_len, max_insert, sc.lengths());
     fbhost::Model hm;
@@ -162,14 +198,14 @@ int main(int argc, char* argv[]) {
         fclose(mi);
     }
     if (out_txt) fclose(out_txt);
+    lap("preamble");
     std::cout << "insertThresholdMin = " << hm.thr_min << "...insertThresholdMax = " << hm.thr_max << std::endl;
     if (const char* mo = getenv("FIGBIRD_MODEL_OUT")) hm.save(mo);
     if (getenv("FIGBIRD_PREAMBLE_ONLY")) return 0;
 
     // ---- the hot path, on the GPU
-    Api api;
-    std::string why;
-    if (!load_api(api, why)) {
+    if (warm.joinable()) warm.join();
+    if (!api_ok) {
         printf("figbird: cannot load libfigbird_cuda.so (%s); there is no CPU fallback\n", why.c_str());
         return 1;
     }
@@ -189,8 +225,6 @@ int main(int argc, char* argv[]) {
     m.max_distance = 200;   // maxDistance, figbird.cpp:103
     m.num_iter = 5;         // num_itr, figbird.cpp:2466
     m.f_mode = f_mode;
-    const int device = getenv("FIGBIRD_DEVICE") ? atoi(getenv("FIGBIRD_DEVICE")) : 0;
-    const int ngpu = getenv("FIGBIRD_GPUS") ? std::max(1, atoi(getenv("FIGBIRD_GPUS"))) : 1;
     std::vector<fb_ctx*> ctxs(ngpu, nullptr);
     for (int k = 0; k < ngpu; k++) {
         int rc = api.create(&m, device + k, &ctxs[k]);
@@ -201,6 +235,7 @@ int main(int argc, char* argv[]) {
         }
     }
 
+    lap("library + context");
     time_t t0, t1;
     time(&t0);
     std::vector<fbhost::GapInfo> gaps;
@@ -238,6 +273,7 @@ int main(int argc, char* argv[]) {
             handle[g] = h;
         }
     }
+    lap("gap files + pack");
     std::vector<int> run_rc(ngpu, FB_OK);
     if (ngpu == 1) {
         run_rc[0] = api.run(ctxs[0]);
@@ -255,6 +291,7 @@ int main(int argc, char* argv[]) {
             printf("figbird: fb_run failed on device %d: %s: %s\n", device + k, api.status_str(run_rc[k]), api.last_error(ctxs[k]));
             return 1;
         }
+    lap("fb_run");
     int rc = FB_OK;
     FILE* gap_out = fopen("gapout.txt", "w");
     std::vector<std::string> filled(gaps.size());
@@ -285,9 +322,11 @@ int main(int argc, char* argv[]) {
     time(&t1);
     std::cout << "Total time to fill gaps in seconds = " << difftime(t1, t0) << std::endl;
 
+    lap("results + gapout.txt");
     // ---- stitch
     std::cout << "# of Contig = " << sc.seqs.size() << std::endl;
     fbhost::stitch(sc, filled, "filledContigs.fa");
+    lap("stitch");
     std::cout << "Figbird.cpp ends successfully" << std::endl;
     return 0;
 }

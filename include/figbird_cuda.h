@@ -88,6 +88,9 @@ typedef struct fb_ctx fb_ctx;
 /* Create a context on CUDA device `device` and copy the model.  Replaces the globals the reference's
  * main() leaves behind for GapFiller (figbird.cpp:2718-2794). */
 int fb_create(const fb_model* model, int device, fb_ctx** out);
+/* Optional: bring up the CUDA context of `device` and load the kernels ahead of fb_create, e.g. on a second host thread
+ * while the caller is still learning the model (a fresh process spends several hundred milliseconds here). */
+int fb_warmup(int device);
 void fb_destroy(fb_ctx* ctx);
 
 /* Register one gap = GapFiller::allocate + initGapFiller (figbird.cpp:1543-1566, 1610-1618) plus the
