@@ -430,6 +430,7 @@ public:
     int threads = 0;                 // 0: FIGBIRD_THREADS, else the hardware's (at most 16)
     size_t stretch_bytes = 0;        // 0: FIGBIRD_SPLIT_STRETCH, else 8 MiB
     long stretches = 0, reruns = 0;  // reruns: stretches whose speculative start was wrong (0 on well-formed input)
+    std::string* myout_text = nullptr;   // in-memory use: myout.sam's text is appended here instead of written to a file
 
     explicit Splitter(const Scaffolds& sc) : sc_(sc) {
         // gaps = N-runs followed by a non-N; the run state is NOT reset between scaffolds (main.cpp:938-972)
@@ -471,7 +472,7 @@ public:
         sh.max_distance = max_distance;
         sh.gaps = &gaps;
         sh.name_to_no = &name_to_no_;
-        sh.want_myout = myout != nullptr;
+        sh.want_myout = myout != nullptr || myout_text != nullptr;
         sh.want_single = single != nullptr;
         sh.want_linking = linking != nullptr;
         sh.want_unmapped = unmapped != nullptr;
@@ -628,6 +629,7 @@ private:
         }
         (void)flushed;
         if (myout && !o.myout.empty()) fwrite(o.myout.data(), 1, o.myout.size(), myout);
+        if (myout_text) myout_text->append(o.myout);
         if (single && !o.single.empty()) fwrite(o.single.data(), 1, o.single.size(), single);
         if (linking && !o.linking.empty()) fwrite(o.linking.data(), 1, o.linking.size(), linking);
         if (unmapped && !o.unmapped.empty()) fwrite(o.unmapped.data(), 1, o.unmapped.size(), unmapped);

@@ -151,16 +151,11 @@ int main(int argc, char* argv[]) {
     int max_read_len = 0, max_insert = 0;
     if (from_sam) {
         split = new fbhost::Splitter(sc);
-        char* buf = nullptr;
-        size_t len = 0;
-        FILE* mem = open_memstream(&buf, &len);
-        if (!split->run(from_sam, mem, nullptr, nullptr, nullptr, false)) {
+        split->myout_text = &myout_text;
+        if (!split->run(from_sam, nullptr, nullptr, nullptr, nullptr, false)) {
             printf("Can't open map file\n");
             return 1;
         }
-        fclose(mem);
-        myout_text.assign(buf, len);
-        free(buf);
         total_count = split->total_count;
         un_count = split->un_count;
         max_read_len = (int)split->max_read_len;
