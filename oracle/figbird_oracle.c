@@ -69,6 +69,9 @@ typedef struct {
     char** seq;    /* mate sequence as scored (reverse-complemented when the anchor is forward) */
     int* len2;
     char* consensus;
+    int shards;       /* record-sharded restatement (see orc_fill_gap_sharded); 0 or 1: the reference's single sum */
+    double* part;     /* [max_rows][5] one shard's partial counts */
+    double* total;    /* [max_rows][5] rank-ordered sum of the partial counts */
 } filler;
 
 /* computeProbsGap, figbird.cpp:1568-1587.  0/0 -> NaN is kept. */
@@ -126,7 +129,18 @@ static double place_reads(filler* g) {
         for (int j = 0; j < 5; j++) g->counts[5 * i + j] = 0;
 
     double lik = 0;
-    for (int r = 0; r < g->nrec; r++) {
+    const int shards = g->shards > 1 ? g->shards : 1;
+    double* const counts_home = g->counts;
+    for (int sh = 0; sh < shards; sh++) {
+    /* shard sh takes the records [sh*R/S, (sh+1)*R/S) and accumulates them, in the reference's order, into its own
+     * zeroed array; the shards' arrays are then added in shard order (what the ranks of the GPU path do) */
+    const int r_lo = (int)((long)sh * g->nrec / shards), r_hi = (int)((long)(sh + 1) * g->nrec / shards);
+    if (shards > 1) {
+        for (long i = D; i < rows - D; i++)
+            for (int j = 0; j < 5; j++) g->part[5 * i + j] = 0;
+        g->counts = g->part;
+    }
+    for (int r = r_lo; r < r_hi; r++) {
         const orc_record* rc = &g->recs[r];
         const char* s2 = g->seq[r];
         const int L2 = g->len2[r];
@@ -164,6 +178,18 @@ static double place_reads(filler* g) {
         if (f == 1) lik += best;
         else if (best > 0) lik += log(best); /* :1951-1955 */
     }
+    if (shards > 1) {
+        g->counts = counts_home;
+        for (long i = D; i < rows - D; i++)
+            for (int j = 0; j < 5; j++) {
+                if (sh == 0) g->total[5 * i + j] = g->part[5 * i + j];
+                else g->total[5 * i + j] = g->total[5 * i + j] + g->part[5 * i + j];
+            }
+    }
+    }
+    if (shards > 1)
+        for (long i = D; i < rows - D; i++)
+            for (int j = 0; j < 5; j++) g->counts[5 * i + j] = g->total[5 * i + j];
     return lik;
 }
 
@@ -257,6 +283,11 @@ static int hard_assign(filler* g, int gb, const char* best, int* total, int* dis
 
 int orc_fill_gap(const orc_model* m, const char* contig, long contig_len, long gap_start, int orig_gap,
                  const orc_record* recs, int nrec, orc_result* out) {
+    return orc_fill_gap_sharded(m, contig, contig_len, gap_start, orig_gap, recs, nrec, 1, out);
+}
+
+int orc_fill_gap_sharded(const orc_model* m, const char* contig, long contig_len, long gap_start, int orig_gap,
+                         const orc_record* recs, int nrec, int shards, orc_result* out) {
     const int D = m->max_distance;
     /* Outside these bounds the reference reads past its arrays; refuse instead. */
     if (orig_gap < 1 || gap_start < D || gap_start + orig_gap + D > contig_len) return -2;
@@ -278,6 +309,9 @@ int orc_fill_gap(const orc_model* m, const char* contig, long contig_len, long g
     g.counts = (double*)calloc((size_t)max_rows * 5, sizeof(double));
     g.probs = (double*)calloc((size_t)max_rows * 5, sizeof(double));
     g.eprobs = (double*)calloc((size_t)max_rows * 5, sizeof(double));
+    g.shards = shards;
+    g.part = (double*)calloc((size_t)max_rows * 5, sizeof(double));
+    g.total = (double*)calloc((size_t)max_rows * 5, sizeof(double));
     g.consensus = (char*)calloc((size_t)cap + 2, 1);
     char* best = (char*)calloc((size_t)cap + 2, 1);
     g.seq = (char**)calloc((size_t)(nrec > 0 ? nrec : 1), sizeof(char*));
@@ -335,6 +369,8 @@ int orc_fill_gap(const orc_model* m, const char* contig, long contig_len, long g
     free(g.counts);
     free(g.probs);
     free(g.eprobs);
+    free(g.part);
+    free(g.total);
     free(g.consensus);
     free(best);
     return rc;

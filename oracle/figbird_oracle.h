@@ -62,6 +62,14 @@ typedef struct orc_result {
 int orc_fill_gap(const orc_model* m, const char* contig, long contig_len, long gap_start, int orig_gap,
                  const orc_record* recs, int nrec, orc_result* out);
 
+/* The same with the M-step sum of placeReads grouped the way the record-sharded multi-GPU scan groups it: the records
+ * are cut into `shards` contiguous blocks [s*R/S, (s+1)*R/S), each block is accumulated in the reference's order into
+ * its own array, and the arrays are added in block order, ((p0 + p1) + p2) + ...  With shards <= 1 this is orc_fill_gap.
+ * This is NOT the reference's arithmetic (it differs from it in the last bits); it pins, bit for bit, what
+ * fb_set_partition_records computes with `shards` ranks. */
+int orc_fill_gap_sharded(const orc_model* m, const char* contig, long contig_len, long gap_start, int orig_gap,
+                         const orc_record* recs, int nrec, int shards, orc_result* out);
+
 /* Estimate range only (figbird.cpp:2438-2453), float arithmetic included. */
 void orc_gap_range(int orig_gap, int* gap_min, int* gap_max);
 

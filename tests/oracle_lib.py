@@ -71,6 +71,9 @@ def lib():
         _lib.orc_fill_gap.restype = C.c_int
         _lib.orc_fill_gap.argtypes = [C.POINTER(OrcModel), C.c_char_p, C.c_long, C.c_long, C.c_int,
                                       C.POINTER(OrcRecord), C.c_int, C.POINTER(OrcResult)]
+        _lib.orc_fill_gap_sharded.restype = C.c_int
+        _lib.orc_fill_gap_sharded.argtypes = [C.POINTER(OrcModel), C.c_char_p, C.c_long, C.c_long, C.c_int,
+                                              C.POINTER(OrcRecord), C.c_int, C.c_int, C.POINTER(OrcResult)]
         _lib.orc_gap_range.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         _lib.orc_count_likelihoods.restype = C.c_long
         _lib.orc_count_likelihoods.argtypes = [C.POINTER(OrcModel), C.c_long, C.c_int, C.POINTER(OrcRecord), C.c_int]
@@ -139,8 +142,9 @@ def gap_range(orig):
     return a.value, b.value
 
 
-def fill_gap(model, contig, gap_start, orig_gap, recs, dump_estimate=0):
-    """Run the oracle on one gap.  contig: bytes (upper-cased scaffold).  Returns a dict."""
+def fill_gap(model, contig, gap_start, orig_gap, recs, dump_estimate=0, shards=1):
+    """Run the oracle on one gap.  contig: bytes (upper-cased scaffold).  Returns a dict.
+    shards > 1: the record-sharded grouping of the M-step sums (orc_fill_gap_sharded) instead of the reference's."""
     L = lib()
     m = model.as_orc()
     arr = (OrcRecord * max(1, len(recs)))()
@@ -166,7 +170,7 @@ def fill_gap(model, contig, gap_start, orig_gap, recs, dump_estimate=0):
         probs, counts = np.zeros(n), np.zeros(n)
         res.probs_dump = probs.ctypes.data_as(C.POINTER(C.c_double))
         res.counts_dump = counts.ctypes.data_as(C.POINTER(C.c_double))
-    rc = L.orc_fill_gap(C.byref(m), contig, len(contig), gap_start, orig_gap, arr, len(recs), C.byref(res))
+    rc = L.orc_fill_gap_sharded(C.byref(m), contig, len(contig), gap_start, orig_gap, arr, len(recs), int(shards), C.byref(res))
     if rc != 0:
         raise RuntimeError(f"orc_fill_gap failed: {rc}")
     return dict(gap_min=res.gap_min, gap_max=res.gap_max, best_estimate=res.best_estimate, best_lik=res.best_lik,

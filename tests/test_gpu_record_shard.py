@@ -43,31 +43,35 @@ def _shard_run(case, gaps, world):
 
 @pytest.mark.parametrize("world", [1, 2, 3])
 def test_record_sharded_scan_matches_oracle(built, world):
+    """Bit for bit against the oracle's restatement of the rank-ordered sum (orc_fill_gap_sharded), to rounding against
+    the reference's own grouping (the unsharded oracle, pinned to the reference by the golden fixtures)."""
     case = G.Case("multi_gap_err1pct")
     gaps = case.gaps[:4]
     liks, results, counts = _shard_run(case, gaps, world)
     for i, g in enumerate(gaps):
         orc = O.fill_gap(case.oracle_model(), g["window"], case.D, g["orig"], g["recs"])
+        sh = O.fill_gap(case.oracle_model(), g["window"], case.D, g["orig"], g["recs"], shards=world)
         for r in range(world):
             assert np.array_equal(liks[r][i], liks[0][i])            # every rank holds the same bits
+        assert np.array_equal(liks[0][i], sh["liks"])                # ... and they are the sharded oracle's
+        assert np.allclose(liks[0][i], orc["liks"], rtol=REL, atol=0)
         if world == 1:
             assert np.array_equal(liks[0][i], orc["liks"])
-        else:
-            assert np.allclose(liks[0][i], orc["liks"], rtol=REL, atol=0)
         res = results[i]
-        assert res["best_estimate"] == orc["best_estimate"]
-        assert res["filled"] == orc["filled"]
-        assert (res["total_reads"], res["discarded"]) == (orc["total_reads"], orc["discarded"])
-        o2 = O.fill_gap(case.oracle_model(), g["window"], case.D, g["orig"], g["recs"], dump_estimate=res["best_estimate"])
-        want = o2["counts"][case.D:case.D + res["best_estimate"]]
-        if world == 1:
-            assert np.array_equal(counts[i], want, equal_nan=True)
-        else:
-            assert np.allclose(counts[i], want, rtol=REL, atol=0, equal_nan=True)
-            # per-position probabilities, computeProbsGap (figbird.cpp:1568-1587), within north_star's 1e-5 relative
-            with np.errstate(invalid="ignore", divide="ignore"):
-                pg = (counts[i][:, :4] + counts[i][:, 4:5] / 4) / counts[i].sum(axis=1, keepdims=True)
-            assert np.allclose(pg, o2["probs"][case.D:case.D + res["best_estimate"], :4], rtol=1e-5, atol=0, equal_nan=True)
+        for want in (orc, sh):
+            assert res["best_estimate"] == want["best_estimate"]
+            assert res["filled"] == want["filled"]
+            assert (res["total_reads"], res["discarded"]) == (want["total_reads"], want["discarded"])
+        be = res["best_estimate"]
+        o2 = O.fill_gap(case.oracle_model(), g["window"], case.D, g["orig"], g["recs"], dump_estimate=be)
+        s2 = O.fill_gap(case.oracle_model(), g["window"], case.D, g["orig"], g["recs"], dump_estimate=be, shards=world)
+        assert np.array_equal(counts[i], s2["counts"][case.D:case.D + be], equal_nan=True)
+        want = o2["counts"][case.D:case.D + be]
+        assert np.allclose(counts[i], want, rtol=REL, atol=0, equal_nan=True)
+        # per-position probabilities, computeProbsGap (figbird.cpp:1568-1587), within north_star's 1e-5 relative
+        with np.errstate(invalid="ignore", divide="ignore"):
+            pg = (counts[i][:, :4] + counts[i][:, 4:5] / 4) / counts[i].sum(axis=1, keepdims=True)
+        assert np.allclose(pg, o2["probs"][case.D:case.D + be, :4], rtol=1e-5, atol=0, equal_nan=True)
 
 
 def test_more_ranks_than_records(built):
@@ -77,6 +81,8 @@ def test_more_ranks_than_records(built):
     g["recs"] = g["recs"][:2]
     liks, results, _ = _shard_run(case, [g], 3)
     orc = O.fill_gap(case.oracle_model(), g["window"], case.D, g["orig"], g["recs"])
+    sh = O.fill_gap(case.oracle_model(), g["window"], case.D, g["orig"], g["recs"], shards=3)
+    assert np.array_equal(liks[0][0], sh["liks"])
     assert np.allclose(liks[0][0], orc["liks"], rtol=REL, atol=0)
     assert results[0]["filled"] == orc["filled"] and results[0]["best_estimate"] == orc["best_estimate"]
 
