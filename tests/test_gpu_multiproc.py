@@ -23,6 +23,7 @@ def _worker(rank, world, port, exchange, q):
         import torch
         import torch.distributed as dist
         import golden_lib as G
+        import oracle_lib as O
         from gapprober_b200 import FigbirdContext, multigpu
         ndev = torch.cuda.device_count()
         dev = rank if ndev >= world else 0
@@ -42,6 +43,10 @@ def _worker(rank, world, port, exchange, q):
                 ok, why = False, f"gap {gi}: filled sequence differs"
             if not np.allclose(liks[gi], g["liks"], rtol=1e-9, atol=0):
                 ok, why = False, f"gap {gi}: likelihoods differ"
+            if rank == 0:     # the rank-ordered grouping, bit for bit (the oracle restates it)
+                sh = O.fill_gap(case.oracle_model(), g["window"], case.D, g["orig"], g["recs"], shards=world)
+                if not np.array_equal(liks[gi], sh["liks"]) or merged[gi]["filled"] != sh["filled"]:
+                    ok, why = False, f"gap {gi}: differs from the sharded oracle"
         # every rank must hold the same likelihood bits (the rank-ordered sum is the same computation everywhere)
         allv = [None] * world
         dist.all_gather_object(allv, [x.tobytes() for x in liks])
