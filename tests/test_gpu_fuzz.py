@@ -27,7 +27,8 @@ def _draw(seed):
     return args
 
 
-@pytest.mark.parametrize("seed", range(8))
+# FB_FUZZ_CASES=<n> widens the sweep (the default 8 keep the suite short)
+@pytest.mark.parametrize("seed", range(int(os.environ.get("FB_FUZZ_CASES", "8"))))
 def test_random_case_matches_reference(seed, built, tmp_path):
     if not refrun.have_ref():
         pytest.skip("oracle/_ref binaries not built")
