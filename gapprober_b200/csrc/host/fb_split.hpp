@@ -69,6 +69,7 @@ struct SplitShared {
     int max_distance = 200;                              // main.cpp:80
     const std::vector<SplitGap>* gaps = nullptr;         // the workers read the positions only
     const std::unordered_map<std::string, long>* name_to_no = nullptr;
+    const std::vector<std::pair<int, int>>* gaps_of_contig = nullptr;   // [contig] -> index range of its gaps (they are consecutive)
     bool want_myout = false, want_single = false, want_linking = false, want_unmapped = false, keep_text = false;
 };
 
@@ -307,8 +308,11 @@ private:
 
     int check_pos(long contig_no, long pos, int strand) const {   // main.cpp:197-219: first gap whose window holds the anchor
         const std::vector<SplitGap>& gaps = *sh_.gaps;
-        for (size_t i = 0; i < gaps.size(); i++) {
-            const SplitGap& g = gaps[i];
+        // the reference walks all gaps and skips those of other scaffolds; a scaffold's gaps are consecutive, so walk only them
+        if (contig_no < 0 || contig_no >= (long)sh_.gaps_of_contig->size()) return -1;
+        const std::pair<int, int> range = (*sh_.gaps_of_contig)[(size_t)contig_no];
+        for (int i = range.first; i < range.second; i++) {
+            const SplitGap& g = gaps[(size_t)i];
             if (contig_no != g.contig_no) continue;
             const long gs = g.start, ge = g.start + g.length;
             if ((strand == 0 && pos > gs - sh_.max_distance && pos < ge) || (strand == 1 && pos > ge && pos < ge + sh_.max_distance)) return (int)i;
@@ -450,6 +454,12 @@ public:
             }
         }
         for (size_t c = 0; c < sc.names.size() && c < sc.seqs.size(); c++) name_to_no_.emplace(sc.names[c], (long)c);   // first wins, like the hash chain
+        gaps_of_contig_.assign(sc.seqs.size(), std::make_pair(0, 0));
+        for (size_t i = 0; i < gaps.size(); i++) {            // contig numbers never decrease along the vector
+            std::pair<int, int>& r = gaps_of_contig_[(size_t)gaps[i].contig_no];
+            if (r.second == 0) r.first = (int)i;
+            r.second = (int)i + 1;
+        }
         contig_read_counts.assign(sc.seqs.size(), 0.0);
         read_counts.assign(sc.seqs.size(), std::vector<int>(sc.seqs.size(), 0));
     }
@@ -472,6 +482,7 @@ public:
         sh.max_distance = max_distance;
         sh.gaps = &gaps;
         sh.name_to_no = &name_to_no_;
+        sh.gaps_of_contig = &gaps_of_contig_;
         sh.want_myout = myout != nullptr || myout_text != nullptr;
         sh.want_single = single != nullptr;
         sh.want_linking = linking != nullptr;
@@ -644,6 +655,7 @@ private:
 
     const Scaffolds& sc_;
     std::unordered_map<std::string, long> name_to_no_;
+    std::vector<std::pair<int, int>> gaps_of_contig_;
 };
 
 }  // namespace fbhost
