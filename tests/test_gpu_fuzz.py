@@ -49,3 +49,40 @@ def test_random_case_matches_reference(seed, built, tmp_path):
             assert np.array_equal(gf.estimateLikelihoods(), want), (args, gi)
             assert r["best_estimate"] == d["best"][0] and gf.bestString().decode() == d["best"][2], (args, gi)
             assert r["filled"].decode() == ref["gapout"][gi]["filled"], (args, gi)
+
+
+def _draw_long(seed):
+    r = np.random.default_rng(7000 + seed)
+    mean, sd = [(180, 20), (300, 30), (500, 50), (420, 12)][int(r.integers(0, 4))]
+    gaps = [int(r.integers(600, 4000)) for _ in range(int(r.integers(1, 3)))]
+    return ["--genome", str(int(r.integers(40, 70)) * 1000), "--gap-list", ",".join(map(str, gaps)), "--cov", str(int(r.integers(5, 22))),
+            "--ins-mean", str(mean), "--ins-sd", str(sd), "--read-len", str(int(r.choice([76, 100]))),
+            "--err", f"{float(r.choice([0, 0.01])):g}", "--multihit", str(int(r.choice([1, 1, 3])))]
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("FB_FUZZ_LONG_CASES", "4"))))
+def test_random_long_gap_matches_oracle(seed, built, tmp_path):
+    """Long gaps (600 - 4 000 bp): the kernel variants that only they reach — 1024-thread CTAs, tables without the rows
+    no placement touches, global-memory tables — against the oracle (pinned to the reference by the golden fixtures;
+    the reference binary itself needs minutes per case here), profile dump of the winning estimate included."""
+    import oracle_lib as O
+    from gapprober_b200 import FigbirdContext, FigbirdModel, build, synth
+    wd = str(tmp_path / f"long{seed}")
+    args = _draw_long(seed)
+    synth.generate(wd, args, seed=900 + seed)
+    model = FigbirdModel.load(build.learn_model(wd))
+    omodel = O.Model.load(os.path.join(wd, "fb_model.bin"))
+    _, seqs = O.read_fasta(os.path.join(wd, "scaffolds.fa"))
+    with FigbirdContext(model) as fb:
+        gfs = fb.add_workdir(wd)
+        fb.fillGaps()
+        for gi, (c, s, l) in enumerate(O.read_gap_info(os.path.join(wd, "gapInfo.txt"))):
+            recs = O.read_gap_file(os.path.join(wd, "Gaps", f"gaps_{gi}.sam"))
+            r = gfs[gi].result()
+            orc = O.fill_gap(omodel, seqs[c], s, l, recs, dump_estimate=0)
+            assert np.array_equal(gfs[gi].estimateLikelihoods(), orc["liks"]), (args, gi)
+            assert (r["best_estimate"], r["filled"]) == (orc["best_estimate"], orc["filled"]), (args, gi)
+            assert (r["total_reads"], r["discarded"]) == (orc["total_reads"], orc["discarded"]), (args, gi)
+            o2 = O.fill_gap(omodel, seqs[c], s, l, recs, dump_estimate=r["best_estimate"])
+            probs, counts = gfs[gi].dumpProfile(r["best_estimate"])
+            assert np.array_equal(probs, o2["probs"], equal_nan=True) and np.array_equal(counts, o2["counts"], equal_nan=True), (args, gi)
