@@ -817,13 +817,14 @@ int fb_owns_gap(fb_ctx* c, int gap) {
     return c->gaps[gap].owned ? 1 : 0;
 }
 
-int fb_upload(fb_ctx* c) {
-    if (!c) return FB_EINVAL;
-    FB_CUDA(c, cudaSetDevice(c->device));
-    const int D = c->D, pwin = c->thr_max - c->thr_min + 1;
-    Trace tr;
-    if (tr.on) fprintf(stderr, "[fb_trace] add_gap_files: parse + pack %.3f ms, append %.3f ms\n", c->t_parse_ms, c->t_pack_ms);
-    c->t_parse_ms = c->t_pack_ms = 0;
+}  // extern "C"
+
+namespace {
+
+// fb_upload, step 1 — the work list: every (owned gap, estimate) unit, ordered for the persistent CTAs, and the size bins.
+// mp / co: doubles of per-record maxima and bytes of consensus strings the units need.
+int plan_units(fb_ctx* c, Trace& tr, long long& mp_out, long long& co_out) {
+    const int D = c->D;
     // ---- units: every (owned gap, estimate); heaviest first so persistent CTAs balance (LPT).
     // The per-gap sums are independent: computed on several host threads, merged in gap order.
     struct U { int gap, gp; double cost; long liks; int hole_lo, hole_len; int key; };
@@ -968,6 +969,13 @@ int fb_upload(fb_ctx* c) {
         bn.lmax = std::max(bn.lmax, c->gaps[u.gap].lmax);
     }
     tr.lap("upload:   unit array");
+    mp_out = mp;
+    co_out = co;
+    return FB_OK;
+}
+
+// fb_upload, step 2 — launch geometry of every bin: table strides, records per round, CTA size, cluster size, grid.
+int plan_bins(fb_ctx* c, int pwin, size_t& gws_need_out, Trace& tr) {
     // ---- shared-memory geometry per bin
     size_t gws_need = 0;
     for (Bin& b : c->bins) {
@@ -1042,6 +1050,13 @@ int fb_upload(fb_ctx* c) {
     if (tr.on)
         for (const Bin& b : c->bins) fprintf(stderr, "[fb_trace]      threads %d\n", b.threads);
     tr.lap("upload: units + bins");
+    gws_need_out = gws_need;
+    return FB_OK;
+}
+
+// fb_upload, step 3 — streams and events per bin, device buffers, host -> device copies.
+int upload_buffers(fb_ctx* c, long long mp, long long co, size_t gws_need, Trace& tr) {
+    fb_stats& st = c->stats;
     while (c->bin_done.size() < c->bins.size()) {
         cudaEvent_t a, b;
         FB_CUDA(c, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
@@ -1133,6 +1148,25 @@ int fb_upload(fb_ctx* c) {
     c->uploaded = true;
     c->ran = c->scanned = false;
     return FB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fb_upload(fb_ctx* c) {
+    if (!c) return FB_EINVAL;
+    FB_CUDA(c, cudaSetDevice(c->device));
+    const int pwin = c->thr_max - c->thr_min + 1;
+    Trace tr;
+    if (tr.on) fprintf(stderr, "[fb_trace] add_gap_files: parse + pack %.3f ms, append %.3f ms\n", c->t_parse_ms, c->t_pack_ms);
+    c->t_parse_ms = c->t_pack_ms = 0;
+    long long mp = 0, co = 0;
+    size_t gws_need = 0;
+    int rc = plan_units(c, tr, mp, co);
+    if (rc == FB_OK) rc = plan_bins(c, pwin, gws_need, tr);
+    if (rc == FB_OK) rc = upload_buffers(c, mp, co, gws_need, tr);
+    return rc;
 }
 
 }  // extern "C"
