@@ -412,6 +412,9 @@ def run_ours(a):
                                      "one gap set dealt to ranks by descending (estimates x gap-file bytes), no data-path collective"),
                        "filled_bases_total": filled_total, "host_wall_s": wall},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            # BASELINE's second metric: the reference has no convergence test, "convergence" = every (gap, estimate) unit x 5
+            # iterations + finalize of the whole gap set
+            "seconds_to_em_convergence": {"device_resident": dev_seconds / a.steps, "end_to_end": e2e_seconds / a.steps},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
