@@ -1292,16 +1292,22 @@ int fb_run_scan(fb_ctx* c) {
     for (size_t bi = 0; bi < c->bins.size(); bi++) {
         const Bin& b = c->bins[bi];
         FB_CUDA(c, cudaEventSynchronize(c->bin_copied[bi]));
-        for (int k = 0; k < b.n_units; k++) {
-            const FbUnit& u = c->h_units[b.first_unit + k];
-            HostGap& g = c->gaps[u.gap];
-            const double* mp = c->h_maxprob.p + u.mp_off;
-            double lik = 0;
-            for (int r = 0; r < g.nrec; r++)
-                if (mp[r] > 0) lik += log(mp[r]);
-            g.liks[u.gp - g.gmin] = lik;
-            g.cons_off[u.gp - g.gmin] = u.cons_off;
-        }
+        // units are independent (each writes its own slot of its gap's arrays); a unit's sum keeps the record order.
+        // Blocks of units on the host threads: a big gap set has millions of log() calls per bin.
+        const int per = 512, nblock = (b.n_units + per - 1) / per;
+        parallel_for(nblock, 0, [&](int blk) {
+            const int k1 = std::min(b.n_units, (blk + 1) * per);
+            for (int k = blk * per; k < k1; k++) {
+                const FbUnit& u = c->h_units[b.first_unit + k];
+                HostGap& g = c->gaps[u.gap];
+                const double* mp = c->h_maxprob.p + u.mp_off;
+                double lik = 0;
+                for (int r = 0; r < g.nrec; r++)
+                    if (mp[r] > 0) lik += log(mp[r]);
+                g.liks[u.gp - g.gmin] = lik;
+                g.cons_off[u.gp - g.gmin] = u.cons_off;
+            }
+        });
     }
     FB_CUDA(c, cudaStreamSynchronize(c->stream));
     tr.lap("run: EM + host log sums");
