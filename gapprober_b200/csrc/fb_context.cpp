@@ -194,6 +194,7 @@ struct fb_ctx {
     DevBuf<int> d_unit_nrec, d_shard_err;
     DevBuf<unsigned long long> d_flags;   // device-side barrier of the record-sharded scan: one word per rank, written by the peers
     unsigned long long shard_epoch = 0;   // passes run with the device-side barrier (the same on every rank)
+    bool shard_poisoned = false;          // a barrier failed: flags hold FB_FLAG_POISON until the next upload resets them
     DevBuf<int> d_counters;
     DevBuf<double> d_maxprob, d_gws, d_finprob, d_dump;
     DevBuf<char> d_cons;
@@ -990,7 +991,14 @@ int plan_bins(fb_ctx* c, int pwin, size_t& gws_need_out, Trace& tr) {
         // tuning knob: records per pipeline round (the M-step sets up one record per lane, so at most 32)
         const int pref = getenv("FB_CHUNK") ? std::max(1, std::min(32, atoi(getenv("FB_CHUNK")))) : 16;
         for (int want : {pref, 8, 4}) {
-            if (want >= 1 && fb_em_smem_bytes(b.nr_stride, b.gp_stride, b.p_stride, want, pwin, false) <= two_cta) { b.chunk = want; break; }
+            if (want < 1) continue;
+            const size_t need = fb_em_smem_bytes(b.nr_stride, b.gp_stride, b.p_stride, want, pwin, false);
+            if (need > two_cta) continue;
+            // the estimate above leaves 512 B for the kernel's static shared memory; ask the runtime whether two CTAs
+            // of this size really are co-resident before planning a grid of 2 x SMs
+            int fit = 0;
+            if (fb_em_ctas_per_sm(FB_THREADS, false, need, &fit) != cudaSuccess) { cudaGetLastError(); fit = 0; }
+            if (fit >= 2) { b.chunk = want; break; }
         }
         if (!b.chunk) {
             ctas = 1;
@@ -1130,11 +1138,14 @@ int upload_buffers(fb_ctx* c, long long mp, long long co, size_t gws_need, Trace
         FB_CUDA(c, c->d_parts[1].ensure(c->shard_counts));
         FB_CUDA(c, c->d_sumcounts.ensure(c->shard_counts));
         FB_CUDA(c, c->d_maxmerge.ensure(c->shard_maxprob));
-        if (!c->d_flags.p) {     // allocated and zeroed once: the tokens the peers write only ever grow
+        if (!c->d_flags.p || c->shard_poisoned) {     // allocated and zeroed once: the tokens the peers write only ever grow
+            // (after a failed barrier every rank uploads again, which starts flags, error word and epoch afresh)
             FB_CUDA(c, c->d_flags.ensure(FB_MAX_SHARDS));
             FB_CUDA(c, c->d_shard_err.ensure(1));
             FB_CUDA(c, cudaMemset(c->d_flags.p, 0, sizeof(unsigned long long) * FB_MAX_SHARDS));
             FB_CUDA(c, cudaMemset(c->d_shard_err.p, 0, sizeof(int)));
+            c->shard_epoch = 0;
+            c->shard_poisoned = false;
         }
         FB_CUDA(c, cudaMemcpyAsync(c->d_gapmeta_scan.p, gm_scan.data(), ng * sizeof(FbGapMeta), cudaMemcpyHostToDevice, c->stream));
         FB_CUDA(c, cudaMemcpyAsync(c->d_units_scan.p, u_scan.data(), u_scan.size() * sizeof(FbUnit), cudaMemcpyHostToDevice, c->stream));
@@ -1506,6 +1517,7 @@ int shard_enqueue_iter(fb_ctx* c, int it, const double* const* peer_counts, doub
             p.parts_in[q] = peer_counts[q];
         }
         p.part_out = out_counts;
+        p.abort = c->d_shard_err.p;
         cudaStream_t bs = c->bin_streams[bi];
         FB_CUDA(c, cudaStreamWaitEvent(bs, c->ev0, 0));
         FB_CUDA(c, launch_bin(b, p, bs));
@@ -1532,6 +1544,7 @@ int shard_finish(fb_ctx* c, const double* const* peer_counts, const double* cons
     f.sum_counts = c->d_sumcounts.p;
     f.maxprob_out = c->d_maxmerge.p;
     f.unit_cons = c->d_cons.p;
+    f.abort = c->d_shard_err.p;
     FB_CUDA(c, fb_launch_shard_finish(f, c->stream));
     c->stats.aux_launches++;
     FB_CUDA(c, cudaMemcpyAsync(c->h_maxprob.p, c->d_maxmerge.p, c->shard_maxprob * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -1609,6 +1622,16 @@ int fb_shard_scan_all(fb_ctx* c, const double* const* peer_counts0, const double
     fp.rank = rank;
     fp.world = world;
     fp.error = c->d_shard_err.p;
+    {
+        // a wait gives up after FB_BARRIER_TIMEOUT_MS of SM clock (default 20 s: first-call module loads and an
+        // imbalanced rank stay far below it)
+        const char* tm = getenv("FB_BARRIER_TIMEOUT_MS");
+        const double ms = tm ? std::max(1.0, atof(tm)) : 20000.0;
+        int khz = 1965000;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device);
+        fp.timeout_cycles = (long long)(ms * (double)khz);
+    }
+    if (c->shard_poisoned) return c->fail(FB_ESTATE, "a barrier of an earlier record-sharded scan failed: upload again on every rank");
     const unsigned long long stride = (unsigned long long)niter + 2;
     const unsigned long long epoch = ++c->shard_epoch, base = epoch * stride;
     auto wait_for = [&](unsigned long long token) {
@@ -1640,13 +1663,27 @@ int fb_shard_scan_all(fb_ctx* c, const double* const* peer_counts0, const double
     FB_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     FB_CUDA(c, cudaStreamSynchronize(c->stream));
     if (err) {
-        cudaMemset(c->d_shard_err.p, 0, sizeof(int));
-        return c->fail(FB_ECUDA, "record-sharded scan: a peer did not reach the barrier in time");
+        // the flags of this pass are poisoned on every rank that waited on this one (and the other way round): the
+        // results of the pass are void everywhere; the next fb_upload starts the tokens afresh
+        c->shard_poisoned = true;
+        return c->fail(FB_ECUDA, "record-sharded scan: a rank did not reach a barrier in time (the pass is void on every rank)");
     }
     float ms = 0;
     cudaEventElapsedTime(&ms, c->evs, c->ev1);
     c->stats.em_kernel_ms = ms;            // the whole device-side sequence, barriers included
     shard_host_liks(c);
+    return FB_OK;
+}
+
+int fb_shard_reset(fb_ctx* c) {
+    if (!c) return FB_EINVAL;
+    if (!c->d_flags.p) return FB_OK;
+    FB_CUDA(c, cudaSetDevice(c->device));
+    FB_CUDA(c, cudaDeviceSynchronize());
+    FB_CUDA(c, cudaMemset(c->d_flags.p, 0, sizeof(unsigned long long) * FB_MAX_SHARDS));
+    FB_CUDA(c, cudaMemset(c->d_shard_err.p, 0, sizeof(int)));
+    c->shard_epoch = 0;
+    c->shard_poisoned = false;
     return FB_OK;
 }
 

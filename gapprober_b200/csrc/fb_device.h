@@ -77,6 +77,7 @@ struct FbEmParams {
     const double* parts_in[FB_MAX_SHARDS];   // last iteration's partial counts of every rank (own, peer-mapped or gathered)
     int n_parts;                             // 0: first iteration, start from initialize()
     double* part_out;                        // this rank's partial counts of this iteration (nullptr: not sharded)
+    const int* abort;                        // record-sharded scan: non-zero once a barrier has failed -> the launch does nothing
 };
 
 struct FbStageParams {
@@ -102,6 +103,7 @@ struct FbShardFinParams {
     double* sum_counts;                      // same layout as the partial counts
     double* maxprob_out;
     char* unit_cons;
+    const int* abort;                        // non-zero once a barrier of this pass has failed: skip the reduction
 };
 
 struct FbFinParams {
@@ -126,6 +128,7 @@ struct FbFinParams {
 
 size_t fb_em_smem_bytes(int nr_stride, int gp_stride, int p_stride, int chunk, int pwin, bool global_tables);
 cudaError_t fb_launch_em(const FbEmParams& p, int grid, int threads, bool global_tables, size_t smem, cudaStream_t s);   // threads: 512 or 1024
+cudaError_t fb_em_ctas_per_sm(int threads, bool global_tables, size_t smem, int* n);   // occupancy of the plain variant, static smem included
 // cluster variant: n_clusters thread-block clusters of `cluster` CTAs, each cluster running one unit at a time
 cudaError_t fb_launch_em_cluster(const FbEmParams& p, int n_clusters, int cluster, size_t smem, cudaStream_t s);
 cudaError_t fb_em_max_clusters(int cluster, size_t smem, int* n);     // co-resident clusters of that size on this device
@@ -136,9 +139,11 @@ struct FbFlagParams {
     unsigned long long* peer_flags[FB_MAX_SHARDS];   // signal: every rank's flag array (own included)
     const unsigned long long* own_flags;             // wait: this rank's array, written by the peers
     unsigned long long token;
+    long long timeout_cycles;                        // wait: give up after this many SM clock cycles
     int rank, world;
-    int* error;                                      // wait: set to 1 when a peer did not arrive in time
+    int* error;                                      // set to 1 when a peer did not arrive in time, or reported that one did not
 };
+#define FB_FLAG_POISON (~0ull)                       // stored instead of a token by a rank whose pass has failed
 cudaError_t fb_launch_flag_signal(const FbFlagParams& p, cudaStream_t s);
 cudaError_t fb_launch_flag_wait(const FbFlagParams& p, cudaStream_t s);
 cudaError_t fb_launch_stage(const FbStageParams& p, cudaStream_t s);

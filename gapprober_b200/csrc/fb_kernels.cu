@@ -313,6 +313,7 @@ __global__ void __launch_bounds__(256) fb_stage_kernel(const FbStageParams p) {
 template <bool GT, bool CLU, int NT>
 __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(const __grid_constant__ FbEmParams p) {
     static_assert(!(GT && CLU), "the cluster variant keeps its tables in shared memory");
+    if (p.abort && *reinterpret_cast<const volatile int*>(p.abort)) return;   // a barrier of this record-sharded pass has failed
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned crank = 0, csize = 1;
     if (CLU) {
@@ -400,7 +401,7 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
             int b = 4;
             if (x < D) b = fl[x];
             else if (x >= D + gp) b = fl[D + (x - D - gp)];
-            if (p.n_parts && b == 4) {
+            if (p.n_parts && x >= D && x < D + gp) {   // gap rows only: a flank row with a non-ACGT base keeps sRow[4]
                 // record-sharded scan, iteration > 0: the counts of this gap row are the sum of every rank's partial
                 // counts of the previous iteration, always added in rank order
                 const size_t o = 5 * (size_t)unit.cons_off + (x - D);
@@ -742,6 +743,7 @@ __global__ void __launch_bounds__(FB_FIN_THREADS) fb_finalize_kernel(const FbFin
 // (the same order the next iteration would have used), computeSequence(0) on the sum (figbird.cpp:1991-2004); thread
 // per record: the owner's per-record maximum (every other rank holds 0 there).
 __global__ void __launch_bounds__(256) fb_shard_finish_kernel(const FbShardFinParams p) {
+    if (p.abort && *reinterpret_cast<const volatile int*>(p.abort)) return;
     for (int ui = blockIdx.x; ui < p.n_units; ui += gridDim.x) {
         const FbUnit unit = p.units[ui];
         const int gp = unit.gp;
@@ -774,28 +776,40 @@ __global__ void __launch_bounds__(256) fb_shard_finish_kernel(const FbShardFinPa
 
 // Device-side barrier of the record-sharded scan.  Every rank owns an array of flags in its exchange memory; the peers
 // store into it over NVLink.  signal: after this rank's launches of a phase (stream order), tell every peer; wait: hold
-// the stream until every rank has reached `want`.  Tokens only grow.  A wait gives up after ~10^10 cycles and raises the
-// error word instead of hanging the GPU.
+// the stream until every rank has reached `want`.  Tokens only grow.  A wait gives up after ~10^10 cycles; it then
+// raises this rank's error word AND stores FB_FLAG_POISON into its slot of every peer's array, so that no peer goes on
+// to add up this rank's stale partial counts: a wait that reads the poison raises its own error word and passes it on.
+// Once the error word is set the EM launches and the closing reduction that follow in the stream return at once, and
+// every later signal of the pass carries the poison instead of its token.
+__device__ __forceinline__ void flag_store(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 __global__ void fb_flag_signal_kernel(FbFlagParams p) {
     const int q = threadIdx.x;
     if (q >= p.world) return;
     __threadfence_system();          // the partial counts written by the preceding kernels are visible before the flag
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.peer_flags[q] + p.rank), "l"(p.token) : "memory");
+    const bool failed = *reinterpret_cast<volatile int*>(p.error) != 0;
+    flag_store(p.peer_flags[q] + p.rank, failed ? FB_FLAG_POISON : p.token);
 }
 
 __global__ void fb_flag_wait_kernel(FbFlagParams p) {
     const int q = threadIdx.x;
     if (q >= p.world) return;
     const long long t0 = clock64();
+    bool failed = false;
     for (;;) {
         unsigned long long v;
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p.own_flags + q) : "memory");
+        if (v == FB_FLAG_POISON) { failed = true; break; }
         if (v >= p.token) break;
-        if (clock64() - t0 > 10000000000ll) {
-            atomicExch(p.error, 1);
-            break;
-        }
+        if (clock64() - t0 > p.timeout_cycles) { failed = true; break; }
         __nanosleep(200);
+    }
+    if (failed) {
+        atomicExch(p.error, 1);
+        for (int k = 0; k < p.world; k++)
+            if (k != p.rank) flag_store(p.peer_flags[k] + p.rank, FB_FLAG_POISON);
     }
 }
 
@@ -834,6 +848,17 @@ cudaError_t fb_kernels_init(int* max_smem_optin, int* sm_count) {
     e = cudaFuncSetAttribute(fb_em_kernel<true, false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, *max_smem_optin - 1024);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(fb_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, *max_smem_optin - 8192);
+}
+
+// CTAs of the plain (non-cluster) EM kernel that fit one SM with `smem` bytes of dynamic shared memory: the static
+// shared memory of the kernel and the per-CTA system reserve are the runtime's to count.
+cudaError_t fb_em_ctas_per_sm(int threads, bool global_tables, size_t smem, int* n) {
+    if (threads == 1024) {
+        if (global_tables) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, fb_em_kernel<true, false, 1024>, 1024, smem);
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, fb_em_kernel<false, false, 1024>, 1024, smem);
+    }
+    if (global_tables) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, fb_em_kernel<true, false, 512>, FB_THREADS, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, fb_em_kernel<false, false, 512>, FB_THREADS, smem);
 }
 
 cudaError_t fb_launch_em(const FbEmParams& p, int grid, int threads, bool global_tables, size_t smem, cudaStream_t s) {

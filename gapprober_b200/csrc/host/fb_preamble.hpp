@@ -246,7 +246,8 @@ private:
 
     // Cut the text into about `parts` ranges.  cut1: at line starts (pass 1).  cut2: at the start of a line PAIR whose
     // names differ from the pair before it, so that no multi-hit group of pass 2 straddles a cut.  Refuses (leaves the
-    // cuts empty -> single range) when the text has '@' lines or lines the reference's 1023-byte fgets would split.
+    // cuts empty -> single range) when the text has '@' lines, lines the reference's 1023-byte fgets would split, or
+    // lines without an MD or IH tag (their values carry over from the line before, which a chunk start would lose).
     static void plan_chunks(const std::string& text, int parts, std::vector<size_t>& cut1, std::vector<size_t>& cut2) {
         const size_t n = text.size();
         const char* d = text.data();
@@ -277,6 +278,9 @@ private:
                     const char* nl = (const char*)memchr(p, '\n', (size_t)(e - p));
                     if (!nl) { bad[c] = 1; break; }
                     if (nl - p >= kMaxRecLen - 1) bad[c] = 1;
+                    // the MD and IH values are sticky across lines in the reference (locals that a line without the tag
+                    // does not reset): a chunk may only start afresh if every line carries both tags itself
+                    if (!memmem(p, (size_t)(nl - p), "\tMD", 3) || !memmem(p, (size_t)(nl - p), "\tIH", 3)) bad[c] = 1;
                     cnt++;
                     p = nl + 1;
                 }

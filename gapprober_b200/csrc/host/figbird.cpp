@@ -313,6 +313,16 @@ int main(int argc, char* argv[]) {
         std::cout << "Gap " << g << " is done." << std::endl;
     }
     fclose(gap_out);
+    {
+        // Gaps the library refused (closer than maxDistance to a scaffold end, where the reference's own arithmetic leaves
+        // its arrays — figbird.cpp:1623 vs 2149 — or mates longer than maxDistance) stay N-runs; say how many, on both streams.
+        size_t refused = 0;
+        for (size_t g = 0; g < gaps.size(); g++) refused += handle[g] < 0;
+        if (refused) {
+            std::cout << "figbird: " << refused << " of " << gaps.size() << " gaps left unfilled (outside the reference's defined territory)" << std::endl;
+            fprintf(stderr, "figbird: %zu of %zu gaps left unfilled\n", refused, gaps.size());
+        }
+    }
     for (fb_ctx* cx : ctxs) api.destroy(cx);
     time(&t1);
     std::cout << "Total time to fill gaps in seconds = " << difftime(t1, t0) << std::endl;

@@ -86,7 +86,7 @@ ABI_SYMBOLS = [
     "fb_run_device", "fb_result", "fb_estimate_liks", "fb_best_string", "fb_dump_profile", "fb_get_stats",
     "fb_clear_gaps", "fb_gap_range", "fb_last_error", "fb_status_str", "fb_abi_version",
     "fb_set_partition_records", "fb_shard_sizes", "fb_shard_buffers", "fb_shard_scan_iter", "fb_shard_scan_finish", "fb_shard_scan_all",
-    "fb_shard_counts", "fb_ipc_export", "fb_ipc_open", "fb_ipc_close",
+    "fb_shard_counts", "fb_shard_reset", "fb_ipc_export", "fb_ipc_open", "fb_ipc_close",
 ]
 
 _lib = None
@@ -143,6 +143,7 @@ def load_library():
     L.fb_shard_scan_iter.argtypes = [vp, C.c_int, dpp, vp]
     L.fb_shard_scan_finish.argtypes = [vp, dpp, dpp]
     L.fb_shard_counts.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    L.fb_shard_reset.argtypes = [vp]
     L.fb_ipc_export.argtypes = [vp, vp, C.c_char_p]
     L.fb_ipc_open.argtypes = [vp, C.c_char_p, dpp]
     L.fb_ipc_close.argtypes = [vp, vp]
@@ -455,6 +456,10 @@ class FigbirdContext:
         """One EM iteration over the local record blocks; peer_counts: device addresses of every rank's previous partial counts."""
         arr = self._ptr_array(peer_counts) if peer_counts else None
         self._check(self._L.fb_shard_scan_iter(self._h, int(it), arr, C.c_void_p(int(out_counts))))
+
+    def shardReset(self):
+        """After a failed device-side barrier: start flags, error word and pass counter afresh (call on every rank)."""
+        self._check(self._L.fb_shard_reset(self._h))
 
     def shardScanFinish(self, peer_counts, peer_maxprob):
         self._check(self._L.fb_shard_scan_finish(self._h, self._ptr_array(peer_counts), self._ptr_array(peer_maxprob)))

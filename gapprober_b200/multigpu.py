@@ -196,7 +196,22 @@ class RecordShardSession:
         import torch
         ctx = self.ctx
         if self.exchange == "p2p" and self.world > 1:
-            ctx.shardScanAll(*self.peers)
+            # A rank whose barrier wait gave up returns an error; a rank that had already finished its pass may not
+            # know yet.  The status is reduced over the ranks before anybody uses results, and a failed pass is void
+            # on every rank: flags are reset everywhere and all ranks raise.
+            failed, err = 0, None
+            try:
+                ctx.shardScanAll(*self.peers)
+            except Exception as e:       # noqa: BLE001 - the status goes through the all-reduce below
+                failed, err = 1, e
+            t = torch.tensor([failed], dtype=torch.int32, device=self._ctl_device())
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            if int(t.item()):
+                torch.cuda.synchronize(self.device)
+                self._barrier()
+                ctx.shardReset()
+                self._barrier()
+                raise RuntimeError(f"record-sharded scan failed on at least one rank (this rank: {err or 'ok'}); the pass is void")
             return
         if self.exchange in ("p2p", "p2p-host"):
             for it in range(self.num_iter):

@@ -172,6 +172,13 @@ int fb_shard_scan_finish(fb_ctx* ctx, const double* const* peer_counts, const do
  * times.  Equivalent to the fb_shard_scan_iter / barrier / fb_shard_scan_finish sequence. */
 int fb_shard_scan_all(fb_ctx* ctx, const double* const* peer_counts_slot0, const double* const* peer_counts_slot1,
                       const double* const* peer_maxprob, unsigned long long* const* peer_flags);
+/* A wait of the device-side barrier gives up after FB_BARRIER_TIMEOUT_MS (environment, default 20000) and the call
+ * returns FB_ECUDA.  The failure is passed on: the rank that gave up poisons its flag in every peer's memory, a peer
+ * that reads the poison fails the same way instead of adding up stale counts, and the launches still queued behind a
+ * failed barrier do nothing.  A rank that had already finished its pass may still return FB_OK, so callers reduce the
+ * status over the ranks before using results (RecordShardSession.scan does) and then call fb_shard_reset on EVERY rank
+ * (flags, error word and pass counter start afresh; ranks must be quiescent, e.g. between two host barriers). */
+int fb_shard_reset(fb_ctx* ctx);
 /* Parity tap: summed counts of the gap rows of one unit after fb_shard_scan_finish, laid out [estimate][5]. */
 int fb_shard_counts(fb_ctx* ctx, int gap, int estimate, double* counts);
 /* CUDA IPC plumbing for one-process-per-GPU runs: export a cudaMalloc'ed buffer as a 64-byte handle, map a peer's

@@ -103,3 +103,69 @@ def test_record_sharded_call_order(built):
             fb.shardScanIter(1, None, c1)        # iterations after the first need the peers' counts
         with pytest.raises(FigbirdError):
             fb.setPartitionRecords(0, 1000)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_flank_with_non_acgt_bases(built, world):
+    """Scaffold bases that are not ACGT right next to the gap (a neighbouring gap's N-run reaches into the flank): those
+    flank rows keep the one-hot 'N' row of initialize() in every iteration; only gap rows take the exchanged counts."""
+    case = G.Case("multi_gap_err1pct")
+    gaps = []
+    for g in case.gaps[:3]:
+        g = dict(g)
+        w = bytearray(g["window"])
+        D, orig = case.D, g["orig"]
+        for x in (D - 1, D - 7, D - 40, D + orig, D + orig + 3, D + orig + 55):
+            w[x] = ord("N")
+        g["window"] = bytes(w)
+        gaps.append(g)
+    liks, results, counts = _shard_run(case, gaps, world)
+    for i, g in enumerate(gaps):
+        sh = O.fill_gap(case.oracle_model(), g["window"], case.D, g["orig"], g["recs"], shards=world)
+        orc = O.fill_gap(case.oracle_model(), g["window"], case.D, g["orig"], g["recs"])
+        assert np.array_equal(liks[0][i], sh["liks"])
+        assert np.allclose(liks[0][i], orc["liks"], rtol=REL, atol=0)
+        assert results[i]["filled"] == sh["filled"] == orc["filled"]
+        assert results[i]["best_estimate"] == sh["best_estimate"]
+
+
+def test_failed_barrier_poisons_the_peers(built, monkeypatch):
+    """A rank whose peer never arrives gives up after FB_BARRIER_TIMEOUT_MS, reports an error, and poisons its flag in
+    the peer's memory; the peer's next pass then fails at once instead of summing stale counts.  fb_shard_reset on
+    both starts afresh."""
+    import torch
+    from gapprober_b200 import FigbirdContext, FigbirdError, multigpu
+    monkeypatch.setenv("FB_BARRIER_TIMEOUT_MS", "200")
+    case = G.Case("lib180_100bp_60x")
+    ctxs = [FigbirdContext(case.figbird_model()) for _ in range(2)]
+    try:
+        for r, fb in enumerate(ctxs):
+            _register(fb, case, case.gaps[:1])
+            fb.setPartitionRecords(r, 2)
+            fb.upload()
+        bufs = [fb.shardBuffers() for fb in ctxs]
+        peers = [[bufs[q][k] for q in range(2)] for k in range(4)]
+
+        def flags_of(r):
+            iface = {"shape": (16,), "typestr": "<i8", "data": (int(bufs[r][3]), False), "version": 3, "strides": None}
+            holder = type("F", (), {"__cuda_array_interface__": iface})()
+            return torch.as_tensor(holder, device="cuda").cpu().numpy()
+
+        with pytest.raises(FigbirdError, match="barrier"):
+            ctxs[0].shardScanAll(*peers)                     # rank 1 never runs: the wait of iteration 1 times out
+        assert flags_of(1)[0] == -1                          # rank 0's slot in rank 1's array holds the poison
+        with pytest.raises(FigbirdError):
+            ctxs[1].shardScanAll(*peers)                     # reads the poison at its first wait, no 200 ms spin per barrier
+        assert flags_of(0)[1] == -1
+        with pytest.raises(FigbirdError, match="upload again"):
+            ctxs[0].shardScanAll(*peers)
+        for fb in ctxs:
+            fb.shardReset()
+        assert not flags_of(0).any() and not flags_of(1).any()
+        # and the contexts are usable again
+        multigpu.scan_record_sharded_local(ctxs)
+        sh = O.fill_gap(case.oracle_model(), case.gaps[0]["window"], case.D, case.gaps[0]["orig"], case.gaps[0]["recs"], shards=2)
+        assert np.array_equal(ctxs[0].scanLiks(0), sh["liks"])
+    finally:
+        for fb in ctxs:
+            fb.close()

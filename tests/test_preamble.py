@@ -62,3 +62,28 @@ def test_threaded_preamble_equals_serial_and_reference(built, tmp_path):
         subprocess.run([refrun.REF_DUMP, "scaffolds.fa", " 0", "250"], cwd=wd, check=True, stdout=subprocess.DEVNULL)
         assert open(os.path.join(wd, "fb_model.bin"), "rb").read() == models["8"][0]
         assert open(os.path.join(wd, "mappedInserts.txt")).read() == models["8"][1]
+
+
+def test_lines_without_md_or_ih_tags_are_not_chunked(built, tmp_path):
+    """A line without an MD or IH tag reuses the previous line's values (sticky state, as in the reference's second pass,
+    figbird.cpp:1151, 1204).  A chunk that started at such a line would lose that state, so the threaded scan must fall
+    back to one range and give the serial model.  (No comparison with the reference here: its first pass reads
+    uninitialised stack locals for such lines, figbird.cpp:835-838, 883 — the splitter never writes them.)"""
+    from gapprober_b200 import build, synth
+    wd = str(tmp_path / "tagless")
+    synth.generate(wd, ["--genome", "400000", "--scaffolds", "2", "--gap-list", "120,300", "--cov", "45", "--ins-mean", "200", "--ins-sd", "25",
+                        "--err", "0.01"], seed=52)
+    src = open(os.path.join(wd, "myout.sam")).read().splitlines(keepends=True)
+    with open(os.path.join(wd, "myout.sam"), "w") as f:
+        for rep in range(3):
+            for k, ln in enumerate(src):
+                if k % 997 == 5:                              # replace the two trailing tag columns (MD:Z:..., IH:i:n)
+                    ln = "\t".join(ln.rstrip("\n").split("\t")[:7] + ["XX:i:0"]) + "\n"
+                f.write(ln)
+    assert os.path.getsize(os.path.join(wd, "myout.sam")) > (8 << 20)
+    models = {}
+    for threads in ("1", "8"):
+        env = dict(os.environ, FIGBIRD_PREAMBLE_ONLY="1", FIGBIRD_MODEL_OUT=f"m{threads}.bin", FIGBIRD_THREADS=threads)
+        subprocess.run([build.build_host(), "scaffolds.fa", " 0", "250"], cwd=wd, env=env, check=True, stdout=subprocess.DEVNULL)
+        models[threads] = open(os.path.join(wd, f"m{threads}.bin"), "rb").read()
+    assert models["1"] == models["8"]
