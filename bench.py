@@ -4,7 +4,9 @@
 Metric (BASELINE.json): read-placement likelihoods per second — one likelihood = one (record, placement) score
 that passes the insert-window test in one placeReads call; counted analytically, the same counter for
 the GPU and the CPU arm.  A "step" = fillGap for every gap of the workload (estimate scan x 5 EM iterations +
-finalize).  Workload at N=1: BASELINE.json configs[1] (R. sphaeroides scale, ~200 gaps, 1 % errors, 50x).
+finalize).  Workload: BASELINE.json configs[3], the one north_star's target is quoted on — human chr14 scale,
+~5 000 gaps, 40x — which fits one GPU (0.4 s per step); `--gpus N` splits that ONE gap set over the ranks by gap
+(strong scaling, no data-path collective).  `--config cfg2_rhodobacter --scaling weak` is the round-1 line.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (one process per GPU under torchrun)
   python bench.py --impl reference [--gpus N] [--steps K] ...    the unmodified reference (oracle/_ref/figbird.out)
@@ -110,13 +112,18 @@ def load_peaks():
     return {"hbm_gbs": 6650.0}, "fallback"
 
 
-def sample_gaps(wd, model, target_liks):
-    """Pick gaps (in file order) until the analytic likelihood count reaches target_liks."""
+def sample_gaps(wd, model, target_liks, seed):
+    """A seeded random subset of the gaps: gaps are drawn without replacement from
+    random.Random(seed) until the analytic likelihood count reaches target_liks."""
+    import random
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
     gaps = O.read_gap_info(os.path.join(wd, "gapInfo.txt"))
+    order = list(range(len(gaps)))
+    random.Random(seed).shuffle(order)
     picked, total = [], 0
-    for gi, (c, s, l) in enumerate(gaps):
+    for gi in order:
+        c, s, l = gaps[gi]
         recs = O.read_gap_file(os.path.join(wd, "Gaps", f"gaps_{gi}.sam"))
         a, b = O.gap_range(l)
         n = sum(O.count_likelihoods(model, s, gp, recs) for gp in range(a, b + 1)) * model.num_iter
@@ -157,14 +164,14 @@ def time_reference(dirs):
     return time.perf_counter() - t0
 
 
-def cpu_reference_rate(wd, target_liks, procs, tag, t_pre=None):
-    """likelihoods/s of the reference's own CPU EM on `procs` host cores over a bounded sample.
-    The reference's wall time includes its preamble (myout.sam scan); that part is measured with an empty
-    gapInfo.txt on the same number of concurrent processes and subtracted."""
+def cpu_reference_rate(wd, target_liks, procs, tag, seed):
+    """likelihoods/s of the reference's own CPU EM on `procs` host cores over a bounded, seeded random sample of the
+    gap set.  The reference's wall time includes its preamble (myout.sam scan); that part is measured in the same call,
+    with the same gaps emptied of records, on the same number of concurrent processes, and subtracted."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
     model = O.Model.load(os.path.join(wd, "fb_model.bin"))
-    picked, _ = sample_gaps(wd, model, target_liks * procs)
+    picked, _ = sample_gaps(wd, model, target_liks * procs, seed)
     # deal gaps to processes, heaviest first
     loads = [[0, []] for _ in range(procs)]
     for gi, n in sorted(picked, key=lambda x: -x[1]):
@@ -174,17 +181,28 @@ def cpu_reference_rate(wd, target_liks, procs, tag, t_pre=None):
     loads = [l for l in loads if l[1]]
     base = os.path.join(os.environ.get("FB_BENCH_CACHE", "/tmp"), f"fb_cpu_{tag}_{os.getpid()}")
     dirs = [make_sample_dir(wd, f"{base}_{k}", l[1]) for k, l in enumerate(loads)]
-    if t_pre is None:
-        empties = [make_sample_dir(wd, f"{base}_e{k}", l[1][:1], empty=True) for k, l in enumerate(loads)]
-        t_pre = time_reference(empties)
-        for d in empties:
-            shutil.rmtree(d, ignore_errors=True)
+    empties = [make_sample_dir(wd, f"{base}_e{k}", l[1][:1], empty=True) for k, l in enumerate(loads)]
+    t_pre = time_reference(empties)
+    for d in empties:
+        shutil.rmtree(d, ignore_errors=True)
     t_all = time_reference(dirs)
     for d in dirs:
         shutil.rmtree(d, ignore_errors=True)
     liks = sum(l[0] for l in loads)
     em_s = max(t_all - t_pre, 1e-6)
     return liks / em_s, dict(liks=liks, gaps=sum(len(l[1]) for l in loads), procs=len(loads), em_s=em_s, preamble_s=t_pre)
+
+
+def workload_config(a, n_gaps):
+    """The `config` object of the JSON line: what the workload IS.  Both arms print exactly this (the reference arm
+    times a bounded sample of it — described in its cpu_baseline.sample — and echoes how the product arm splits it)."""
+    part = {"gap": "gaps dealt to the ranks by descending cost (estimates x gap-file bytes), no data-path collective",
+            "estimate": "(gap, estimate) units dealt to the ranks; per-estimate likelihoods all-reduced (MAX) before finalize",
+            "record": "every rank scans every unit over its block of the records; partial counts exchanged every iteration"}
+    return {"workload": a.config, "seed": a.seed, "gaps": n_gaps, "scaling": a.scaling,
+            "partition": ("rank r fills the gap set of seed+r (replicas of the workload, no data-path collective)" if a.scaling == "weak"
+                          else part[a.partition]),
+            "l2": "flushed between steps (256 MiB write)"}
 
 
 def run_reference_arm(a):
@@ -196,29 +214,81 @@ def run_reference_arm(a):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/figbird.out has not been built (needs /root/reference at build time)"}))
         return
     wd = prepare_workload(a.config, a.seed)
+    n_gaps = sum(1 for ln in open(os.path.join(wd, "gapInfo.txt")) if ln.strip())
     cores = os.cpu_count() or 1
-    # bounded sample per step: ~4 s of single-core EM per process
+    # bounded sample per step: ~1-4 s of single-core EM per process, a fresh seeded random subset of the gaps every step
     per_proc = int(a.ref_liks)
-    rates, info, t_pre = [], None, None
+    rates, info = [], None
     for step in range(a.warmup + a.steps):
-        r, info = cpu_reference_rate(wd, per_proc, cores, "ref", t_pre)
-        t_pre = info["preamble_s"]
+        r, info = cpu_reference_rate(wd, per_proc, cores, "ref", a.seed * 1000 + step)
         if step >= a.warmup:
             rates.append((r, info))
     liks = sum(i["liks"] for _, i in rates)
     secs = sum(i["em_s"] for _, i in rates)
     value = liks / secs
-    sample = (f"{info['gaps']} gaps / {info['liks']} likelihoods per step on {info['procs']} processes; "
-              f"EM seconds = wall - preamble wall ({info['preamble_s']:.2f} s)")
+    sample = (f"per step a seeded random subset of the gap set (random.Random({a.seed}*1000+step)): last step {info['gaps']} of {n_gaps} gaps / "
+              f"{info['liks']} likelihoods on {info['procs']} processes of the unmodified figbird.out -O2; EM seconds = wall - preamble wall "
+              f"(measured every step with the same gaps emptied, last {info['preamble_s']:.2f} s)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": 1e3 * secs / max(1, a.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": a.config, "seed": a.seed, "note": "unmodified reference figbird.out, host CPU only"},
+        "ms_per_step": 1e3 * secs / max(1, a.steps), "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(a, n_gaps),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["procs"], "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def sha_of_fills(fills):
+    """sha256 over 'index:filled' lines in gap order — the same digest whatever rank filled which gap."""
+    import hashlib
+    h = hashlib.sha256()
+    for i in sorted(fills):
+        v = fills[i]
+        h.update(f"{i}:".encode() + (v if isinstance(v, bytes) else str(v).encode()) + b"\n")
+    return h.hexdigest()
+
+
+def multi_gpu_check(model, gaps, gap_files, seqs, rank, world, local, seed, n_pick=24):
+    """Before the timed region: one small fixed gap set filled four ways — on rank 0's GPU alone, and split over all
+    ranks by gap, by (gap, estimate) unit (NCCL all-reduce(MAX) of the likelihoods) and by record block (partial counts
+    read from the peers' memory over NVLink between iterations separated by the device-side flag barrier; NCCL
+    all-gather when IPC mapping is refused).  The four digests of the filled sequences must be equal."""
+    import random
+
+    import torch
+    import torch.distributed as dist
+    from gapprober_b200 import FigbirdContext, multigpu
+    pick = sorted(random.Random(seed).sample(range(len(gaps)), min(n_pick, len(gaps))))
+    sub = [(gaps[i][0], gaps[i][1], gaps[i][2], gap_files[i], seqs[gaps[i][0]]) for i in pick]
+    dev = torch.device("cuda", local)
+    out = {"gaps": len(sub)}
+    for mode in ("gap", "estimate", "record"):
+        try:
+            with FigbirdContext(model, device=local) as fb:
+                gfs = fb.add_gap_files(sub)
+                kw = {"device": dev}
+                res = multigpu.fill_partitioned(fb, gfs, rank, world, by=mode, **kw)
+                if mode == "record" and world > 1:
+                    out["record_exchange"] = getattr(fb, "_last_exchange", None)
+            out[mode + "_sha"] = sha_of_fills({i: r["filled"] for i, r in res.items()})
+        except Exception as e:     # the self-check must not take the bench down: report what failed
+            out[mode + "_sha"] = f"failed: {type(e).__name__}: {e}"[:200]
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier()
+    n1 = [None]
+    if rank == 0:
+        with FigbirdContext(model, device=local) as fb:
+            gfs = fb.add_gap_files(sub)
+            fb.fillGaps()
+            n1[0] = sha_of_fills({i: gf.result()["filled"] for i, gf in enumerate(gfs)})
+    if world > 1:
+        dist.broadcast_object_list(n1, src=0)
+    out["one_gpu_sha"] = n1[0]
+    out["all_equal"] = all(out[k] == n1[0] for k in ("gap_sha", "estimate_sha", "record_sha"))
+    return out
 
 
 def run_ours(a):
@@ -233,6 +303,7 @@ def run_ours(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from gapprober_b200 import FigbirdContext, FigbirdModel, read_gap_info, read_scaffolds
+    from gapprober_b200.figbird import measure_smem_peak
 
     def barrier():
         torch.cuda.synchronize()
@@ -240,8 +311,9 @@ def run_ours(a):
             dist.barrier()
 
     weak = a.scaling == "weak"
-    # weak: the gap set grows with N — rank r fills the gaps of its own copy of the workload (seed + r);
-    # strong: one gap set, dealt to the ranks by descending cost (fb_set_partition).  No data-path collective either way.
+    # strong (default): ONE gap set, dealt to the ranks by descending cost (fb_set_partition's rule on cheap proxies);
+    # weak: the gap set grows with N — rank r fills the gaps of its own copy of the workload (seed + r).
+    # No data-path collective either way.
     my_seed = a.seed + (rank if weak else 0)
     if weak or rank == 0:
         prepare_workload(a.config, my_seed)
@@ -251,6 +323,12 @@ def run_ours(a):
     _, seqs = read_scaffolds(os.path.join(wd, "scaffolds.fa"))
     gaps = read_gap_info(os.path.join(wd, "gapInfo.txt"))
     gap_files = [os.path.join(wd, "Gaps", f"gaps_{gi}.sam") for gi in range(len(gaps))]
+
+    # ---- driver-visible proof of the inter-GPU data paths, on a small fixed gap set, before anything is timed
+    check = None
+    if not a.no_check:
+        check = multi_gpu_check(model, gaps, gap_files, seqs, rank, world, local, a.seed)
+    smem_peak_gbs = measure_smem_peak(local)      # conflict-free LDS.128 on every SM, measured now on this GPU
 
     fb = FigbirdContext(model, device=local)
 
@@ -328,6 +406,14 @@ def run_ours(a):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    def allgather(x):
+        if world == 1:
+            return [x]
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [float(v.item()) for v in out]
+
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     # ---- device-resident arm -------------------------------------------------------------------------
@@ -357,8 +443,10 @@ def run_ours(a):
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
     st = fb.stats()
-    dev_seconds = allmax(step_ms / 1e3)     # CUDA-event time of the steps, max over ranks
+    rank_ms = allgather(step_ms / a.steps)          # per-rank time of a step: how even the dealing is
+    dev_seconds = max(rank_ms) * a.steps / 1e3      # CUDA-event time of the steps, max over ranks
     liks_all = allsum(float(st["likelihoods"]))
+    rank_liks = allgather(float(st["likelihoods"]))
     value = liks_all * a.steps / dev_seconds
     launches = (st["em_launches"] + st["finalize_launches"] + st["aux_launches"]) * a.steps
 
@@ -378,12 +466,17 @@ def run_ours(a):
     e2e_seconds = allmax(time.perf_counter() - t0)
     e2e_value = liks_all * a.steps / e2e_seconds
 
-    # a result checksum so the step cannot be optimised away: total filled length over owned gaps
-    filled_total = 0
-    for i, gf in enumerate(fb._gaps):
-        if not (by_estimate or by_record) or fb.hasResult(i):
-            filled_total += gf.result()["filled_len"]
-    filled_total = int(allsum(float(filled_total)))
+    # ---- the result itself: every filled sequence of the whole gap set, gathered from the ranks that own them.  The
+    # digest must not depend on N or on the partition (compare the lines of the 1/2/4/8-GPU runs).
+    from gapprober_b200.multigpu import gather_results
+    local_fill = {}
+    for k, gi in enumerate(mine):
+        if fb.hasResult(k):
+            local_fill[(rank if weak else 0, gi)] = fb._gaps[k].result()["filled"]
+    fills = gather_results(local_fill)
+    filled_total = sum(len(v) for v in fills.values())
+    digest = sha_of_fills({f"{k[0]}/{k[1]}": v for k, v in fills.items()})
+    complete = len(fills) == len(gaps) * (world if weak else 1)
 
     if rank == 0:
         peaks, peak_kind = load_peaks()
@@ -391,26 +484,29 @@ def run_ours(a):
         alg_bytes = st["algorithmic_bytes"]
         achieved = alg_bytes / em_s / 1e9
         smem_bytes = st["base_terms"] * 16
-        smem_peak = 148 * 128 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")   # dram__bytes_read+write of the EM kernel from the committed ncu capture
-        if os.path.exists(tp) and a.config == "cfg2_rhodobacter":
+        smem_theory = 148 * 128 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e9
+        n_em = max(1, st["em_launches"])
+        # dram__bytes of the EM launches from the committed ncu capture of THIS workload, used only while the launch
+        # structure is still the one that was profiled (profiles/r2_traffic.json, written by tools/ncu_summary.py)
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "r2_traffic.json")
+        if os.path.exists(tp) and world == 1:
             try:
-                traffic = json.load(open(tp))["dram_bytes_per_launch"]
+                ent = json.load(open(tp)).get(a.config)
+                if ent and ent.get("launches_per_step") == n_em:
+                    traffic, traffic_src = ent["dram_bytes_per_launch"], ent.get("source")
             except Exception:
                 traffic = None
-        n_em = max(1, st["em_launches"])
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * dev_seconds / a.steps, "higher_is_better": True, "scaling": a.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": a.config, "seed": a.seed, "gaps": len(gaps), "gaps_this_rank": len(mine), "units": st["n_units"], "records": st["n_records"],
-                       "likelihoods_per_step_this_rank": st["likelihoods"], "l2": "flushed between steps (256 MiB write)",
-                       "partition": ("rank r fills the gap set of seed+r (gap-partitioned, no data-path collective)" if weak else
-                                     "(gap, estimate) units dealt to ranks by cost; per-estimate likelihoods all-gathered before finalize" if by_estimate else
-                                     f"record-sharded: every rank scans every unit over its block of the records; partial counts exchanged every iteration ({sess[0].exchange})" if by_record else
-                                     "one gap set dealt to ranks by descending (estimates x gap-file bytes), no data-path collective"),
-                       "filled_bases_total": filled_total, "host_wall_s": wall},
+            "config": workload_config(a, len(gaps)),
+            "work": {"gaps_this_rank": len(mine), "units_this_rank": st["n_units"], "records_this_rank": st["n_records"],
+                     "likelihoods_per_step": liks_all, "likelihoods_per_step_by_rank": rank_liks,
+                     "step_ms_by_rank": rank_ms, "step_ms_min": min(rank_ms), "step_ms_max": max(rank_ms), "host_wall_s": wall},
+            "result": {"filled_sha256": digest, "gaps_filled": len(fills), "complete": complete, "filled_bases_total": filled_total},
+            "multi_gpu_check": check,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             # BASELINE's second metric: the reference has no convergence test, "convergence" = every (gap, estimate) unit x 5
             # iterations + finalize of the whole gap set
@@ -418,29 +514,30 @@ def run_ours(a):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
-                         "frac": achieved / peaks.get("hbm_gbs"), "traffic": traffic, "peak_source": peak_kind,
+                         "frac": achieved / peaks.get("hbm_gbs"), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_kind,
                          "kernel": "fb_em_kernel", "launches_per_step": n_em, "avg_launch_ms": 1e3 * em_s / n_em,
                          "algorithmic_bytes_per_launch": alg_bytes / n_em, "kernel_ms_per_step": 1e3 * em_s,
-                         "note": "achieved = SURVEY 8(d) algorithmic bytes / CUDA-event time of the EM launches; the profile and counts "
-                                 "stay in shared memory for all 5 iterations, so measured DRAM traffic is far below the algorithmic bytes and "
+                         "note": "rank 0's launches.  achieved = SURVEY 8(d) algorithmic bytes / CUDA-event time of the EM launches; the profile and "
+                                 "counts stay in shared memory for all 5 iterations, so measured DRAM traffic is far below the algorithmic bytes and "
                                  "HBM is not the binding roof (~6.5 algorithmic B per likelihood); shared-memory bandwidth is: see smem"},
             # the roof that binds: every base term of the E-step needs its own 16-byte {P,Q} pair from shared memory
             "smem": {"useful_bytes_per_step": smem_bytes, "achieved_gbs": smem_bytes / em_s / 1e9,
-                     "peak_gbs": smem_peak, "frac": smem_bytes / em_s / 1e9 / smem_peak,
-                     "peak_source": "148 SMs x 128 B/clk x max SM clock (B300_MICROARCH.md: smem crossbar 128 B/clk/SM)",
+                     "peak_gbs": smem_peak_gbs, "frac": smem_bytes / em_s / 1e9 / smem_peak_gbs,
+                     "peak_source": "measured in this run before the timed region: conflict-free LDS.128 on every SM (fb_measure_smem_peak)",
+                     "theoretical_peak_gbs": smem_theory,
                      "fp64_instr_per_step": st["base_terms"] * 5, "fp64_ginstr_s": st["base_terms"] * 5 / em_s / 1e9,
-                     "note": "useful bytes = 16 B per base term; ncu reports 80-82 % shared-memory pipe utilisation for the same launches "
-                             "(profiles/r1_ncu_full_summary.csv) — lane packing (81 %) and the M-step's reads account for the difference"},
+                     "note": "useful bytes = 16 B per base term of the E-step; lanes without a placement, the M-step's score reads and the "
+                             "staging are issued on top of that (profiles/README.md has the wavefront accounting from ncu)"},
         }
         if world == 1 and not a.no_cpu:
             try:
-                rate, info = cpu_reference_rate(wd, a.cpu_liks, 1, "cb") if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "figbird.out")) else (None, None)
+                rate, info = cpu_reference_rate(wd, a.cpu_liks, 1, "cb", a.seed) if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "figbird.out")) else (None, None)
             except Exception as e:   # the checker must not take the bench down
                 rate, info = None, {"error": str(e)}
             if rate:
                 line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "reference",
-                                        "sample": f"{info['gaps']} gaps, {info['liks']} likelihoods, unmodified figbird.out -O2, 1 thread; "
-                                                  f"EM {info['em_s']:.2f} s = wall - preamble {info['preamble_s']:.2f} s"}
+                                        "sample": f"seeded random subset: {info['gaps']} of {len(gaps)} gaps, {info['liks']} likelihoods, unmodified "
+                                                  f"figbird.out -O2, 1 thread; EM {info['em_s']:.2f} s = wall - preamble {info['preamble_s']:.2f} s"}
             else:
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": f"unavailable: {info}"}
         print(json.dumps(line))
@@ -457,12 +554,13 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="cfg2_rhodobacter")
+    ap.add_argument("--config", default="cfg4_chr14", help="a name from gapprober_b200.synth.CONFIGS (BASELINE.json configs)")
     ap.add_argument("--seed", type=int, default=2)
     ap.add_argument("--cpu-liks", type=float, default=2.0e7, help="likelihoods in the cpu_baseline sample (~15-25 s of one core)")
     ap.add_argument("--ref-liks", type=float, default=4.0e6, help="likelihoods per process per step in the reference arm")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
+    ap.add_argument("--no-check", action="store_true", help="skip the multi-GPU self-check that precedes the timed region")
     ap.add_argument("--partition", default="gap", choices=["gap", "estimate", "record"],
                     help="strong scaling only: deal gaps, (gap, estimate) units when few gaps dominate, or blocks of every gap's records "
                          "(BASELINE config 3: partial counts exchanged every EM iteration)")

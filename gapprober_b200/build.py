@@ -37,7 +37,7 @@ def _newer(target, sources):
 
 
 def build_library(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, f) for f in ("fb_kernels.cu", "fb_context.cpp")]
+    srcs = [os.path.join(CSRC, f) for f in ("fb_kernels.cu", "fb_microbench.cu", "fb_context.cpp")]
     deps = srcs + [os.path.join(CSRC, "fb_device.h"), os.path.join(ROOT, "include", "figbird_cuda.h")]
     if force or _newer(LIB, deps):
         cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", LIB] + srcs

@@ -595,7 +595,8 @@ void parallel_for(int n, int threads, F fn) {
         // one process per GPU shares the host cores with its siblings (torchrun exports LOCAL_WORLD_SIZE)
         const char* lws = getenv("LOCAL_WORLD_SIZE");
         const int procs = lws ? std::max(1, atoi(lws)) : 1;
-        threads = std::max(1, std::min((hw > 0 ? hw : 1) / procs, 16));
+        // ... but never fewer than 4 threads per rank: the host loops are short bursts that rarely coincide across ranks
+        threads = std::max(std::min(4, hw > 0 ? hw : 1), std::min((hw > 0 ? hw : 1) / procs, 16));
     }
     threads = std::min(threads, n);
     if (threads <= 1) {
@@ -1845,6 +1846,14 @@ int fb_dump_profile(fb_ctx* c, int gap, int estimate, double* probs, double* cou
         }
     }
     return c->fail(FB_EINVAL, "estimate %d is not in the scan range of gap %d (or the gap is not owned)", estimate, gap);
+}
+
+int fb_measure_smem_peak(int device, double* gbs) {
+    if (!gbs) return FB_EINVAL;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return FB_ECUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return FB_ECUDA;
+    return fb_microbench_smem(gbs, 5) == cudaSuccess ? FB_OK : FB_ECUDA;
 }
 
 int fb_get_stats(fb_ctx* c, fb_stats* out) {

@@ -149,3 +149,4 @@ cudaError_t fb_launch_flag_wait(const FbFlagParams& p, cudaStream_t s);
 cudaError_t fb_launch_stage(const FbStageParams& p, cudaStream_t s);
 cudaError_t fb_launch_shard_finish(const FbShardFinParams& p, cudaStream_t s);
 cudaError_t fb_kernels_init(int* max_smem_optin, int* sm_count);
+cudaError_t fb_microbench_smem(double* gbs, int reps);     // fb_microbench.cu: measured shared-memory read bandwidth (LDS.128, conflict-free)

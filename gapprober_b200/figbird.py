@@ -86,7 +86,7 @@ ABI_SYMBOLS = [
     "fb_run_device", "fb_result", "fb_estimate_liks", "fb_best_string", "fb_dump_profile", "fb_get_stats",
     "fb_clear_gaps", "fb_gap_range", "fb_last_error", "fb_status_str", "fb_abi_version",
     "fb_set_partition_records", "fb_shard_sizes", "fb_shard_buffers", "fb_shard_scan_iter", "fb_shard_scan_finish", "fb_shard_scan_all",
-    "fb_shard_counts", "fb_shard_reset", "fb_ipc_export", "fb_ipc_open", "fb_ipc_close",
+    "fb_shard_counts", "fb_shard_reset", "fb_measure_smem_peak", "fb_ipc_export", "fb_ipc_open", "fb_ipc_close",
 ]
 
 _lib = None
@@ -144,6 +144,7 @@ def load_library():
     L.fb_shard_scan_finish.argtypes = [vp, dpp, dpp]
     L.fb_shard_counts.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_double)]
     L.fb_shard_reset.argtypes = [vp]
+    L.fb_measure_smem_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.fb_ipc_export.argtypes = [vp, vp, C.c_char_p]
     L.fb_ipc_open.argtypes = [vp, C.c_char_p, dpp]
     L.fb_ipc_close.argtypes = [vp, vp]
@@ -160,6 +161,15 @@ def partition_plan(costs, world):
     if rc != FB_OK:
         raise FigbirdError(rc, "fb_partition_plan")
     return owner
+
+
+def measure_smem_peak(device=0):
+    """Measured shared-memory read bandwidth of the device in GB/s (conflict-free LDS.128 on every SM)."""
+    v = C.c_double()
+    rc = load_library().fb_measure_smem_peak(int(device), C.byref(v))
+    if rc != FB_OK:
+        raise FigbirdError(rc, "fb_measure_smem_peak")
+    return v.value
 
 
 def gap_range(original_gap):

@@ -39,14 +39,16 @@ def merge_liks(parts):
     return out
 
 
-def fill_partitioned(ctx, gap_fillers, rank, world, group=None, by="gap", **shard_kw):
+def fill_partitioned(ctx, gap_fillers, rank, world, group=None, by="gap", device=None, **shard_kw):
     """Partition + fill + gather: returns {gap_index: result dict} for ALL gaps on every rank.
 
     by="gap": gaps are dealt to ranks (fb_set_partition); no exchange before the final gather.
     by="estimate": (gap, estimate) units are dealt (fb_set_partition_units) — for gap sets dominated by few gaps; the
     per-estimate likelihoods (a few doubles per gap) are all-gathered between the scan and the finalize.
     by="record": every rank scans every unit over its block of each gap's records; the partial counts are exchanged
-    every EM iteration (RecordShardSession; results agree with the other two to rounding, not to the bit)."""
+    every EM iteration (RecordShardSession; results agree with the other two to rounding, not to the bit).
+    device: the rank's torch CUDA device when the process group is NCCL (control scalars and the likelihood exchange
+    then live on the GPU); None under gloo."""
     if world == 1:
         ctx.fillGaps()
         return {i: gf.result() for i, gf in enumerate(gap_fillers)}
@@ -56,15 +58,16 @@ def fill_partitioned(ctx, gap_fillers, rank, world, group=None, by="gap", **shar
         local = {i: gf.result() for i, gf in enumerate(gap_fillers) if ctx.ownsGap(i)}
         return gather_results(local, group)
     if by == "record":
-        with RecordShardSession(ctx, rank, world, group=group, **shard_kw) as sess:
+        with RecordShardSession(ctx, rank, world, group=group, device=device, **shard_kw) as sess:
             sess.scan()
+            ctx._last_exchange = sess.exchange
         ctx.runFinalize()
         local = {i: gf.result() for i, gf in enumerate(gap_fillers) if ctx.hasResult(i)}
         return gather_results(local, group)
     ctx.setPartitionUnits(rank, world)
     ctx.upload()
     ctx.runScan()
-    exchange_liks(ctx, len(gap_fillers), group)
+    exchange_liks(ctx, len(gap_fillers), group, device=device)
     ctx.runFinalize()
     local = {i: gf.result() for i, gf in enumerate(gap_fillers) if ctx.hasResult(i)}
     return gather_results(local, group)

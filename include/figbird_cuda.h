@@ -209,6 +209,9 @@ int fb_best_string(fb_ctx* ctx, int gap, char* buf, int cap);         /* bestStr
 int fb_dump_profile(fb_ctx* ctx, int gap, int estimate, double* probs, double* counts);
 
 int fb_get_stats(fb_ctx* ctx, fb_stats* out);
+/* Measurement aid (no counterpart in the reference): shared-memory read bandwidth of `device` in GB/s, measured with
+ * conflict-free 128-bit loads on every SM — the roof that binds the E-step; bench.py reports against it. */
+int fb_measure_smem_peak(int device, double* gbs);
 int fb_clear_gaps(fb_ctx* ctx);                 /* drop all gaps, keep the model */
 /* Estimate range of fillGap (figbird.cpp:2438-2453), float arithmetic included. */
 void fb_gap_range(int orig_gap, int* gap_min, int* gap_max);

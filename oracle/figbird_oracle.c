@@ -288,6 +288,11 @@ int orc_fill_gap(const orc_model* m, const char* contig, long contig_len, long g
 
 int orc_fill_gap_sharded(const orc_model* m, const char* contig, long contig_len, long gap_start, int orig_gap,
                          const orc_record* recs, int nrec, int shards, orc_result* out) {
+    return orc_fill_gap_subset(m, contig, contig_len, gap_start, orig_gap, recs, nrec, shards, NULL, out);
+}
+
+int orc_fill_gap_subset(const orc_model* m, const char* contig, long contig_len, long gap_start, int orig_gap,
+                        const orc_record* recs, int nrec, int shards, const unsigned char* scan, orc_result* out) {
     const int D = m->max_distance;
     /* Outside these bounds the reference reads past its arrays; refuse instead. */
     if (orig_gap < 1 || gap_start < D || gap_start + orig_gap + D > contig_len) return -2;
@@ -331,6 +336,10 @@ int orc_fill_gap_sharded(const orc_model* m, const char* contig, long contig_len
         int best_est = gmin;
         double best_lik = -DBL_MAX, lik = 0;
         for (int gp = gmin; gp <= gmax; gp++) {
+            if (scan && !scan[gp - gmin]) {      /* test aid: estimate left out of the scan */
+                if (out->lik_per_estimate) out->lik_per_estimate[gp - gmin] = NAN;
+                continue;
+            }
             init_profile(&g, gp);
             for (int it = 0; it < m->num_iter; it++) {
                 lik = place_reads(&g);
@@ -351,6 +360,12 @@ int orc_fill_gap_sharded(const orc_model* m, const char* contig, long contig_len
             }
         }
         if (gmax < gmin) rc = -2;
+        if (rc == 0 && scan) {
+            /* finalize sees the extent of the LAST estimate of the full scan (gapMax), whatever subset was scanned */
+            g.gap_len = gmax;
+            g.start_pos = (g.gap_start - D) < 0 ? 0 : (g.gap_start - D);
+            g.end_pos = g.gap_start + gmax + D;
+        }
         if (rc == 0) {
             if (out->best_string) strcpy(out->best_string, best);
             rc = hard_assign(&g, best_est, best, &out->total_reads, &out->discarded);

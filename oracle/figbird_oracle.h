@@ -70,6 +70,13 @@ int orc_fill_gap(const orc_model* m, const char* contig, long contig_len, long g
 int orc_fill_gap_sharded(const orc_model* m, const char* contig, long contig_len, long gap_start, int orig_gap,
                          const orc_record* recs, int nrec, int shards, orc_result* out);
 
+/* Test aid for gaps whose full scan takes minutes on one core (the single-gap stress corners): scan[gp - gap_min] == 0
+ * leaves estimate gp out of the scan (its likelihood reads NaN); the '>=' selection and finalize then run over the
+ * scanned estimates only.  scan == NULL scans everything.  Each scanned estimate is computed exactly as in the full
+ * scan (estimates are independent, figbird.cpp:2468-2501). */
+int orc_fill_gap_subset(const orc_model* m, const char* contig, long contig_len, long gap_start, int orig_gap,
+                        const orc_record* recs, int nrec, int shards, const unsigned char* scan, orc_result* out);
+
 /* Estimate range only (figbird.cpp:2438-2453), float arithmetic included. */
 void orc_gap_range(int orig_gap, int* gap_min, int* gap_max);
 

@@ -74,6 +74,9 @@ def lib():
         _lib.orc_fill_gap_sharded.restype = C.c_int
         _lib.orc_fill_gap_sharded.argtypes = [C.POINTER(OrcModel), C.c_char_p, C.c_long, C.c_long, C.c_int,
                                               C.POINTER(OrcRecord), C.c_int, C.c_int, C.POINTER(OrcResult)]
+        _lib.orc_fill_gap_subset.restype = C.c_int
+        _lib.orc_fill_gap_subset.argtypes = [C.POINTER(OrcModel), C.c_char_p, C.c_long, C.c_long, C.c_int,
+                                             C.POINTER(OrcRecord), C.c_int, C.c_int, C.c_char_p, C.POINTER(OrcResult)]
         _lib.orc_gap_range.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         _lib.orc_count_likelihoods.restype = C.c_long
         _lib.orc_count_likelihoods.argtypes = [C.POINTER(OrcModel), C.c_long, C.c_int, C.POINTER(OrcRecord), C.c_int]
@@ -142,9 +145,10 @@ def gap_range(orig):
     return a.value, b.value
 
 
-def fill_gap(model, contig, gap_start, orig_gap, recs, dump_estimate=0, shards=1):
+def fill_gap(model, contig, gap_start, orig_gap, recs, dump_estimate=0, shards=1, estimates=None):
     """Run the oracle on one gap.  contig: bytes (upper-cased scaffold).  Returns a dict.
-    shards > 1: the record-sharded grouping of the M-step sums (orc_fill_gap_sharded) instead of the reference's."""
+    shards > 1: the record-sharded grouping of the M-step sums (orc_fill_gap_sharded) instead of the reference's.
+    estimates: scan only these estimates (orc_fill_gap_subset); the others read NaN in 'liks'."""
     L = lib()
     m = model.as_orc()
     arr = (OrcRecord * max(1, len(recs)))()
@@ -170,7 +174,17 @@ def fill_gap(model, contig, gap_start, orig_gap, recs, dump_estimate=0, shards=1
         probs, counts = np.zeros(n), np.zeros(n)
         res.probs_dump = probs.ctypes.data_as(C.POINTER(C.c_double))
         res.counts_dump = counts.ctypes.data_as(C.POINTER(C.c_double))
-    rc = L.orc_fill_gap_sharded(C.byref(m), contig, len(contig), gap_start, orig_gap, arr, len(recs), int(shards), C.byref(res))
+    scan = None
+    if estimates is not None:
+        mask = bytearray(max(1, ne))
+        for e in estimates:
+            mask[int(e) - gmin] = 1
+        scan = bytes(mask)
+    rc = L.orc_fill_gap_subset(C.byref(m), contig, len(contig), gap_start, orig_gap, arr, len(recs), int(shards), scan, C.byref(res))
+    if rc == -3 and estimates is not None:
+        # finalize counted >= 10000 reads for base A at some position: the reference's checkDuplicate then indexes past
+        # its stack array (figbird.cpp:1967-1982) — undefined there, so only the scan's outputs are returned
+        return dict(undefined_finalize=True, best_string=best.value, liks=liks[:ne].copy(), filled=None)
     if rc != 0:
         raise RuntimeError(f"orc_fill_gap failed: {rc}")
     return dict(gap_min=res.gap_min, gap_max=res.gap_max, best_estimate=res.best_estimate, best_lik=res.best_lik,

@@ -35,3 +35,41 @@ def run_reference(wd, dump_probs=True, f_mode=0):
             gapout.append(dict(gap=int(p[0]), ctg=int(p[1]), start=int(p[2]), orig=int(p[3]), filled_len=int(p[4]),
                                filled=p[5] if len(p) > 5 else ""))
     return dict(model=model, dump=dump, gapout=gapout, stdout=out)
+
+
+def run_reference_on_gaps(wd, gap_ids, procs, tmp):
+    """The instrumented reference on a SUBSET of the gaps of wd, spread over `procs` concurrent processes (each gets a
+    working directory with its share of the gaps renumbered from 0 and the big inputs symlinked).  Returns
+    {gap_id: dict(est={estimate: lik}, best=(estimate, lik, bestString), filled=str)}."""
+    import shutil
+    lines = open(os.path.join(wd, "gapInfo.txt")).read().splitlines()
+    shares = [list(gap_ids[k::procs]) for k in range(procs)]
+    shares = [s for s in shares if s]
+    dirs = []
+    for k, share in enumerate(shares):
+        d = os.path.join(tmp, f"refpart{k}")
+        if os.path.isdir(d):
+            shutil.rmtree(d)
+        os.makedirs(os.path.join(d, "Gaps"))
+        for f in ("scaffolds.fa", "myout.sam", "stat.txt"):
+            os.symlink(os.path.join(wd, f), os.path.join(d, f))
+        with open(os.path.join(d, "gapInfo.txt"), "w") as f:
+            for j, gi in enumerate(share):
+                f.write(lines[gi] + "\n")
+                os.symlink(os.path.join(wd, "Gaps", f"gaps_{gi}.sam"), os.path.join(d, "Gaps", f"gaps_{j}.sam"))
+        dirs.append(d)
+    env = dict(os.environ)
+    env.pop("FB_DUMP_PROBS", None)
+    ps = [subprocess.Popen([REF_DUMP, "scaffolds.fa", " 0", "250"], cwd=d, env=env, stdout=subprocess.DEVNULL) for d in dirs]
+    for p in ps:
+        if p.wait() != 0:
+            raise RuntimeError("reference figbird_dump.out failed")
+    out = {}
+    for d, share in zip(dirs, shares):
+        dump = O.parse_dump(os.path.join(d, "fb_dump.txt"))
+        rows = open(os.path.join(d, "gapout.txt")).read().splitlines()
+        for j, gi in enumerate(share):
+            e = dump[f"Gaps/gaps_{j}.sam"]
+            p = rows[j].split("\t")
+            out[gi] = dict(est=e["est"], best=e["best"], filled=p[5] if len(p) > 5 else "")
+    return out

@@ -16,14 +16,17 @@ def test_reference_arm_json_line(built):
     if not refrun.have_ref():
         pytest.skip("oracle/_ref binaries not built")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                        "--ref-liks", "2e5"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+                        "--ref-liks", "2e5", "--config", "cfg3_staph"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-500:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "read-placement likelihoods/sec" and d["unit"] == "likelihoods/s"
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
-    assert d["config"]["workload"] == "cfg2_rhodobacter"
+    # the config object is the workload's identity, the same keys the product arm prints
+    assert d["config"]["workload"] == "cfg3_staph" and d["config"]["gaps"] == 100
+    assert set(d["config"]) == {"workload", "seed", "gaps", "scaling", "partition", "l2"}
+    assert "seeded random subset" in d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = d["cpu_baseline"]
     assert cb["kind"] == "reference" and cb["value"] == d["value"] and cb["cores"] >= 1 and cb["sample"]
@@ -33,7 +36,7 @@ def test_product_arm_needs_a_gpu(built):
     import torch
     if torch.cuda.is_available():
         pytest.skip("a GPU is visible")
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--config", "cfg3_staph"], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
                        text=True, timeout=600)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
 
@@ -49,7 +52,7 @@ def test_reference_arm_under_torchrun_prints_once(built):
     s.close()
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", str(port), os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
-                        "--warmup", "0", "--ref-liks", "2e5"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+                        "--warmup", "0", "--ref-liks", "2e5", "--config", "cfg3_staph"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-500:]
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1 and json.loads(lines[0])["impl"] == "reference" and json.loads(lines[0])["n_gpus"] == 2

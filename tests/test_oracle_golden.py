@@ -51,3 +51,18 @@ def test_oracle_refuses_undefined_territory(built):
     g = case.gaps[0]
     with pytest.raises(RuntimeError):
         O.fill_gap(case.oracle_model(), g["window"][50:], case.D - 50, g["orig"], g["recs"])   # gap closer than D to the scaffold start
+
+
+def test_estimate_subset_scan_equals_the_full_scan(built):
+    """orc_fill_gap_subset (the test aid for gaps too big to scan fully on one core): a scanned estimate has the bits
+    it has in the full scan, the others read NaN, and with the full scan's winner in the subset the fill is the same."""
+    import golden_lib as G
+    case = G.Case("multi_gap_err1pct")
+    for g in case.gaps[:3]:
+        full = O.fill_gap(case.oracle_model(), g["window"], case.D, g["orig"], g["recs"])
+        sub = sorted({full["gap_min"], full["best_estimate"], full["gap_max"]})
+        part = O.fill_gap(case.oracle_model(), g["window"], case.D, g["orig"], g["recs"], estimates=sub)
+        for e in range(full["gap_min"], full["gap_max"] + 1):
+            v = part["liks"][e - full["gap_min"]]
+            assert (v == full["liks"][e - full["gap_min"]]) if e in sub else np.isnan(v)
+        assert (part["best_estimate"], part["filled"], part["discarded"]) == (full["best_estimate"], full["filled"], full["discarded"])
