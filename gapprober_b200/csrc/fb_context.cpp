@@ -157,11 +157,15 @@ struct fb_ctx {
 
     // model (host copies)
     int max_read_len = 0, thr_min = 0, thr_max = 0, cutoff = 0, D = 200, num_iter = 5;
+    bool f1 = false;           // the reference's log-domain mode (argv[2] = 1, figbird.cpp:1814-1815)
+    double theta = 0;          // smallest double that passes finalize's cut-off test (cutoff_threshold)
+    bool host_log = false;     // FB_HOST_LOG=1: per-record maxima go home and the host libm sums their logs (the round-1 path)
     double T[25];
     std::vector<double> epos, match;
     std::vector<double2> h_eo;   // {1 - e[k], e[k]}, copied into every EM launch's parameters
     // model (device)
     DevBuf<double> d_ild, d_epos, d_match;
+    DevBuf<double> d_ild_em;   // what the E-step starts a score from: ILD[t], or log(ILD[t]) from the host libm in f=1 mode
 
     // gaps + records (host staging)
     std::vector<HostGap> gaps;
@@ -196,12 +200,16 @@ struct fb_ctx {
     unsigned long long shard_epoch = 0;   // passes run with the device-side barrier (the same on every rank)
     bool shard_poisoned = false;          // a barrier failed: flags hold FB_FLAG_POISON until the next upload resets them
     DevBuf<int> d_counters;
-    DevBuf<double> d_maxprob, d_gws, d_finprob, d_dump;
+    DevBuf<double> d_maxprob, d_gws, d_dump;
     DevBuf<char> d_cons;
-    DevBuf<int> d_finpos, d_gaplist, d_bestgp;
-    DevBuf<long long> d_bestoff;
-    PinBuf<double> h_maxprob, h_finprob;
-    PinBuf<int> h_finpos;
+    DevBuf<int> d_gaplist, d_bestgp;
+    DevBuf<long long> d_bestoff, d_filled_off;
+    DevBuf<double> d_unit_lik;
+    DevBuf<int> d_fin_counts, d_fin_counts_off, d_tickets, d_discarded;
+    DevBuf<char> d_filled;
+    PinBuf<double> h_maxprob, h_unit_lik;
+    PinBuf<int> h_discarded;
+    PinBuf<char> h_filled;
     PinBuf<unsigned char> h_stage;   // pinned staging for the host->device copies
 
     fb_stats stats;
@@ -217,6 +225,31 @@ struct fb_ctx {
         return code;
     }
 };
+
+// finalize keeps a record when -log(maxProb) <= gapProbCutOff (figbird.cpp:2293).  log() is monotone, so that is a
+// threshold on maxProb: theta = the smallest positive double that passes, found by bisection over the bit patterns with
+// the reference's own libm, then checked exhaustively for 4096 doubles either side (a libm whose log wiggled there
+// would make the threshold form wrong: refuse rather than guess).  maxProb = 0 never passes (-log(0) = inf); when no
+// double passes, theta = +inf.
+static bool cutoff_threshold(int cutoff, double* theta) {
+    auto pass = [&](double x) { return -log(x) <= cutoff; };
+    auto as_d = [](uint64_t u) { double x; memcpy(&x, &u, 8); return x; };
+    uint64_t lo = 1, hi = 0x7fefffffffffffffull;           // denorm_min .. DBL_MAX
+    if (pass(as_d(lo))) { *theta = as_d(lo); return true; }
+    if (!pass(as_d(hi))) { *theta = INFINITY; return true; }
+    while (hi - lo > 1) {                                    // invariant: !pass(lo) && pass(hi)
+        const uint64_t mid = lo + (hi - lo) / 2;
+        if (pass(as_d(mid))) hi = mid;
+        else lo = mid;
+    }
+    for (int64_t k = -4096; k <= 4096; k++) {
+        const uint64_t u = hi + (uint64_t)k;
+        if (u < 1 || u > 0x7fefffffffffffffull) continue;
+        if (pass(as_d(u)) != (u >= hi)) return false;
+    }
+    *theta = as_d(hi);
+    return true;
+}
 
 #define FB_CUDA(ctx, call)                                                                             \
     do {                                                                                               \
@@ -270,7 +303,7 @@ int fb_warmup(int device) {
 int fb_create(const fb_model* m, int device, fb_ctx** out) {
     if (!m || !out) return FB_EINVAL;
     *out = nullptr;
-    if (m->f_mode != 0) return FB_EUNSUPPORTED;
+    if (m->f_mode != 0 && m->f_mode != 1) return FB_EUNSUPPORTED;
     if (m->max_read_len < 1 || m->max_distance < 1 || m->num_iter < 1 || !m->error_pos || !m->in_pos || !m->del_pos || !m->ild)
         return FB_EINVAL;
     if (m->thr_min < 0 || m->thr_max < m->thr_min || m->thr_max >= m->ild_len) return FB_EINVAL;
@@ -311,10 +344,24 @@ int fb_create(const fb_model* m, int device, fb_ctx** out) {
         c->epos[k] = m->error_pos[k];
         c->match[k] = 1 - m->error_pos[k] - m->in_pos[k] - m->del_pos[k];           // figbird.cpp:2272
     }
+    c->f1 = m->f_mode == 1;
+    c->host_log = getenv("FB_HOST_LOG") && atoi(getenv("FB_HOST_LOG")) != 0;
+    if (!cutoff_threshold(m->gap_prob_cutoff, &c->theta)) {
+        c->err = "the host libm's log() is not monotone around exp(-gapProbCutOff): cannot turn the cut-off test into a threshold";
+        fprintf(stderr, "figbird_cuda: %s\n", c->err.c_str());
+        return bail(FB_EUNSUPPORTED);
+    }
     const int pwin = m->thr_max - m->thr_min + 1;
-    if (c->d_ild.ensure(pwin) || c->d_epos.ensure(FB_MAX_READ) || c->d_match.ensure(FB_MAX_READ))
+    if (c->d_ild.ensure(pwin) || c->d_ild_em.ensure(pwin) || c->d_epos.ensure(FB_MAX_READ) || c->d_match.ensure(FB_MAX_READ))
         return bail(FB_ECUDA);
     cudaMemcpy(c->d_ild.p, m->ild + m->thr_min, sizeof(double) * pwin, cudaMemcpyHostToDevice);
+    {
+        // f=1: tempProb starts from log(ILD[t]) (figbird.cpp:1835): taken with the host libm, once per t
+        std::vector<double> start(m->ild + m->thr_min, m->ild + m->thr_min + pwin);
+        if (c->f1)
+            for (double& v : start) v = log(v);
+        cudaMemcpy(c->d_ild_em.p, start.data(), sizeof(double) * pwin, cudaMemcpyHostToDevice);
+    }
     cudaMemcpy(c->d_epos.p, c->epos.data(), sizeof(double) * FB_MAX_READ, cudaMemcpyHostToDevice);
     cudaMemcpy(c->d_match.p, c->match.data(), sizeof(double) * FB_MAX_READ, cudaMemcpyHostToDevice);
     if (cudaDeviceSynchronize() != cudaSuccess) return bail(FB_ECUDA);
@@ -327,13 +374,15 @@ void fb_destroy(fb_ctx* c) {
     cudaSetDevice(c->device);
     c->d_ild.release(); c->d_epos.release(); c->d_match.release();
     c->d_gapmeta.release(); c->d_flank.release(); c->d_codes.release(); c->d_nmask.release(); c->d_rmeta.release();
-    c->d_units.release(); c->d_counters.release(); c->d_maxprob.release(); c->d_gws.release(); c->d_finprob.release();
-    c->d_dump.release(); c->d_cons.release(); c->d_finpos.release(); c->d_gaplist.release(); c->d_bestgp.release();
+    c->d_units.release(); c->d_counters.release(); c->d_maxprob.release(); c->d_gws.release();
+    c->d_dump.release(); c->d_cons.release(); c->d_gaplist.release(); c->d_bestgp.release();
     c->d_bestoff.release();
     c->d_st_mask.release(); c->d_st_cls4.release(); c->d_st_jl.release(); c->d_st_cum.release();
     c->d_units_scan.release(); c->d_gapmeta_scan.release(); c->d_parts[0].release(); c->d_parts[1].release();
     c->d_sumcounts.release(); c->d_maxmerge.release(); c->d_unit_nrec.release(); c->d_shard_err.release(); c->d_flags.release();
-    c->h_maxprob.release(); c->h_finprob.release(); c->h_finpos.release(); c->h_stage.release();
+    c->h_maxprob.release(); c->h_stage.release();
+    c->d_ild_em.release(); c->d_filled_off.release(); c->d_unit_lik.release(); c->d_fin_counts.release(); c->d_fin_counts_off.release();
+    c->d_tickets.release(); c->d_discarded.release(); c->d_filled.release(); c->h_unit_lik.release(); c->h_discarded.release(); c->h_filled.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev2) cudaEventDestroy(c->ev2);
@@ -797,6 +846,7 @@ int fb_set_partition_units(fb_ctx* c, int rank, int world) {
 
 int fb_set_partition_records(fb_ctx* c, int rank, int world) {
     if (!c || world < 1 || world > FB_MAX_SHARDS || rank < 0 || rank >= world) return FB_EINVAL;
+    if (c->f1) return c->fail(FB_EUNSUPPORTED, "the record-sharded scan runs f=0 only (gap and estimate partitions run both modes)");
     c->part_rank = rank;
     c->part_world = world;
     c->unit_mode = false;
@@ -998,7 +1048,7 @@ int plan_bins(fb_ctx* c, int pwin, size_t& gws_need_out, Trace& tr) {
             // the estimate above leaves 512 B for the kernel's static shared memory; ask the runtime whether two CTAs
             // of this size really are co-resident before planning a grid of 2 x SMs
             int fit = 0;
-            if (fb_em_ctas_per_sm(FB_THREADS, false, need, &fit) != cudaSuccess) { cudaGetLastError(); fit = 0; }
+            if (fb_em_ctas_per_sm(FB_THREADS, false, c->f1, need, &fit) != cudaSuccess) { cudaGetLastError(); fit = 0; }
             if (fit >= 2) { b.chunk = want; break; }
         }
         if (!b.chunk) {
@@ -1043,7 +1093,7 @@ int plan_bins(fb_ctx* c, int pwin, size_t& gws_need_out, Trace& tr) {
             if (b.global_tables) continue;
             for (int cl = want; cl > 1; cl >>= 1) {
                 int fit = 0;
-                if (fb_em_max_clusters(cl, b.smem, &fit) == cudaSuccess && fit > 0) {
+                if (fb_em_max_clusters(cl, c->f1, b.smem, &fit) == cudaSuccess && fit > 0) {
                     b.cluster = cl;
                     b.grid = std::min(b.n_units, fit);
                     break;
@@ -1091,15 +1141,23 @@ int upload_buffers(fb_ctx* c, long long mp, long long co, size_t gws_need, Trace
     FB_CUDA(c, c->d_counters.ensure(c->bins.size() + 1));
     FB_CUDA(c, c->d_maxprob.ensure((size_t)mp));
     FB_CUDA(c, c->d_cons.ensure((size_t)co));
-    FB_CUDA(c, c->d_finprob.ensure(nr));
-    FB_CUDA(c, c->d_finpos.ensure(nr));
     FB_CUDA(c, c->d_gaplist.ensure(ng));
     FB_CUDA(c, c->d_bestgp.ensure(ng));
     FB_CUDA(c, c->d_bestoff.ensure(ng));
+    FB_CUDA(c, c->d_filled_off.ensure(ng));
+    FB_CUDA(c, c->d_fin_counts_off.ensure(ng));
+    FB_CUDA(c, c->d_tickets.ensure(2 * ng));          // tickets[ng] + discarded[ng], zeroed together
+    FB_CUDA(c, c->h_discarded.ensure(ng));
+    FB_CUDA(c, c->d_unit_lik.ensure(c->h_units.size()));
+    FB_CUDA(c, c->h_unit_lik.ensure(c->h_units.size()));
+    {
+        size_t fill_cap = 0;                             // the filled sequences of all gaps, at most gmax bases each
+        for (const HostGap& g : c->gaps) fill_cap += (size_t)std::max(g.gmax, 1);
+        FB_CUDA(c, c->d_filled.ensure(fill_cap));
+        FB_CUDA(c, c->h_filled.ensure(fill_cap));
+    }
     if (gws_need) FB_CUDA(c, c->d_gws.ensure(gws_need));
-    FB_CUDA(c, c->h_maxprob.ensure((size_t)mp));
-    FB_CUDA(c, c->h_finprob.ensure(nr));
-    FB_CUDA(c, c->h_finpos.ensure(nr));
+    if (c->host_log || c->rec_mode) FB_CUDA(c, c->h_maxprob.ensure((size_t)mp));
     long h2d = 0;
     const size_t stage_need = ng * sizeof(FbGapMeta) + c->h_flank.size() + (c->h_codes.size() + c->h_nmask.size()) * sizeof(uint4) +
                               nr * sizeof(FbRecMeta) + c->h_units.size() * sizeof(FbUnit) + 6 * 256;
@@ -1188,7 +1246,7 @@ namespace {
 void fill_em_params(fb_ctx* c, FbEmParams& p) {
     memset(&p, 0, sizeof p);
     memcpy(p.eo_tab, c->h_eo.data(), sizeof p.eo_tab);
-    p.ild = c->d_ild.p;
+    p.ild = c->d_ild_em.p;
     memcpy(p.T, c->T, sizeof p.T);
     p.thr_min = c->thr_min;
     p.thr_max = c->thr_max;
@@ -1224,9 +1282,9 @@ cudaError_t launch_stage(fb_ctx* c, cudaStream_t s) {
     return fb_launch_stage(sp, s);
 }
 
-cudaError_t launch_bin(const Bin& b, const FbEmParams& p, cudaStream_t s) {
-    if (b.cluster > 1) return fb_launch_em_cluster(p, b.grid, b.cluster, b.smem, s);
-    return fb_launch_em(p, b.grid, b.threads, b.global_tables, b.smem, s);
+cudaError_t launch_bin(const fb_ctx* c, const Bin& b, const FbEmParams& p, cudaStream_t s) {
+    if (b.cluster > 1) return fb_launch_em_cluster(p, b.grid, b.cluster, c->f1, b.smem, s);
+    return fb_launch_em(p, b.grid, b.threads, b.global_tables, c->f1, b.smem, s);
 }
 
 void fill_bin_params(fb_ctx* c, size_t bi, FbEmParams& p) {
@@ -1234,6 +1292,7 @@ void fill_bin_params(fb_ctx* c, size_t bi, FbEmParams& p) {
     fill_em_params(c, p);
     p.units = c->d_units.p + b.first_unit;
     p.n_units = b.n_units;
+    p.unit_lik = c->d_unit_lik.p + b.first_unit;
     p.work_counter = c->d_counters.p + bi;
     p.nr_stride = b.nr_stride;
     p.gp_stride = b.gp_stride;
@@ -1247,7 +1306,10 @@ void fill_bin_params(fb_ctx* c, size_t bi, FbEmParams& p) {
 
 extern "C" {
 
-// EM scan of the units this context owns: launches, per-bin copies, host log sums (figbird.cpp:2468-2478, 1951-1955).
+// EM scan of the units this context owns (figbird.cpp:2468-2478): one persistent launch per size bin; every unit ends
+// with its likelihood (figbird.cpp:1951-1955) computed on the device — glibc's log restated bit for bit, the sum taken in
+// record order (fb_glibc_math.h) — so 8 bytes per unit come home instead of 8 bytes per (unit, record).
+// FB_HOST_LOG=1 keeps the round-1 route for comparison: per-record maxima to the host, log() and the sum by the host libm.
 int fb_run_scan(fb_ctx* c) {
     if (!c) return FB_EINVAL;
     if (!c->uploaded) return c->fail(FB_ESTATE, "fb_run_scan before fb_upload");
@@ -1259,8 +1321,8 @@ int fb_run_scan(fb_ctx* c) {
     st.em_launches = st.finalize_launches = 0;
     st.finalize_likelihoods = 0;
     st.finalize_kernel_ms = 0;
+    const bool host_log = c->host_log || c->rec_mode;
 
-    // ---- EM scan: one persistent launch per size bin
     FB_CUDA(c, cudaEventRecord(c->evs, c->stream));
     FB_CUDA(c, cudaMemsetAsync(c->d_counters.p, 0, sizeof(int) * (c->bins.size() + 1), c->stream));
     FB_CUDA(c, launch_stage(c, c->stream));
@@ -1270,30 +1332,35 @@ int fb_run_scan(fb_ctx* c) {
         const Bin& b = c->bins[bi];
         FbEmParams p;
         fill_bin_params(c, bi, p);
+        if (host_log) p.unit_lik = nullptr;
         // every bin runs on its own stream: as the persistent CTAs of one bin drain, CTAs of the next bin take over the
         // freed SMs, so only the last (smallest) bin has a tail
         cudaStream_t bs = c->bin_streams[bi];
         FB_CUDA(c, cudaStreamWaitEvent(bs, c->ev0, 0));
-        FB_CUDA(c, launch_bin(b, p, bs));
+        FB_CUDA(c, launch_bin(c, b, p, bs));
         st.em_launches++;
-        // this bin's slice of unit_maxprob goes home on the copy stream while the other bins compute
+        // this bin's results go home on the copy stream while the other bins compute
         FB_CUDA(c, cudaEventRecord(c->bin_done[bi], bs));
         FB_CUDA(c, cudaStreamWaitEvent(c->stream, c->bin_done[bi], 0));
         FB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->bin_done[bi], 0));
-        const FbUnit& u0 = c->h_units[b.first_unit];
-        const FbUnit& u1 = c->h_units[b.first_unit + b.n_units - 1];
-        const size_t lo = (size_t)u0.mp_off, hi = (size_t)u1.mp_off + c->unit_nrec[b.first_unit + b.n_units - 1];
-        if (hi > lo) {
-            FB_CUDA(c, cudaMemcpyAsync(c->h_maxprob.p + lo, c->d_maxprob.p + lo, (hi - lo) * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
-            d2h += (long)((hi - lo) * sizeof(double));
+        if (host_log) {
+            const FbUnit& u0 = c->h_units[b.first_unit];
+            const FbUnit& u1 = c->h_units[b.first_unit + b.n_units - 1];
+            const size_t lo = (size_t)u0.mp_off, hi = (size_t)u1.mp_off + c->unit_nrec[b.first_unit + b.n_units - 1];
+            if (hi > lo) {
+                FB_CUDA(c, cudaMemcpyAsync(c->h_maxprob.p + lo, c->d_maxprob.p + lo, (hi - lo) * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+                d2h += (long)((hi - lo) * sizeof(double));
+            }
+        } else {
+            FB_CUDA(c, cudaMemcpyAsync(c->h_unit_lik.p + b.first_unit, c->d_unit_lik.p + b.first_unit, (size_t)b.n_units * sizeof(double),
+                                       cudaMemcpyDeviceToHost, c->copy_stream));
+            d2h += (long)((size_t)b.n_units * sizeof(double));
         }
         FB_CUDA(c, cudaEventRecord(c->bin_copied[bi], c->copy_stream));
     }
     FB_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     tr.lap("run: launches enqueued");
 
-    // ---- likelihood per unit (figbird.cpp:1951-1955): the per-record maxima of a bin are copied back on a second
-    // stream as soon as that bin's launch has finished, and the host sums glibc log() over them while later bins run.
     // Estimates scanned by another rank stay NaN until fb_merge_liks.
     for (HostGap& g : c->gaps) {
         g.done = false;
@@ -1304,25 +1371,30 @@ int fb_run_scan(fb_ctx* c) {
     for (size_t bi = 0; bi < c->bins.size(); bi++) {
         const Bin& b = c->bins[bi];
         FB_CUDA(c, cudaEventSynchronize(c->bin_copied[bi]));
-        // units are independent (each writes its own slot of its gap's arrays); a unit's sum keeps the record order.
-        // Blocks of units on the host threads: a big gap set has millions of log() calls per bin.
+        // units are independent (each writes its own slot of its gap's arrays)
         const int per = 512, nblock = (b.n_units + per - 1) / per;
-        parallel_for(nblock, 0, [&](int blk) {
+        parallel_for(nblock, host_log ? 0 : 4, [&](int blk) {
             const int k1 = std::min(b.n_units, (blk + 1) * per);
             for (int k = blk * per; k < k1; k++) {
                 const FbUnit& u = c->h_units[b.first_unit + k];
                 HostGap& g = c->gaps[u.gap];
-                const double* mp = c->h_maxprob.p + u.mp_off;
                 double lik = 0;
-                for (int r = 0; r < g.nrec; r++)
-                    if (mp[r] > 0) lik += log(mp[r]);
+                if (host_log) {
+                    const double* mp = c->h_maxprob.p + u.mp_off;
+                    for (int r = 0; r < g.nrec; r++) {
+                        if (c->f1) lik += mp[r];                       // figbird.cpp:1951 (f=1: unconditional)
+                        else if (mp[r] > 0) lik += log(mp[r]);         // figbird.cpp:1953-1955
+                    }
+                } else {
+                    lik = c->h_unit_lik.p[b.first_unit + k];
+                }
                 g.liks[u.gp - g.gmin] = lik;
                 g.cons_off[u.gp - g.gmin] = u.cons_off;
             }
         });
     }
     FB_CUDA(c, cudaStreamSynchronize(c->stream));
-    tr.lap("run: EM + host log sums");
+    tr.lap(host_log ? "run: EM + host log sums" : "run: EM");
     float ms = 0;
     cudaEventElapsedTime(&ms, c->ev0, c->ev1);
     st.em_kernel_ms = ms;
@@ -1333,7 +1405,8 @@ int fb_run_scan(fb_ctx* c) {
 }
 
 // Best estimate per gap (figbird.cpp:2479-2490) and finalize (figbird.cpp:2087-2393) for every gap whose winning
-// estimate was scanned by this context.
+// estimate was scanned by this context.  The whole of finalize runs on the device (fb_finalize_kernel); the filled
+// sequences and one discard count per gap come home.
 int fb_run_finalize(fb_ctx* c) {
     if (!c) return FB_EINVAL;
     if (!c->scanned) return c->fail(FB_ESTATE, "fb_run_finalize before fb_run_scan");
@@ -1342,17 +1415,19 @@ int fb_run_finalize(fb_ctx* c) {
     const int D = c->D;
     long d2h = st.d2h_bytes;
     Trace tr;
-    std::vector<long long> cons_off_of_best(c->gaps.size(), 0);
-    std::vector<int> gaplist, bestgp(c->gaps.size(), 0);
-    for (size_t gi = 0; gi < c->gaps.size(); gi++) {
+    const size_t ng = c->gaps.size();
+    std::vector<long long> cons_off_of_best(ng, 0), filled_off(ng, 0);
+    std::vector<int> gaplist, bestgp(ng, 0), counts_off(ng, 0);
+    for (size_t gi = 0; gi < ng; gi++) {
         HostGap& g = c->gaps[gi];
         if (!g.owned) continue;
         double best = -DBL_MAX;
         int be = g.gmin;
         for (int gp = g.gmin; gp <= g.gmax; gp++) {
             const double l = g.liks[gp - g.gmin];
-            if (std::isnan(l)) return c->fail(FB_ESTATE, "gap %zu: estimate %d was scanned by another rank and its likelihood has not been merged", gi, gp);
-            if (l >= best) {   // last estimate wins ties
+            if (std::isnan(l) && g.cons_off[gp - g.gmin] < 0)
+                return c->fail(FB_ESTATE, "gap %zu: estimate %d was scanned by another rank and its likelihood has not been merged", gi, gp);
+            if (l >= best) {   // last estimate wins ties; a NaN likelihood (f=1 only) never wins, as in the reference
                 best = l;
                 be = gp;
             }
@@ -1366,12 +1441,42 @@ int fb_run_finalize(fb_ctx* c) {
         gaplist.push_back((int)gi);
     }
 
-    // ---- finalize scoring on the device
+    size_t fill_total = 0, counts_total = 0;
     if (!gaplist.empty()) {
-        FB_CUDA(c, cudaMemcpyAsync(c->d_gaplist.p, gaplist.data(), gaplist.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-        FB_CUDA(c, cudaMemcpyAsync(c->d_bestgp.p, bestgp.data(), bestgp.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-        FB_CUDA(c, cudaMemcpyAsync(c->d_bestoff.p, cons_off_of_best.data(), cons_off_of_best.size() * sizeof(long long),
-                                   cudaMemcpyHostToDevice, c->stream));
+        int rows = 0, gbmax = 1, max_nrec = 1;
+        for (int gi : gaplist) {
+            const HostGap& g = c->gaps[gi];
+            rows = std::max(rows, g.best_est + 2 * g.lmax);
+            gbmax = std::max(gbmax, g.best_est);
+            max_nrec = std::max(max_nrec, g.nrec);
+            filled_off[gi] = (long long)fill_total;
+            fill_total += (size_t)g.best_est;
+        }
+        // records are independent in finalize: enough CTAs per gap to fill the GPU, at least one record per warp
+        const int per_cta = FB_FIN_THREADS / 32;
+        const int slices = std::max(1, std::min((4 * c->sm_count + (int)gaplist.size() - 1) / (int)gaplist.size(), (max_nrec + per_cta - 1) / per_cta));
+        if (slices > 1)
+            for (int gi : gaplist) {
+                counts_off[gi] = (int)counts_total;
+                counts_total += 5 * (size_t)c->gaps[gi].best_est;
+            }
+        const size_t smem = sizeof(int) * 5 * (size_t)gbmax + (size_t)rows + 16;
+        if (smem > (size_t)c->max_smem - 8192) return c->fail(FB_EINVAL, "gap estimate %d too long for finalize", gbmax);
+        FB_CUDA(c, c->d_fin_counts.ensure(counts_total));
+        unsigned char* pin = c->h_stage.p;        // the small per-pass arrays leave from pinned memory (fb_upload sized it for far more)
+        auto up = [&](void* dst, const void* src, size_t bytes) {
+            memcpy(pin, src, bytes);
+            cudaError_t e = cudaMemcpyAsync(dst, pin, bytes, cudaMemcpyHostToDevice, c->stream);
+            pin += (bytes + 255) & ~size_t(255);
+            return e;
+        };
+        FB_CUDA(c, up(c->d_gaplist.p, gaplist.data(), gaplist.size() * sizeof(int)));
+        FB_CUDA(c, up(c->d_bestgp.p, bestgp.data(), ng * sizeof(int)));
+        FB_CUDA(c, up(c->d_bestoff.p, cons_off_of_best.data(), ng * sizeof(long long)));
+        FB_CUDA(c, up(c->d_filled_off.p, filled_off.data(), ng * sizeof(long long)));
+        FB_CUDA(c, up(c->d_fin_counts_off.p, counts_off.data(), ng * sizeof(int)));
+        FB_CUDA(c, cudaMemsetAsync(c->d_tickets.p, 0, sizeof(int) * 2 * ng, c->stream));
+        if (counts_total) FB_CUDA(c, cudaMemsetAsync(c->d_fin_counts.p, 0, sizeof(int) * counts_total, c->stream));
         FbFinParams f;
         memset(&f, 0, sizeof f);
         f.ild = c->d_ild.p;
@@ -1390,68 +1495,39 @@ int fb_run_finalize(fb_ctx* c) {
         f.best_gp = c->d_bestgp.p;
         f.best_cons_off = c->d_bestoff.p;
         f.unit_cons = c->d_cons.p;
-        f.fin_maxprob = c->d_finprob.p;
-        f.fin_maxpos = c->d_finpos.p;
-        int rows = 0;
-        for (int gi : gaplist) rows = std::max(rows, c->gaps[gi].best_est + 2 * c->gaps[gi].lmax);
         f.gmax_stride = rows;
-        if ((size_t)rows + 16 > (size_t)c->max_smem - 8192) return c->fail(FB_EINVAL, "gap estimate %d too long for finalize", rows);
+        f.gb_stride = gbmax;
+        f.theta = c->theta;
+        f.fin_counts = c->d_fin_counts.p;
+        f.fin_counts_off = c->d_fin_counts_off.p;
+        f.tickets = c->d_tickets.p;
+        f.discarded = c->d_tickets.p + ng;
+        f.filled = c->d_filled.p;
+        f.filled_off = c->d_filled_off.p;
         FB_CUDA(c, cudaEventRecord(c->ev2, c->stream));
-        // records are independent in finalize: enough CTAs per gap to fill the GPU, at least one record per warp
-        int max_nrec = 1;
-        for (int gi : gaplist) max_nrec = std::max(max_nrec, c->gaps[gi].nrec);
-        const int per_cta = FB_FIN_THREADS / 32;
-        const int slices = std::max(1, std::min((4 * c->sm_count + (int)gaplist.size() - 1) / (int)gaplist.size(), (max_nrec + per_cta - 1) / per_cta));
-        FB_CUDA(c, fb_launch_finalize(f, (int)gaplist.size(), slices, (size_t)rows + 16, c->stream));
+        FB_CUDA(c, fb_launch_finalize(f, (int)gaplist.size(), slices, smem, c->stream));
         FB_CUDA(c, cudaEventRecord(c->ev3, c->stream));
         st.finalize_launches = 1;
-        const size_t nr = c->h_rmeta.size();
-        FB_CUDA(c, cudaMemcpyAsync(c->h_finprob.p, c->d_finprob.p, nr * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        FB_CUDA(c, cudaMemcpyAsync(c->h_finpos.p, c->d_finpos.p, nr * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        d2h += (long)(nr * (sizeof(double) + sizeof(int)));
-        FB_CUDA(c, cudaStreamSynchronize(c->stream));
+        FB_CUDA(c, cudaMemcpyAsync(c->h_filled.p, c->d_filled.p, fill_total, cudaMemcpyDeviceToHost, c->stream));
+        FB_CUDA(c, cudaMemcpyAsync(c->h_discarded.p, c->d_tickets.p + ng, ng * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        d2h += (long)(fill_total + ng * sizeof(int));
+        FB_CUDA(c, cudaEventRecord(c->eve, c->stream));
+        FB_CUDA(c, cudaEventSynchronize(c->eve));
+    } else {
+        FB_CUDA(c, cudaEventRecord(c->eve, c->stream));
+        FB_CUDA(c, cudaEventSynchronize(c->eve));
     }
-
-    tr.lap("run: select + finalize kernel");
-    // ---- finalize on the host: cut-off, +1 counts, computeSequence(1), getConcensus (gaps are independent: host threads)
-    std::vector<long> fin_liks(gaplist.size(), 0);
-    parallel_for((int)gaplist.size(), 0, [&](int k) {
-        HostGap& g = c->gaps[gaplist[k]];
-        const int gb = g.best_est;
-        std::vector<int> cnt((size_t)gb * 5, 0);
-        int disc = 0;
-        for (int r = 0; r < g.nrec; r++) {
-            const int rec = g.rec_off + r;
-            const FbRecMeta& m = c->h_rmeta[rec];
-            const int L2 = m.flags & 0xff;
-            fin_liks[k] += placements(m, D, gb);
-            const double mp = c->h_finprob.p[rec];
-            if (-log(mp) <= c->cutoff) {                       // figbird.cpp:2293
-                const int pos = c->h_finpos.p[rec];
-                const uint8_t* cs = &c->h_bytes[(size_t)rec * FB_MAX_READ];
-                for (int j = 0; j < L2; j++) {
-                    int x = pos + j;
-                    if (x >= D && x < D + gb) cnt[(size_t)(x - D) * 5 + cs[j]] += 1;
-                }
-            } else {
-                disc++;
-            }
-        }
+    tr.lap("run: select + finalize kernel + results");
+    // ---- hand the results to the gaps (figbird.cpp:2382, 2050-2063)
+    for (int gi : gaplist) {
+        HostGap& g = c->gaps[gi];
         g.total_reads = g.nrec;
-        g.discarded = disc;
-        g.filled.assign((size_t)gb, 'N');
-        for (int i = 0; i < gb; i++) {                          // computeSequence(1), figbird.cpp:1989-2045
-            int mx = 0, idx = -1;
-            for (int q = 0; q < 5; q++)
-                if (cnt[(size_t)i * 5 + q] > mx) { mx = cnt[(size_t)i * 5 + q]; idx = q; }
-            g.filled[i] = idx < 0 ? 'N' : "ACGTN"[idx];
-        }
+        g.discarded = c->h_discarded.p[gi];
+        g.filled.assign(c->h_filled.p + filled_off[gi], (size_t)g.best_est);
         g.done = true;
-    });
-    for (long v : fin_liks) st.finalize_likelihoods += v;
-    tr.lap("run: host finalize");
-    FB_CUDA(c, cudaEventRecord(c->eve, c->stream));
-    FB_CUDA(c, cudaEventSynchronize(c->eve));
+        for (int r = 0; r < g.nrec; r++) st.finalize_likelihoods += placements(c->h_rmeta[g.rec_off + r], D, g.best_est);
+    }
+    tr.lap("run: results");
     float ms = 0;
     cudaEventElapsedTime(&ms, c->evs, c->eve);
     st.step_ms = ms;
@@ -1519,9 +1595,10 @@ int shard_enqueue_iter(fb_ctx* c, int it, const double* const* peer_counts, doub
         }
         p.part_out = out_counts;
         p.abort = c->d_shard_err.p;
+        p.unit_lik = nullptr;                 // the likelihoods come from the merged maxima of all ranks (shard_host_liks)
         cudaStream_t bs = c->bin_streams[bi];
         FB_CUDA(c, cudaStreamWaitEvent(bs, c->ev0, 0));
-        FB_CUDA(c, launch_bin(b, p, bs));
+        FB_CUDA(c, launch_bin(c, b, p, bs));
         st.em_launches++;
         FB_CUDA(c, cudaEventRecord(c->bin_done[bi], bs));
         FB_CUDA(c, cudaStreamWaitEvent(c->stream, c->bin_done[bi], 0));
@@ -1838,7 +1915,7 @@ int fb_dump_profile(fb_ctx* c, int gap, int estimate, double* probs, double* cou
             p.dump_unit = 0;
             FB_CUDA(c, cudaMemsetAsync(p.work_counter, 0, sizeof(int), c->stream));
             FB_CUDA(c, launch_stage(c, c->stream));
-            FB_CUDA(c, fb_launch_em(p, 1, b.threads, b.global_tables, b.smem, c->stream));
+            FB_CUDA(c, fb_launch_em(p, 1, b.threads, b.global_tables, c->f1, b.smem, c->stream));
             FB_CUDA(c, cudaMemcpyAsync(probs, c->d_dump.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
             FB_CUDA(c, cudaMemcpyAsync(counts, c->d_dump.p + n, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
             FB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -1846,6 +1923,24 @@ int fb_dump_profile(fb_ctx* c, int gap, int estimate, double* probs, double* cou
         }
     }
     return c->fail(FB_EINVAL, "estimate %d is not in the scan range of gap %d (or the gap is not owned)", estimate, gap);
+}
+
+int fb_devmath_eval(int device, int what, const double* in, double* out, long n) {
+    if (!in || !out || n < 0 || (what != 0 && what != 1)) return FB_EINVAL;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return FB_ECUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return FB_ECUDA;
+    double *di = nullptr, *dout = nullptr;
+    int rc = FB_ECUDA;
+    if (cudaMalloc((void**)&di, sizeof(double) * (size_t)std::max(n, 1L)) == cudaSuccess &&
+        cudaMalloc((void**)&dout, sizeof(double) * (size_t)std::max(n, 1L)) == cudaSuccess &&
+        cudaMemcpy(di, in, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice) == cudaSuccess &&
+        fb_launch_devmath(di, dout, n, what, nullptr) == cudaSuccess &&
+        cudaMemcpy(out, dout, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost) == cudaSuccess)
+        rc = FB_OK;
+    cudaFree(di);
+    cudaFree(dout);
+    return rc;
 }
 
 int fb_measure_smem_peak(int device, double* gbs) {

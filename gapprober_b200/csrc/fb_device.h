@@ -60,6 +60,7 @@ struct FbEmParams {
     int* work_counter;
     // outputs
     double* unit_maxprob;   // per (unit, record) max placement score of the last iteration
+    double* unit_lik;       // per unit: the likelihood placeReads returns in the last iteration (nullptr: not wanted)
     char* unit_cons;        // per unit consensus string (computeSequence(0))
     double* dump_probs;     // optional: full profile of unit dump_unit, [(gp + 2D) * 5]
     double* dump_counts;
@@ -121,17 +122,24 @@ struct FbFinParams {
     const int* best_gp;     // [n_gaps] winning estimate
     const long long* best_cons_off;  // [n_gaps] offset of the winning consensus in unit_cons
     const char* unit_cons;
-    double* fin_maxprob;    // [n_records]
-    int* fin_maxpos;        // [n_records]
-    int gmax_stride;        // smem rows for the gap string
+    int gmax_stride;        // smem bytes for the gap string
+    int gb_stride;          // smem rows of the per-CTA counts (largest winning estimate of the launch)
+    double theta;           // smallest double x with -log(x) <= gapProbCutOff (host libm): the cut-off test is x >= theta
+    int* fin_counts;        // global counts of the gaps finalized by several CTAs, [.][5], zeroed before the launch
+    const int* fin_counts_off;   // [n_gaps] offset of a gap's counts in fin_counts
+    int* tickets;           // [n_gaps] CTAs of the gap that have added their counts, zeroed before the launch
+    int* discarded;         // [n_gaps] out: records that failed the cut-off test (zeroed before the launch)
+    char* filled;           // out: the filled sequences of the launch's gaps, back to back
+    const long long* filled_off;   // [n_gaps] offset of gap g's sequence in `filled`
 };
 
 size_t fb_em_smem_bytes(int nr_stride, int gp_stride, int p_stride, int chunk, int pwin, bool global_tables);
-cudaError_t fb_launch_em(const FbEmParams& p, int grid, int threads, bool global_tables, size_t smem, cudaStream_t s);   // threads: 512 or 1024
-cudaError_t fb_em_ctas_per_sm(int threads, bool global_tables, size_t smem, int* n);   // occupancy of the plain variant, static smem included
+// threads: 512 or 1024; f1: the reference's log-domain mode (argv[2] = 1)
+cudaError_t fb_launch_em(const FbEmParams& p, int grid, int threads, bool global_tables, bool f1, size_t smem, cudaStream_t s);
+cudaError_t fb_em_ctas_per_sm(int threads, bool global_tables, bool f1, size_t smem, int* n);   // occupancy of the plain variant, static smem included
 // cluster variant: n_clusters thread-block clusters of `cluster` CTAs, each cluster running one unit at a time
-cudaError_t fb_launch_em_cluster(const FbEmParams& p, int n_clusters, int cluster, size_t smem, cudaStream_t s);
-cudaError_t fb_em_max_clusters(int cluster, size_t smem, int* n);     // co-resident clusters of that size on this device
+cudaError_t fb_launch_em_cluster(const FbEmParams& p, int n_clusters, int cluster, bool f1, size_t smem, cudaStream_t s);
+cudaError_t fb_em_max_clusters(int cluster, bool f1, size_t smem, int* n);     // co-resident clusters of that size on this device
 // n gaps x `slices` CTAs per gap (a CTA takes every slices-th group of 8 records)
 cudaError_t fb_launch_finalize(const FbFinParams& p, int n, int slices, size_t smem, cudaStream_t s);
 // Flags of the record-sharded scan's device-side barrier (one 64-bit word per rank, in every rank's exchange memory).
@@ -149,4 +157,5 @@ cudaError_t fb_launch_flag_wait(const FbFlagParams& p, cudaStream_t s);
 cudaError_t fb_launch_stage(const FbStageParams& p, cudaStream_t s);
 cudaError_t fb_launch_shard_finish(const FbShardFinParams& p, cudaStream_t s);
 cudaError_t fb_kernels_init(int* max_smem_optin, int* sm_count);
+cudaError_t fb_launch_devmath(const double* in, double* out, long n, int what, cudaStream_t s);   // what: 0 log, 1 pow(10, .)
 cudaError_t fb_microbench_smem(double* gbs, int reps);     // fb_microbench.cu: measured shared-memory read bandwidth (LDS.128, conflict-free)

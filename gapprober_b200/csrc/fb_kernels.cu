@@ -29,6 +29,7 @@
 // binds; DESIGN.md has the arithmetic, profiles/README.md the measurements.
 
 #include "fb_device.h"
+#include "fb_glibc_math.h"
 
 #include <cooperative_groups.h>
 
@@ -61,6 +62,30 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
         v = w > v ? w : v;
     }
     return v;
+}
+
+// placeReads' return value in the last iteration (figbird.cpp:1951-1955): one warp, called once per unit.  Kept out of
+// line so that its registers (the log's) do not weigh on the EM loop.
+template <bool F1>
+__device__ __noinline__ void unit_likelihood(const double* maxprob, int nrec, double* out) {
+    const int lane = threadIdx.x & 31;
+    double acc = 0.0;
+    for (int base = 0; base < nrec; base += 32) {
+        const int r = base + lane;
+        double v = 0.0;
+        bool use = false;
+        if (r < nrec) {
+            v = __ldcg(maxprob + r);              // written by this CTA (cluster) before the barrier the caller passed
+            use = F1 ? true : v > 0.0;
+            if (!F1 && use) v = fbm_log(v);
+        }
+        const unsigned used = __ballot_sync(0xffffffffu, use);
+        for (int k = 0; k < 32; k++) {            // the additions one after the other, in record order, like the CPU's loop
+            const double vk = __shfl_sync(0xffffffffu, v, k);
+            if ((used >> k) & 1u) acc = dadd(acc, vk);
+        }
+    }
+    if (lane == 0) *out = acc;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -210,7 +235,14 @@ __device__ __forceinline__ void load_record_bytes(const uint4* __restrict__ code
 // E-step of 64 placements of one record: lane owns placements ua and ua+32 (two independent product chains).
 // The running score is multiplied base by base in read order (figbird.cpp:1840-1864); REV selects the
 // read-position index k = L2-1-j of a reverse-complemented mate (figbird.cpp:1845-1852).
-template <bool REV, bool TWO>
+// F1 is the reference's log-domain mode (argv[2] = 1): the running score is a SUM of glibc logs of the same terms
+// (figbird.cpp:1856, 1861), started from log(ILD[t]) (figbird.cpp:1835).
+template <bool F1>
+__device__ __forceinline__ double score_step(double s, double term) {
+    return F1 ? dadd(s, fbm_log(term)) : dmul(s, term);
+}
+
+template <bool REV, bool TWO, bool F1>
 __device__ __forceinline__ void score_pair(const unsigned char* pa, const uint32_t* __restrict__ cls4, unsigned cstride, const FbEmParams& p,
                                            int L2, double& sa, double& sb) {
     int k = REV ? L2 - 1 : 0;    // read-position index of base j (figbird.cpp:1845-1852)
@@ -222,10 +254,10 @@ __device__ __forceinline__ void score_pair(const unsigned char* pa, const uint32
             const unsigned char* a = pa + ((cw >> (4 * q)) & 7u) * cstride + q * 16;   // class table of this base, row of this placement
             const double2 va = *reinterpret_cast<const double2*>(a);
             const double2 e = p.eo_tab[REV ? k - q : k + q];                // {1 - e[k], e[k]} via the constant cache
-            sa = dmul(sa, dadd(dmul(va.x, e.x), dmul(e.y, va.y)));          // figbird.cpp:1855 / 1862
+            sa = score_step<F1>(sa, dadd(dmul(va.x, e.x), dmul(e.y, va.y)));   // figbird.cpp:1855 / 1862
             if (TWO) {
                 const double2 vb = *reinterpret_cast<const double2*>(a + 32 * 16);
-                sb = dmul(sb, dadd(dmul(vb.x, e.x), dmul(e.y, vb.y)));
+                sb = score_step<F1>(sb, dadd(dmul(vb.x, e.x), dmul(e.y, vb.y)));
             }
         }
         pa += 64;
@@ -236,14 +268,35 @@ __device__ __forceinline__ void score_pair(const unsigned char* pa, const uint32
         const unsigned char* a = pa + c * cstride;
         const double2 va = *reinterpret_cast<const double2*>(a);
         const double2 e = p.eo_tab[k];
-        sa = dmul(sa, dadd(dmul(va.x, e.x), dmul(e.y, va.y)));
+        sa = score_step<F1>(sa, dadd(dmul(va.x, e.x), dmul(e.y, va.y)));
         if (TWO) {
             const double2 vb = *reinterpret_cast<const double2*>(a + 32 * 16);
-            sb = dmul(sb, dadd(dmul(vb.x, e.x), dmul(e.y, vb.y)));
+            sb = score_step<F1>(sb, dadd(dmul(vb.x, e.x), dmul(e.y, vb.y)));
         }
         pa += 16;
         k += REV ? -1 : 1;
     }
+}
+
+// Per-record running maximum as an unsigned key (atomicMax in shared memory).  f=0: maxProb starts at 0 and only scores
+// above 0 win (figbird.cpp:1815, 1866), so the bit pattern of a positive double orders correctly and 0 means "none".
+// f=1: maxProb starts at -DBL_MAX and log scores are negative (figbird.cpp:1814): the usual order-preserving flip of
+// the sign-magnitude pattern; scores that do not beat -DBL_MAX (NaN, -inf, -DBL_MAX itself) give the key of -DBL_MAX.
+template <bool F1>
+__device__ __forceinline__ unsigned long long score_key(double s, bool valid) {
+    if (!F1) return (valid && s > 0.0) ? (unsigned long long)__double_as_longlong(s) : 0ull;
+    const double v = (valid && s > -1.7976931348623157e308) ? s : -1.7976931348623157e308;
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+template <bool F1>
+__device__ __forceinline__ double key_score(unsigned long long k) {
+    if (!F1) return __longlong_as_double((long long)k);
+    return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
+}
+template <bool F1>
+__device__ __forceinline__ unsigned long long key_init() {
+    return F1 ? score_key<true>(-1.7976931348623157e308, true) : 0ull;
 }
 
 // Per-record tables of the EM kernel, one warp per record (they do not depend on the estimate, so every unit of the
@@ -310,7 +363,7 @@ __global__ void __launch_bounds__(256) fb_stage_kernel(const FbStageParams p) {
 //   * the per-round barrier becomes a cluster barrier.
 // NT: threads per CTA — 512 with two CTAs per SM where the tables allow it, 1024 with one CTA per SM for the bigger
 // estimates, so that an SM always has 32 warps to hide the shared-memory (or, with GT, L2) latency.
-template <bool GT, bool CLU, int NT>
+template <bool GT, bool CLU, int NT, bool F1>
 __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(const __grid_constant__ FbEmParams p) {
     static_assert(!(GT && CLU), "the cluster variant keeps its tables in shared memory");
     if (p.abort && *reinterpret_cast<const volatile int*>(p.abort)) return;   // a barrier of this record-sharded pass has failed
@@ -447,9 +500,9 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
                 double* wE = s.w0 + ((ce + 2) & 1) * s.w_stride;
                 const double* wM = s.w0 + ((cm + 2) & 1) * s.w_stride;
                 if (last && tid < n_m) {   // per-record maximum of the last iteration (feeds figbird.cpp:1951-1955 on the host)
-                    if (!CLU) p.unit_maxprob[unit.mp_off + cm * CH + tid] = __longlong_as_double((long long)SM.rmax[tid]);
+                    if (!CLU) p.unit_maxprob[unit.mp_off + cm * CH + tid] = key_score<F1>(SM.rmax[tid]);
                     else if ((unsigned)tid % csize == crank)   // all E tasks of a record run in one CTA: it holds the maximum
-                        p.unit_maxprob[unit.mp_off + cm * CH + tid] = __longlong_as_double((long long)SM.rmax[tid]);
+                        p.unit_maxprob[unit.mp_off + cm * CH + tid] = key_score<F1>(SM.rmax[tid]);
                 }
                 // a cluster deals E tasks by record and M tasks by row block; staging is done by every CTA for itself
                 const int nrb_q = CLU ? (nrb + (int)csize - 1 - (int)crank) / (int)csize : nrb;
@@ -467,7 +520,7 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
                         bulk_g2s(SL.jl, p.st_jl + rec0 * kListBytes, (uint32_t)n_l * kListBytes, bar);
                         bulk_g2s(SL.cum, p.st_cum + rec0 * 32, (uint32_t)n_l * 32u, bar);
                     }
-                    if (tid < n_l) SL.rmax[tid] = 0ull;          // new iteration (or new chunk), new maximum
+                    if (tid < n_l) SL.rmax[tid] = key_init<F1>();   // new iteration (or new chunk), new maximum
                 }
                 const int tM = n_m ? nrb_q * 5 : 0, tE = ne_q * nblk;
                 const int ntask = tM + tE;
@@ -557,33 +610,39 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
                         const int uc = va_ok ? ua : lo;                      // invalid lanes shadow a valid placement
                         const int ta = left ? uc + tb : tb - uc;
                         const int tbb = vb_ok ? (left ? ub + tb : tb - ub) : ta;
-                        double sa = s.ild[ta - p.thr_min], sb = s.ild[tbb - p.thr_min];
+                        double sa = s.ild[ta - p.thr_min], sb = s.ild[tbb - p.thr_min];   // f=1: the table holds log(ILD[t]) (host libm)
                         const unsigned char* pa = reinterpret_cast<const unsigned char*>(s.pq + (uc - R0 - (lo >= hl ? hn : 0)));
                         const uint32_t* cls4 = SE.cls4 + rl * 16;
                         const unsigned cstride = (unsigned)nrs * 16u;
                         const bool two = lo + 64 * blk + 32 <= hi;           // any lane with a second placement?
                         if (two) {
-                            if (rev) score_pair<true, true>(pa, cls4, cstride, p, L2, sa, sb);
-                            else score_pair<false, true>(pa, cls4, cstride, p, L2, sa, sb);
+                            if (rev) score_pair<true, true, F1>(pa, cls4, cstride, p, L2, sa, sb);
+                            else score_pair<false, true, F1>(pa, cls4, cstride, p, L2, sa, sb);
                         } else {
-                            if (rev) score_pair<true, false>(pa, cls4, cstride, p, L2, sa, sb);
-                            else score_pair<false, false>(pa, cls4, cstride, p, L2, sa, sb);
+                            if (rev) score_pair<true, false, F1>(pa, cls4, cstride, p, L2, sa, sb);
+                            else score_pair<false, false, F1>(pa, cls4, cstride, p, L2, sa, sb);
+                        }
+                        // what the M-step adds to the counts: the score itself, pow(10, score) in f=1 (figbird.cpp:1878, 1879)
+                        double wa = sa, wb = sb;
+                        if (F1) {
+                            wa = fbm_pow10(sa);
+                            wb = two ? fbm_pow10(sb) : 0.0;
                         }
                         if (!CLU) {
-                            if (ka < PS) wrow[ka] = va_ok ? sa : 0.0;
-                            if (kb < PS) wrow[kb] = vb_ok ? sb : 0.0;
+                            if (ka < PS) wrow[ka] = va_ok ? wa : 0.0;
+                            if (kb < PS) wrow[kb] = vb_ok ? wb : 0.0;
                         } else {
                             for (unsigned k = 0; k < csize; k++) {   // the M tasks of every CTA read this row from their own copy
                                 double* wr = cg::this_cluster().map_shared_rank(wrow, k);
-                                if (ka < PS) wr[ka] = va_ok ? sa : 0.0;
-                                if (kb < PS) wr[kb] = vb_ok ? sb : 0.0;
+                                if (ka < PS) wr[ka] = va_ok ? wa : 0.0;
+                                if (kb < PS) wr[kb] = vb_ok ? wb : 0.0;
                             }
                         }
-                        // tempProb > maxProb with maxProb starting at 0: NaN and non-positive scores never win
-                        unsigned long long ba = (va_ok && sa > 0.0) ? (unsigned long long)__double_as_longlong(sa) : 0ull;
-                        unsigned long long bb = (vb_ok && sb > 0.0) ? (unsigned long long)__double_as_longlong(sb) : 0ull;
+                        // tempProb > maxProb with maxProb starting at 0 (-DBL_MAX in f=1): NaN and scores not above it never win;
+                        // the maximum is over the scores as the reference compares them (log scores in f=1)
+                        unsigned long long ba = score_key<F1>(sa, va_ok), bb = score_key<F1>(sb, vb_ok);
                         ba = warp_max_u64(ba > bb ? ba : bb);
-                        if (lane == 0 && ba) atomicMax(&SE.rmax[rl], ba);
+                        if (lane == 0 && ba > key_init<F1>()) atomicMax(&SE.rmax[rl], ba);
                     }
                 }
                 if (tid == 0) s_queue[(round + 1) & 1] = 0;   // nobody touches the other slot during this round
@@ -595,7 +654,7 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
             }
 
             // chunk 0 of a kept staging gets its per-record maxima reset here, a barrier ahead of the next iteration's E tasks
-            if (keep_staged && !last && tid < min(CH, nrec)) stage_at(s, 0).rmax[tid] = 0ull;
+            if (keep_staged && !last && tid < min(CH, nrec)) stage_at(s, 0).rmax[tid] = key_init<F1>();
             // ---- computeProbsGap + computeErrorProbsGap on the gap rows (flank rows never change)
             for (int xg = tid; xg < gpc; xg += NT) {
                 if (CLU && (unsigned)(xg >> 5) % csize != crank) continue;   // the counts of this row live in another CTA
@@ -642,6 +701,14 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
             sync_all();
         }
 
+        // ---- likelihood of the unit (figbird.cpp:1951-1955, last iteration): sum over the records, IN RECORD ORDER, of
+        // glibc's log of the record's best score (f=0, only where it is above 0) or of the best log score itself (f=1).
+        // One warp: the logs in parallel, the additions one after the other like the CPU's loop.
+        if (p.unit_lik && (!CLU || crank == 0) && tid < 32) {
+            if (CLU) __threadfence();
+            unit_likelihood<F1>(p.unit_maxprob + unit.mp_off, nrec, p.unit_lik + ui);
+        }
+
         // ---- parity tap: the whole profile of one unit, laid out like probsGap/countsGap
         if (p.dump_probs && ui == p.dump_unit) {
             const int rows = gp + 2 * D;
@@ -670,26 +737,35 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
     }
 }
 
-// finalize(), figbird.cpp:2239-2291 / 2310-2359: score every placement of every record against the
-// winning consensus (+ flanks) with the match/mismatch model and keep the best placement, lowest
-// position on ties.  The records of a gap are independent here: CTA (gap, slice) takes every
-// gridDim.y-th group of records, one record per warp, lanes over placements.  The cut-off test
-// (-log(maxProb) <= gapProbCutOff), the +1 counting and computeSequence(1) are done by the host
-// from (maxProb, maxPos).
+// finalize(), figbird.cpp:2087-2393, all of it: score every placement of every record against the winning consensus
+// (+ flanks) with the match/mismatch model and keep the best placement, lowest position on ties (2239-2291 / 2310-2359);
+// a record whose best score passes the cut-off adds +1 to the count of each of its bases that falls into the gap
+// (2293-2306 / 2361-2374); computeSequence(1) turns the counts into the filled sequence (1984-2047).
+//   * The cut-off test -log(maxProb) <= gapProbCutOff is a threshold on maxProb: the host finds, with the reference's own
+//     libm, the smallest double theta that passes (fb_context.cpp: cutoff_threshold) and the kernel compares
+//     maxProb >= theta — the same decision for every double, no log on the device.
+//   * The counts are integers, so their order of accumulation is free: shared-memory atomics per CTA.
+//   * The records of a gap are independent: CTA (gap, slice) takes every gridDim.y-th group of records, one record per
+//     warp, lanes over placements.  With one slice per gap the CTA finishes the gap itself; with several, each CTA adds
+//     its counts to the gap's global counts and the last one to arrive (a ticket per gap) writes the sequence.
 __global__ void __launch_bounds__(FB_FIN_THREADS) fb_finalize_kernel(const FbFinParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint8_t* gcode = smem_raw;                                     // [gmax_stride] codes of flank+best+flank window
-    __shared__ __align__(16) uint8_t cs_all[FB_FIN_THREADS / 32][FB_MAX_READ];
-    __shared__ double sT[25];
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = p.gap_list[blockIdx.x];
     const FbGapMeta gm = p.gaps[g];
     const int D = p.D, gb = p.best_gp[g], lmax = gm.lmax;
+    int* scnt = reinterpret_cast<int*>(smem_raw);                  // [gb][5] counts of this CTA
+    uint8_t* gcode = smem_raw + sizeof(int) * 5 * (size_t)p.gb_stride;   // [gmax_stride] codes of the flank+best+flank window
+    __shared__ __align__(16) uint8_t cs_all[FB_FIN_THREADS / 32][FB_MAX_READ];
+    __shared__ double sT[25];
+    __shared__ int s_disc, s_last;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int R0 = D - lmax + 1, NR = gb + 2 * lmax - 2;
     const uint8_t* fl = p.flank + (size_t)g * 2 * D;
     const char* best = p.unit_cons + p.best_cons_off[g];
     if (tid < 25) sT[tid] = p.T[tid];
+    if (tid == 0) { s_disc = 0; s_last = 0; }
+    for (int i = tid; i < 5 * gb; i += FB_FIN_THREADS) scnt[i] = 0;
     for (int xr = tid; xr < NR; xr += FB_FIN_THREADS) {
         int x = xr + R0, c;
         if (x < D) c = fl[x];
@@ -704,6 +780,7 @@ __global__ void __launch_bounds__(FB_FIN_THREADS) fb_finalize_kernel(const FbFin
 
     uint8_t* cs = cs_all[warp];
     const int nwarp = FB_FIN_THREADS / 32;
+    int disc = 0;
     for (int r = blockIdx.y * nwarp + warp; r < gm.nrec; r += gridDim.y * nwarp) {
         const int rec = gm.rec_off + r;
         const FbRecMeta rm = p.rmeta[rec];
@@ -732,10 +809,45 @@ __global__ void __launch_bounds__(FB_FIN_THREADS) fb_finalize_kernel(const FbFin
             int ou = __shfl_xor_sync(0xffffffffu, bu, o);
             if (ov > bv || (ov == bv && ou < bu)) { bv = ov; bu = ou; }
         }
-        if (lane == 0) {
-            p.fin_maxprob[rec] = bv;
-            p.fin_maxpos[rec] = bv > 0.0 ? bu : 0;   // maxPos stays 0 when nothing scored above 0 (figbird.cpp:2235)
+        const int pos = bv > 0.0 ? bu : 0;       // maxPos stays 0 when nothing scored above 0 (figbird.cpp:2235)
+        if (bv >= p.theta) {                     // -log(maxProb) <= gapProbCutOff, figbird.cpp:2293
+            for (int j = lane; j < L2; j += 32) {
+                const int x = pos + j;
+                if (x >= D && x < D + gb) atomicAdd(&scnt[(x - D) * 5 + cs[j]], 1);
+            }
+        } else {
+            disc++;                              // the same in every lane
         }
+    }
+    if (lane == 0 && disc) atomicAdd(&s_disc, disc);
+    __syncthreads();
+
+    const int* cnt = scnt;
+    if (gridDim.y > 1) {
+        int* gc = p.fin_counts + p.fin_counts_off[g];
+        for (int i = tid; i < 5 * gb; i += FB_FIN_THREADS)
+            if (scnt[i]) atomicAdd(&gc[i], scnt[i]);
+        if (tid == 0 && s_disc) atomicAdd(&p.discarded[g], s_disc);
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = atomicAdd(&p.tickets[g], 1) == (int)gridDim.y - 1;
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        cnt = gc;
+    } else if (tid == 0) {
+        p.discarded[g] = s_disc;
+    }
+    // computeSequence(1), figbird.cpp:1989-2045: first strict maximum above 0, 'N' where no read was counted
+    char* out = p.filled + p.filled_off[g];
+    for (int i = tid; i < gb; i += FB_FIN_THREADS) {
+        int mx = 0, idx = -1;
+#pragma unroll
+        for (int q = 0; q < 5; q++) {
+            const int v = gridDim.y > 1 ? __ldcg(cnt + i * 5 + q) : cnt[i * 5 + q];
+            if (v > mx) { mx = v; idx = q; }
+        }
+        out[i] = idx < 0 ? 'N' : "ACGTN"[idx];
     }
 }
 
@@ -813,7 +925,18 @@ __global__ void fb_flag_wait_kernel(FbFlagParams p) {
     }
 }
 
+// Test tap: the device's log / pow(10, .) applied element-wise (tests compare the bits with the host libm).
+__global__ void fb_devmath_kernel(const double* __restrict__ in, double* __restrict__ out, long n, int what) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        out[i] = what == 0 ? fbm_log(in[i]) : fbm_pow10(in[i]);
+}
+
 }  // namespace
+
+cudaError_t fb_launch_devmath(const double* in, double* out, long n, int what, cudaStream_t s) {
+    fb_devmath_kernel<<<1184, 256, 0, s>>>(in, out, n, what);
+    return cudaGetLastError();
+}
 
 cudaError_t fb_launch_flag_signal(const FbFlagParams& p, cudaStream_t s) {
     fb_flag_signal_kernel<<<1, 32, 0, s>>>(p);
@@ -829,6 +952,19 @@ size_t fb_em_smem_bytes(int nr_stride, int gp_stride, int p_stride, int chunk, i
     return em_carve(nullptr, nullptr, nr_stride, gp_stride, p_stride, chunk, pwin, global_tables);
 }
 
+// The EM kernel's variants: tables in shared or global memory (GT), one CTA or a thread-block cluster per unit (CLU),
+// 512 or 1024 threads per CTA (NT), linear or log-domain scores (F1).
+using EmKernel = void (*)(const FbEmParams);
+static EmKernel em_variant(bool gt, bool clu, int threads, bool f1) {
+    if (clu) return f1 ? fb_em_kernel<false, true, 512, true> : fb_em_kernel<false, true, 512, false>;
+    if (threads == 1024) {
+        if (gt) return f1 ? fb_em_kernel<true, false, 1024, true> : fb_em_kernel<true, false, 1024, false>;
+        return f1 ? fb_em_kernel<false, false, 1024, true> : fb_em_kernel<false, false, 1024, false>;
+    }
+    if (gt) return f1 ? fb_em_kernel<true, false, 512, true> : fb_em_kernel<true, false, 512, false>;
+    return f1 ? fb_em_kernel<false, false, 512, true> : fb_em_kernel<false, false, 512, false>;
+}
+
 cudaError_t fb_kernels_init(int* max_smem_optin, int* sm_count) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -837,38 +973,25 @@ cudaError_t fb_kernels_init(int* max_smem_optin, int* sm_count) {
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(fb_em_kernel<false, false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, *max_smem_optin - 1024);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(fb_em_kernel<false, false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, *max_smem_optin - 1024);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(fb_em_kernel<false, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, *max_smem_optin - 1024);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(fb_em_kernel<true, false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, *max_smem_optin - 1024);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(fb_em_kernel<true, false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, *max_smem_optin - 1024);
-    if (e != cudaSuccess) return e;
+    for (int f1 = 0; f1 < 2; f1++) {
+        for (int v = 0; v < 5; v++) {
+            const bool gt = v == 3 || v == 4, clu = v == 2;
+            const int threads = (v == 1 || v == 4) ? 1024 : 512;
+            e = cudaFuncSetAttribute(em_variant(gt, clu, threads, f1 != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, *max_smem_optin - 1024);
+            if (e != cudaSuccess) return e;
+        }
+    }
     return cudaFuncSetAttribute(fb_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, *max_smem_optin - 8192);
 }
 
 // CTAs of the plain (non-cluster) EM kernel that fit one SM with `smem` bytes of dynamic shared memory: the static
 // shared memory of the kernel and the per-CTA system reserve are the runtime's to count.
-cudaError_t fb_em_ctas_per_sm(int threads, bool global_tables, size_t smem, int* n) {
-    if (threads == 1024) {
-        if (global_tables) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, fb_em_kernel<true, false, 1024>, 1024, smem);
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, fb_em_kernel<false, false, 1024>, 1024, smem);
-    }
-    if (global_tables) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, fb_em_kernel<true, false, 512>, FB_THREADS, smem);
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, fb_em_kernel<false, false, 512>, FB_THREADS, smem);
+cudaError_t fb_em_ctas_per_sm(int threads, bool global_tables, bool f1, size_t smem, int* n) {
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, em_variant(global_tables, false, threads, f1), threads == 1024 ? 1024 : FB_THREADS, smem);
 }
 
-cudaError_t fb_launch_em(const FbEmParams& p, int grid, int threads, bool global_tables, size_t smem, cudaStream_t s) {
-    if (threads == 1024) {
-        if (global_tables) fb_em_kernel<true, false, 1024><<<grid, 1024, smem, s>>>(p);
-        else fb_em_kernel<false, false, 1024><<<grid, 1024, smem, s>>>(p);
-    } else {
-        if (global_tables) fb_em_kernel<true, false, 512><<<grid, FB_THREADS, smem, s>>>(p);
-        else fb_em_kernel<false, false, 512><<<grid, FB_THREADS, smem, s>>>(p);
-    }
+cudaError_t fb_launch_em(const FbEmParams& p, int grid, int threads, bool global_tables, bool f1, size_t smem, cudaStream_t s) {
+    em_variant(global_tables, false, threads, f1)<<<grid, threads == 1024 ? 1024 : FB_THREADS, smem, s>>>(p);
     return cudaGetLastError();
 }
 
@@ -886,18 +1009,18 @@ static void cluster_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, i
     cfg->numAttrs = 1;
 }
 
-cudaError_t fb_em_max_clusters(int cluster, size_t smem, int* n) {
+cudaError_t fb_em_max_clusters(int cluster, bool f1, size_t smem, int* n) {
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr;
     cluster_config(&cfg, &attr, cluster, cluster, smem, nullptr);
-    return cudaOccupancyMaxActiveClusters(n, fb_em_kernel<false, true, 512>, &cfg);
+    return cudaOccupancyMaxActiveClusters(n, em_variant(false, true, 512, f1), &cfg);
 }
 
-cudaError_t fb_launch_em_cluster(const FbEmParams& p, int n_clusters, int cluster, size_t smem, cudaStream_t s) {
+cudaError_t fb_launch_em_cluster(const FbEmParams& p, int n_clusters, int cluster, bool f1, size_t smem, cudaStream_t s) {
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr;
     cluster_config(&cfg, &attr, n_clusters * cluster, cluster, smem, s);
-    return cudaLaunchKernelEx(&cfg, fb_em_kernel<false, true, 512>, p);
+    return cudaLaunchKernelEx(&cfg, em_variant(false, true, 512, f1), p);
 }
 
 cudaError_t fb_launch_finalize(const FbFinParams& p, int n, int slices, size_t smem, cudaStream_t s) {

@@ -225,7 +225,7 @@ int main(int argc, char* argv[]) {
         int rc = api.create(&m, device + k, &ctxs[k]);
         if (rc != FB_OK) {
             printf("figbird: fb_create failed on device %d: %s%s\n", device + k, api.status_str(rc),
-                   rc == FB_EUNSUPPORTED ? " (only f=0, the mode GapProber.py uses, runs on the GPU)" : "");
+                   rc == FB_EUNSUPPORTED ? " (f must be 0 or 1)" : "");
             return 1;
         }
     }

@@ -86,7 +86,7 @@ ABI_SYMBOLS = [
     "fb_run_device", "fb_result", "fb_estimate_liks", "fb_best_string", "fb_dump_profile", "fb_get_stats",
     "fb_clear_gaps", "fb_gap_range", "fb_last_error", "fb_status_str", "fb_abi_version",
     "fb_set_partition_records", "fb_shard_sizes", "fb_shard_buffers", "fb_shard_scan_iter", "fb_shard_scan_finish", "fb_shard_scan_all",
-    "fb_shard_counts", "fb_shard_reset", "fb_measure_smem_peak", "fb_ipc_export", "fb_ipc_open", "fb_ipc_close",
+    "fb_shard_counts", "fb_shard_reset", "fb_measure_smem_peak", "fb_devmath_eval", "fb_ipc_export", "fb_ipc_open", "fb_ipc_close",
 ]
 
 _lib = None
@@ -145,6 +145,7 @@ def load_library():
     L.fb_shard_counts.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_double)]
     L.fb_shard_reset.argtypes = [vp]
     L.fb_measure_smem_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    L.fb_devmath_eval.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_long]
     L.fb_ipc_export.argtypes = [vp, vp, C.c_char_p]
     L.fb_ipc_open.argtypes = [vp, C.c_char_p, dpp]
     L.fb_ipc_close.argtypes = [vp, vp]
@@ -170,6 +171,17 @@ def measure_smem_peak(device=0):
     if rc != FB_OK:
         raise FigbirdError(rc, "fb_measure_smem_peak")
     return v.value
+
+
+def device_math(what, x, device=0):
+    """The device's restatement of glibc's log ("log") or pow(10, .) ("pow10") applied to an array (parity tap)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    dp = C.POINTER(C.c_double)
+    rc = load_library().fb_devmath_eval(int(device), {"log": 0, "pow10": 1}[what], x.ctypes.data_as(dp), out.ctypes.data_as(dp), x.size)
+    if rc != FB_OK:
+        raise FigbirdError(rc, "fb_devmath_eval")
+    return out
 
 
 def gap_range(original_gap):

@@ -28,7 +28,8 @@ typedef enum fb_status {
     FB_ECUDA = -3,    /* CUDA runtime error or no device; fb_last_error() has the text                 */
     FB_ENOMEM = -4,
     FB_ESTATE = -5,   /* call out of order (e.g. fb_result before fb_run)                              */
-    FB_EUNSUPPORTED = -6 /* f_mode != 0: the log-domain variant (figbird.cpp:1814-1815) is not on the GPU yet */
+    FB_EUNSUPPORTED = -6 /* f_mode other than 0 / 1; f_mode 1 with the record-sharded partition; a host libm whose log() */
+                         /* is not monotone around the finalize cut-off (see fb_create)                               */
 } fb_status;
 
 /* Constant inputs of the hot path = outputs of the reference's preamble (figbird.cpp:475-823,
@@ -46,7 +47,8 @@ typedef struct fb_model {
     int gap_prob_cutoff;       /* gapProbCutOff                  figbird.cpp:2778 */
     int max_distance;
     int num_iter;
-    int f_mode;
+    int f_mode;                /* argv[2] of figbird: 0 linear-domain scores (what GapProber.py passes), 1 log-domain   */
+                               /* (what run_EM_eval.sh passes): log() per term, pow(10, score) into the counts          */
 } fb_model;
 
 /* One (anchor, unmapped mate) line pair of Gaps/gaps_<n>.sam, as placeReads parses it
@@ -209,6 +211,11 @@ int fb_best_string(fb_ctx* ctx, int gap, char* buf, int cap);         /* bestStr
 int fb_dump_profile(fb_ctx* ctx, int gap, int estimate, double* probs, double* counts);
 
 int fb_get_stats(fb_ctx* ctx, fb_stats* out);
+/* Parity tap for the C-library functions on the path: the device's restatement of the host glibc's log (what = 0) and
+ * pow(10, .) (what = 1) applied to n doubles.  The reference calls log() on every record's best score
+ * (figbird.cpp:1951-1955) and, in f=1 mode, log() per base term and pow(10, s) per placement (figbird.cpp:1856, 1878);
+ * tests compare these results with the host libm bit for bit. */
+int fb_devmath_eval(int device, int what, const double* in, double* out, long n);
 /* Measurement aid (no counterpart in the reference): shared-memory read bandwidth of `device` in GB/s, measured with
  * conflict-free 128-bit loads on every SM — the roof that binds the E-step; bench.py reports against it. */
 int fb_measure_smem_peak(int device, double* gbs);

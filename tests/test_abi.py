@@ -66,12 +66,14 @@ def test_no_cpu_fallback(built):
     assert e.value.status == -3     # FB_ECUDA
 
 
-def test_log_mode_is_refused_not_emulated(built):
-    """f=1 (figbird.cpp:1814-1815) is not on the GPU yet: fb_create must say so (FB_EUNSUPPORTED) before touching CUDA."""
+def test_unknown_mode_is_refused(built):
+    """f may be 0 or 1 (figbird.cpp:2578, 1814-1815); anything else is refused before CUDA is touched."""
     import golden_lib as G
     from gapprober_b200 import FigbirdContext, FigbirdError
+    m = G.Case("logmode_f1").figbird_model()
+    m.f_mode = 2
     with pytest.raises(FigbirdError) as e:
-        FigbirdContext(G.Case("logmode_f1").figbird_model())
+        FigbirdContext(m)
     assert e.value.status == -6
 
 

@@ -14,16 +14,17 @@ pytestmark = pytest.mark.gpu
 ARGS = ["--genome", "150000", "--scaffolds", "3", "--gap-list", "60,120,250,90,400,33", "--cov", "40", "--ins-mean", "180", "--ins-sd", "20", "--err", "0.01"]
 
 
-def test_dropin_outputs_equal_reference(built, tmp_path):
+@pytest.mark.parametrize("f", [" 0", " 1"])     # argv[2]: 0 is what GapProber.py passes, 1 what run_EM_eval.sh passes (log-domain scores)
+def test_dropin_outputs_equal_reference(built, tmp_path, f):
     if not refrun.have_ref():
         pytest.skip("oracle/_ref binaries not built")
     from gapprober_b200 import build, synth
     a, b = str(tmp_path / "ours"), str(tmp_path / "ref")
     synth.generate(a, ARGS, seed=31)
     shutil.copytree(a, b)
-    ours = subprocess.run([build.build_host(), "scaffolds.fa", " 0", "250"], cwd=a, stdout=subprocess.PIPE, text=True)
+    ours = subprocess.run([build.build_host(), "scaffolds.fa", f, "250"], cwd=a, stdout=subprocess.PIPE, text=True)
     assert ours.returncode == 0, ours.stdout
-    ref = subprocess.run([refrun.REF_FIGBIRD, "scaffolds.fa", " 0", "250"], cwd=b, stdout=subprocess.PIPE, text=True, check=True)
+    ref = subprocess.run([refrun.REF_FIGBIRD, "scaffolds.fa", f, "250"], cwd=b, stdout=subprocess.PIPE, text=True, check=True)
     for f in ("gapout.txt", "filledContigs.fa", "mappedInserts.txt"):
         assert filecmp.cmp(os.path.join(a, f), os.path.join(b, f), shallow=False), f
     strip = lambda s: [ln for ln in s.splitlines() if not ln.startswith("Total time to fill gaps")]

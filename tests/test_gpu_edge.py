@@ -239,7 +239,21 @@ def test_kernel_variants_agree_bit_for_bit(built):
         ref = _fill_with_env(case, gaps, {"FB_CLUSTER": "1", "FB_THREADS1": "512"})
         for g, r in zip(gaps, ref):
             assert r[0] == g["filled"] and r[1] == g["best_est"] and r[2] == np.asarray(g["liks"]).tobytes()
+        # FB_HOST_LOG=1: per-record maxima to the host, log() and the record-order sum by the host libm (the round-1 route)
+        # instead of the device's restatement of glibc's log — the likelihood bits must not depend on who takes the log
         for env in ({"FB_CLUSTER": "2"}, {"FB_CLUSTER": "4"}, {"FB_CLUSTER": "1"}, {"FB_CLUSTER": "4", "FB_CHUNK": "8"},
                     {"FB_NO_COMPACT": "1"}, {"FB_NO_COMPACT": "1", "FB_CLUSTER": "2"},
-                    {"FB_CLUSTER": "1", "FB_CHUNK": "32"}, {"FB_CLUSTER": "2", "FB_CHUNK": "5"}):
+                    {"FB_CLUSTER": "1", "FB_CHUNK": "32"}, {"FB_CLUSTER": "2", "FB_CHUNK": "5"},
+                    {"FB_HOST_LOG": "1"}, {"FB_HOST_LOG": "1", "FB_CLUSTER": "4"}):
             assert _fill_with_env(case, gaps, env) == ref, (name, env)
+
+
+def test_log_mode_variants_agree_bit_for_bit(built):
+    """f=1 (log-domain scores): cluster sizes, chunk sizes and the host-libm likelihood route give the golden bits."""
+    case = G.Case("logmode_f1")
+    gaps = case.gaps
+    ref = _fill_with_env(case, gaps, {"FB_CLUSTER": "1"})
+    for g, r in zip(gaps, ref):
+        assert r[0] == g["filled"] and r[1] == g["best_est"] and r[2] == np.asarray(g["liks"]).tobytes()
+    for env in ({"FB_CLUSTER": "2"}, {"FB_CLUSTER": "4", "FB_CHUNK": "8"}, {"FB_HOST_LOG": "1"}, {"FB_NO_COMPACT": "1", "FB_CLUSTER": "2"}):
+        assert _fill_with_env(case, gaps, env) == ref, env

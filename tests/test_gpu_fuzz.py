@@ -27,7 +27,8 @@ def _draw(seed):
     return args
 
 
-# FB_FUZZ_CASES=<n> widens the sweep (the default 8 keep the suite short)
+# FB_FUZZ_CASES=<n> widens the sweep (the default 8 keep the suite short); every third case runs the reference's
+# log-domain mode (argv[2] = 1: log() per base term, pow(10, score) into the counts)
 @pytest.mark.parametrize("seed", range(int(os.environ.get("FB_FUZZ_CASES", "8"))))
 def test_random_case_matches_reference(seed, built, tmp_path):
     if not refrun.have_ref():
@@ -35,10 +36,12 @@ def test_random_case_matches_reference(seed, built, tmp_path):
     from gapprober_b200 import FigbirdContext, FigbirdModel, build, synth
     wd = str(tmp_path / f"fuzz{seed}")
     args = _draw(seed)
+    f_mode = 1 if seed % 3 == 2 else 0
     synth.generate(wd, args, seed=500 + seed)
-    ref = refrun.run_reference(wd, dump_probs=False)
+    ref = refrun.run_reference(wd, dump_probs=False, f_mode=f_mode)
     model = FigbirdModel.load(build.learn_model(wd, out="mine.bin"))           # host preamble ...
     assert open(os.path.join(wd, "mine.bin"), "rb").read() == open(os.path.join(wd, "fb_model.bin"), "rb").read(), args   # ... equals the reference's model
+    model.f_mode = f_mode
     with FigbirdContext(model) as fb:
         gfs = fb.add_workdir(wd)
         fb.fillGaps()
@@ -46,7 +49,31 @@ def test_random_case_matches_reference(seed, built, tmp_path):
             d = ref["dump"][f"Gaps/gaps_{gi}.sam"]
             r = gf.result()
             want = np.array([d["est"][e] for e in range(r["gap_min"], r["gap_max"] + 1)])
-            assert np.array_equal(gf.estimateLikelihoods(), want), (args, gi)
+            assert np.array_equal(gf.estimateLikelihoods(), want, equal_nan=True), (args, f_mode, gi)
+            assert r["best_estimate"] == d["best"][0] and gf.bestString().decode() == d["best"][2], (args, f_mode, gi)
+            assert r["filled"].decode() == ref["gapout"][gi]["filled"], (args, f_mode, gi)
+
+
+@pytest.mark.parametrize("seed", range(100, 100 + int(os.environ.get("FB_FUZZ_F1_CASES", "3"))))
+def test_random_case_log_mode_matches_reference(seed, built, tmp_path):
+    """f=1 only (FB_FUZZ_F1_CASES widens it): per-estimate likelihoods, winner, bestString and fill against the reference binary."""
+    if not refrun.have_ref():
+        pytest.skip("oracle/_ref binaries not built")
+    from gapprober_b200 import FigbirdContext, FigbirdModel, build, synth
+    wd = str(tmp_path / f"f1_{seed}")
+    args = _draw(seed)
+    synth.generate(wd, args, seed=500 + seed)
+    ref = refrun.run_reference(wd, dump_probs=False, f_mode=1)
+    model = FigbirdModel.load(build.learn_model(wd, out="mine.bin"))
+    model.f_mode = 1
+    with FigbirdContext(model) as fb:
+        gfs = fb.add_workdir(wd)
+        fb.fillGaps()
+        for gi, gf in enumerate(gfs):
+            d = ref["dump"][f"Gaps/gaps_{gi}.sam"]
+            r = gf.result()
+            want = np.array([d["est"][e] for e in range(r["gap_min"], r["gap_max"] + 1)])
+            assert np.array_equal(gf.estimateLikelihoods(), want, equal_nan=True), (args, gi)
             assert r["best_estimate"] == d["best"][0] and gf.bestString().decode() == d["best"][2], (args, gi)
             assert r["filled"].decode() == ref["gapout"][gi]["filled"], (args, gi)
 
