@@ -75,6 +75,7 @@ struct HostGap {
     double cost = 0;
     // results
     bool done = false;
+    bool no_winner = false;   // no estimate's likelihood passed 'likelihood >= maxLikelihood' (all -inf / NaN; f=1 only): bestString stays empty
     int best_est = 0;
     double best_lik = 0;
     int total_reads = 0, discarded = 0;
@@ -1423,21 +1424,27 @@ int fb_run_finalize(fb_ctx* c) {
         if (!g.owned) continue;
         double best = -DBL_MAX;
         int be = g.gmin;
+        bool any = false;
         for (int gp = g.gmin; gp <= g.gmax; gp++) {
             const double l = g.liks[gp - g.gmin];
             if (std::isnan(l) && g.cons_off[gp - g.gmin] < 0)
                 return c->fail(FB_ESTATE, "gap %zu: estimate %d was scanned by another rank and its likelihood has not been merged", gi, gp);
-            if (l >= best) {   // last estimate wins ties; a NaN likelihood (f=1 only) never wins, as in the reference
+            if (l >= best) {   // last estimate wins ties; a NaN or -inf likelihood (f=1 only) never wins, as in the reference
                 best = l;
                 be = gp;
+                any = true;
             }
         }
         g.best_lik = best;
         g.best_est = be;
+        // f=1 can leave every estimate at -inf (two records without a placement in the window already do): then no
+        // estimate ever passes the '>=' of figbird.cpp:2479, maxGapEstimate stays gapMin and bestString stays empty —
+        // finalize scores against flank + gapMin non-bases + flank
+        g.no_winner = !any;
         bestgp[gi] = be;
         if (g.cons_off[be - g.gmin] < 0) continue;   // the winner lives on another rank: that rank finalizes this gap
         if (c->rec_mode && (int)(gi % c->part_world) != c->part_rank) continue;   // every rank could; the gaps are dealt round-robin
-        cons_off_of_best[gi] = g.cons_off[be - g.gmin];
+        cons_off_of_best[gi] = any ? g.cons_off[be - g.gmin] : -1;
         gaplist.push_back((int)gi);
     }
 
@@ -1876,6 +1883,10 @@ int fb_best_string(fb_ctx* c, int gap, char* buf, int cap) {
     const HostGap& g = c->gaps[gap];
     if (!c->ran || !g.done) return c->fail(FB_ESTATE, "gap %d has no result in this context", gap);
     if (cap < g.best_est + 1) return FB_EINVAL;
+    if (g.no_winner) {      // bestString was never assigned (see fb_run_finalize)
+        buf[0] = 0;
+        return FB_OK;
+    }
     FB_CUDA(c, cudaSetDevice(c->device));
     for (size_t ui = 0; ui < c->h_units.size(); ui++) {
         const FbUnit& u = c->h_units[ui];

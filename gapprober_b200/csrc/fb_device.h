@@ -120,7 +120,7 @@ struct FbFinParams {
     const FbRecMeta* rmeta;
     const int* gap_list;    // gaps to finalize in this launch
     const int* best_gp;     // [n_gaps] winning estimate
-    const long long* best_cons_off;  // [n_gaps] offset of the winning consensus in unit_cons
+    const long long* best_cons_off;  // [n_gaps] offset of the winning consensus in unit_cons; -1: no winner, empty bestString
     const char* unit_cons;
     int gmax_stride;        // smem bytes for the gap string
     int gb_stride;          // smem rows of the per-CTA counts (largest winning estimate of the launch)

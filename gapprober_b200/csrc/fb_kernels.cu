@@ -762,7 +762,8 @@ __global__ void __launch_bounds__(FB_FIN_THREADS) fb_finalize_kernel(const FbFin
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int R0 = D - lmax + 1, NR = gb + 2 * lmax - 2;
     const uint8_t* fl = p.flank + (size_t)g * 2 * D;
-    const char* best = p.unit_cons + p.best_cons_off[g];
+    const long long boff = p.best_cons_off[g];        // < 0: no estimate won, bestString is empty (non-bases throughout)
+    const char* best = p.unit_cons + (boff < 0 ? 0 : boff);
     if (tid < 25) sT[tid] = p.T[tid];
     if (tid == 0) { s_disc = 0; s_last = 0; }
     for (int i = tid; i < 5 * gb; i += FB_FIN_THREADS) scnt[i] = 0;
@@ -771,7 +772,7 @@ __global__ void __launch_bounds__(FB_FIN_THREADS) fb_finalize_kernel(const FbFin
         if (x < D) c = fl[x];
         else if (x >= D + gb) c = fl[D + (x - D - gb)];
         else {
-            char ch = best[x - D];
+            const char ch = boff < 0 ? 'N' : best[x - D];
             c = ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 4;
         }
         gcode[xr] = (uint8_t)c;
