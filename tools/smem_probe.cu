@@ -2,11 +2,14 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o smem_probe tools/smem_probe.cu && ./smem_probe
 // Prints, per access pattern, shared-memory load instructions per clock and SM and useful GB/s:
 //   lds128 all lanes / lanes < 8 / lanes < 16 / every 4th lane   — does a partly predicated LDS.128 cost fewer wavefronts?
-//   lds64 all lanes, lds64 stride-2 (2-way conflict), shfl.64 (2 x SHFL)  — candidates for the M-step's score reads
+//   lds64 all lanes, lds64 stride-2 (2-way conflict)  — candidates for the M-step's score reads
+// (the clock64 column runs at half the SM clock on this part: read the GB/s column)
 #include <cstdio>
 #include <cuda_runtime.h>
 
 constexpr int kThreads = 1024, kSlots = 4096;
+
+
 
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 2) probe(uint4* sink, int iters, long long* cycles) {
@@ -36,9 +39,6 @@ __global__ void __launch_bounds__(kThreads, 2) probe(uint4* sink, int iters, lon
             } else if (MODE == 5) {            // LDS.64, lanes 16 bytes apart (2-way bank conflict)
                 const uint2 v = reinterpret_cast<const uint2*>(buf)[(2 * at + u * 96u) & (2 * kSlots - 1)];
                 acc.x ^= v.x; acc.y ^= v.y;
-            } else {                           // 64-bit shuffle from the lane below
-                acc.x ^= __shfl_up_sync(0xffffffffu, acc.z + u, 1);
-                acc.y ^= __shfl_up_sync(0xffffffffu, acc.w + u, 1);
             }
         }
         at += 1536u + (acc.x & 32u);
@@ -92,6 +92,5 @@ int main() {
     run<3>("LDS.128 every 4th lane", sms, 16, 0.25);
     run<4>("LDS.64 all lanes, contiguous", sms, 8, 1.0);
     run<5>("LDS.64 all lanes, 16 B apart", sms, 8, 1.0);
-    run<6>("SHFL x2 (64-bit shuffle)", sms, 8, 1.0);
     return 0;
 }
