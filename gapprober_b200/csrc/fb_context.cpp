@@ -205,7 +205,21 @@ struct fb_ctx {
     DevBuf<char> d_cons;
     DevBuf<int> d_gaplist, d_bestgp;
     DevBuf<long long> d_bestoff, d_filled_off;
-    DevBuf<double> d_unit_lik;
+    DevBuf<double> d_unit_lik, d_best_lik;
+    DevBuf<int> d_sel_off, d_sel_unit, d_gmin;
+    std::vector<int> h_sel_off, h_sel_unit, h_gmin;
+    // one-call pass (fb_run_device without a partition that needs a host exchange): everything is enqueued at once —
+    // scan, selection, finalize, copies — and the host waits once.  The finalize geometry is fixed at upload from the
+    // largest estimates, not from the winners.
+    bool fused_ok = false;
+    bool fused_dirty = false;    // fb_run_finalize has overwritten the gap list / offsets the one-call pass keeps on the device
+    std::vector<int> fin_gaplist, fin_counts_off;
+    std::vector<long long> fin_filled_off;
+    int fin_slices = 1, fin_rows = 0, fin_gbmax = 1;
+    size_t fin_smem = 0, fin_counts_total = 0, fin_fill_total = 0;
+    PinBuf<double> h_best_lik;
+    PinBuf<int> h_best_gp;
+    PinBuf<long long> h_best_off;
     DevBuf<int> d_fin_counts, d_fin_counts_off, d_tickets, d_discarded;
     DevBuf<char> d_filled;
     PinBuf<double> h_maxprob, h_unit_lik;
@@ -383,6 +397,8 @@ void fb_destroy(fb_ctx* c) {
     c->d_sumcounts.release(); c->d_maxmerge.release(); c->d_unit_nrec.release(); c->d_shard_err.release(); c->d_flags.release();
     c->h_maxprob.release(); c->h_stage.release();
     c->d_ild_em.release(); c->d_filled_off.release(); c->d_unit_lik.release(); c->d_fin_counts.release(); c->d_fin_counts_off.release();
+    c->d_best_lik.release(); c->d_sel_off.release(); c->d_sel_unit.release(); c->d_gmin.release();
+    c->h_best_lik.release(); c->h_best_gp.release(); c->h_best_off.release();
     c->d_tickets.release(); c->d_discarded.release(); c->d_filled.release(); c->h_unit_lik.release(); c->h_discarded.release(); c->h_filled.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -501,9 +517,79 @@ void pack_gap(const PackConsts& k, int contig_no, long gap_start, int orig_gap, 
     }
 }
 
-// placeReads' parse of one gap file (figbird.cpp:1718-1801), then pack.
+// atoi on a token that is not NUL-terminated: blanks, an optional sign, digits (what the reference's atoi sees).
+inline int tok_atoi(const char* p, const char* e) {
+    while (p < e && (*p == ' ' || (*p >= '\t' && *p <= '\r'))) p++;
+    bool neg = false;
+    if (p < e && (*p == '+' || *p == '-')) neg = *p++ == '-';
+    long v = 0;
+    while (p < e && *p >= '0' && *p <= '9') v = v * 10 + (*p++ - '0');
+    return (int)(neg ? -v : v);
+}
+
+// strtok(line, "\t") over [p, e): the k-th token (0-based) as [*tb, *te); runs of tabs count once, a leading run is
+// skipped, the line's '\n' belongs to the last token.  false when the line has fewer tokens.
+inline bool nth_token(const char* p, const char* e, int k, const char** tb, const char** te) {
+    for (int t = 0;; t++) {
+        while (p < e && *p == '\t') p++;
+        if (p >= e) return false;
+        const char* q = (const char*)memchr(p, '\t', (size_t)(e - p));
+        if (!q) q = e;
+        if (t == k) { *tb = p; *te = q; return true; }
+        p = q;
+    }
+}
+
+// placeReads' parse of one gap file (figbird.cpp:1718-1801), then pack.  The file is read in one go and cut at its
+// newlines; the columns are found the way the reference's fgets + strtok("\t") finds them.  A line of 1023 bytes or
+// more (which the reference's 1024-byte fgets would split) sends the whole file down the literal fgets/strtok route.
+void parse_and_pack_slow(const PackConsts& k, int contig_no, long gap_start, int orig_gap, const char* contig, long contig_len,
+                         const char* gap_file, PackedGap& out);
+
 void parse_and_pack(const PackConsts& k, int contig_no, long gap_start, int orig_gap, const char* contig, long contig_len,
                     const char* gap_file, PackedGap& out) {
+    FILE* fp = gap_file ? fopen(gap_file, "rb") : nullptr;
+    if (!fp) return pack_fail(out, FB_EINVAL, "cannot open %s", gap_file ? gap_file : "(null)");
+    std::string text;
+    {
+        char buf[1 << 16];
+        size_t n;
+        while ((n = fread(buf, 1, sizeof buf, fp)) > 0) text.append(buf, n);
+    }
+    fclose(fp);
+    struct Line { const char *b, *e; };
+    std::vector<Line> lines;
+    const char* p = text.data();
+    const char* end = p + text.size();
+    while (p < end) {
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+        const char* e = nl ? nl + 1 : end;
+        if (e - p >= 1023 || memchr(p, 0, (size_t)(e - p))) return parse_and_pack_slow(k, contig_no, gap_start, orig_gap, contig, contig_len, gap_file, out);
+        lines.push_back({p, e});
+        p = e;
+    }
+    std::vector<fb_record> recs;
+    std::vector<std::pair<const char*, int>> seqs;
+    for (size_t i = 0; i < lines.size(); i++) {
+        if (lines[i].b[0] == '@') continue;                       // figbird.cpp:1720
+        if (i + 1 >= lines.size()) break;                         // the second fgets fails: placeReads stops
+        const Line l1 = lines[i], l2 = lines[++i];
+        const char *fb_, *fe, *pb, *pe, *sb, *se, *mb, *me;
+        if (!nth_token(l1.b, l1.e, 1, &fb_, &fe) || !nth_token(l1.b, l1.e, 3, &pb, &pe) || !nth_token(l1.b, l1.e, 6, &sb, &se)) continue;
+        if (!nth_token(l2.b, l2.e, 6, &mb, &me)) continue;
+        fb_record r;
+        r.strand1 = (tok_atoi(fb_, fe) & 16) >> 4;
+        r.pos1 = tok_atoi(pb, pe);
+        r.len1 = (int)(se - sb);
+        r.seq2 = mb;
+        r.len2 = (int)(me - mb);
+        recs.push_back(r);
+    }
+    pack_gap(k, contig_no, gap_start, orig_gap, contig, contig_len, recs.data(), (int)recs.size(), out);
+}
+
+void parse_and_pack_slow(const PackConsts& k, int contig_no, long gap_start, int orig_gap, const char* contig, long contig_len,
+                         const char* gap_file, PackedGap& out) {
     FILE* fp = gap_file ? fopen(gap_file, "r") : nullptr;
     if (!fp) return pack_fail(out, FB_EINVAL, "cannot open %s", gap_file ? gap_file : "(null)");
     std::vector<fb_record> recs;
@@ -970,10 +1056,13 @@ int plan_units(fb_ctx* c, Trace& tr, long long& mp_out, long long& co_out) {
     // of two: persistent CTAs pull the heaviest units first, finer than that does not change the balance), inside a
     // class in (gap, estimate) order.  One counting sort over the units as the gaps planned them — a gap set of
     // chr14's size has several hundred thousand units.
+    // Both passes run on the host threads: the gaps are cut into contiguous slices, every slice counts its units per key,
+    // a serial prefix over (key, slice) gives every slice its place inside every key (slices in gap order, so the result
+    // is the serial sort's), and the slices scatter.  The running offsets of the unit array (per-record maxima, consensus
+    // bytes) are a prefix sum along the sorted order: per-slice sums, a serial prefix over the slices, then the fill.
     std::vector<U> us;
+    const int kKeys = 16 * 384;
     {
-        const int kKeys = 16 * 384;
-        std::vector<size_t> start(kKeys + 1, 0);
         for (size_t gi = 0; gi < c->gaps.size(); gi++) {
             if (!c->gaps[gi].owned) continue;
             st.n_gaps++;
@@ -981,14 +1070,31 @@ int plan_units(fb_ctx* c, Trace& tr, long long& mp_out, long long& co_out) {
             st.likelihoods += per_gap[gi].liks;
             st.base_terms += per_gap[gi].terms;
             st.algorithmic_bytes += per_gap[gi].bytes;
-            for (const U& u : per_gap[gi].us) start[u.key + 1]++;
         }
-        for (int k = 0; k < kKeys; k++) start[k + 1] += start[k];
-        us.resize(start[kKeys]);
-        for (size_t gi = 0; gi < c->gaps.size(); gi++) {
-            if (!c->gaps[gi].owned) continue;
-            for (const U& u : per_gap[gi].us) us[start[u.key]++] = u;
-        }
+        const int ng = (int)c->gaps.size();
+        const int S = std::max(1, std::min(16, ng / 64));            // slices of gaps
+        std::vector<std::vector<size_t>> cnt((size_t)S, std::vector<size_t>(kKeys, 0));
+        auto slice_lo = [&](int sl) { return (int)((long)ng * sl / S); };
+        parallel_for(S, 0, [&](int sl) {
+            std::vector<size_t>& h = cnt[sl];
+            for (int gi = slice_lo(sl); gi < slice_lo(sl + 1); gi++)
+                if (c->gaps[gi].owned)
+                    for (const U& u : per_gap[gi].us) h[u.key]++;
+        });
+        size_t run = 0;
+        for (int k = 0; k < kKeys; k++)
+            for (int sl = 0; sl < S; sl++) {
+                const size_t n = cnt[sl][k];
+                cnt[sl][k] = run;
+                run += n;
+            }
+        us.resize(run);
+        parallel_for(S, 0, [&](int sl) {
+            std::vector<size_t>& at = cnt[sl];
+            for (int gi = slice_lo(sl); gi < slice_lo(sl + 1); gi++)
+                if (c->gaps[gi].owned)
+                    for (const U& u : per_gap[gi].us) us[at[u.key]++] = u;
+        });
     }
     st.n_units = (long)us.size();
     tr.lap("upload:   sort");
@@ -996,30 +1102,79 @@ int plan_units(fb_ctx* c, Trace& tr, long long& mp_out, long long& co_out) {
     c->unit_nrec.resize(us.size());
     c->bins.clear();
     long long mp = 0, co = 0;
-    for (size_t i = 0; i < us.size(); i++) {
-        FbUnit u;
-        u.gap = us[i].gap;
-        u.gp = us[i].gp;
-        u.mp_off = mp;
-        u.cons_off = co;
-        u.hole_lo = us[i].hole_lo;
-        u.hole_len = us[i].hole_len;
-        mp += c->gaps[u.gap].nrec;
-        co += u.gp;
-        c->h_units[i] = u;
-        c->unit_nrec[i] = c->gaps[u.gap].nrec;
-        int b = bin_of(u.gp - u.hole_len);
-        if (c->bins.empty() || bin_of(c->h_units[c->bins.back().first_unit].gp - c->h_units[c->bins.back().first_unit].hole_len) != b) {
+    {
+        const size_t n = us.size();
+        const int S = (int)std::max<size_t>(1, std::min<size_t>(16, n / 4096));
+        auto lo_of = [&](int sl) { return n * (size_t)sl / (size_t)S; };
+        std::vector<long long> smp((size_t)S + 1, 0), sco((size_t)S + 1, 0);
+        parallel_for(S, 0, [&](int sl) {
+            long long a = 0, b = 0;
+            for (size_t i = lo_of(sl); i < lo_of(sl + 1); i++) {
+                a += c->gaps[us[i].gap].nrec;
+                b += us[i].gp;
+            }
+            smp[sl + 1] = a;
+            sco[sl + 1] = b;
+        });
+        for (int sl = 0; sl < S; sl++) {
+            smp[sl + 1] += smp[sl];
+            sco[sl + 1] += sco[sl];
+        }
+        mp = smp[S];
+        co = sco[S];
+        parallel_for(S, 0, [&](int sl) {
+            long long a = smp[sl], b = sco[sl];
+            for (size_t i = lo_of(sl); i < lo_of(sl + 1); i++) {
+                FbUnit u;
+                u.gap = us[i].gap;
+                u.gp = us[i].gp;
+                u.mp_off = a;
+                u.cons_off = b;
+                u.hole_lo = us[i].hole_lo;
+                u.hole_len = us[i].hole_len;
+                a += c->gaps[u.gap].nrec;
+                b += u.gp;
+                c->h_units[i] = u;
+                c->unit_nrec[i] = c->gaps[u.gap].nrec;
+            }
+        });
+        // bins = maximal runs of one size bin in the sorted order (the key's leading part); their extents by a scan of the runs
+        size_t i0 = 0;
+        while (i0 < n) {
+            const int b = bin_of(us[i0].gp - us[i0].hole_len);
+            size_t i1 = i0 + 1;
+            // keys of one bin are contiguous: binary search for the first unit of another bin
+            size_t lo = i0 + 1, hi = n;
+            while (lo < hi) {
+                const size_t mid = lo + (hi - lo) / 2;
+                if (bin_of(us[mid].gp - us[mid].hole_len) == b) lo = mid + 1;
+                else hi = mid;
+            }
+            i1 = lo;
             Bin nb;
             memset(&nb, 0, sizeof nb);
-            nb.first_unit = (int)i;
+            nb.first_unit = (int)i0;
+            nb.n_units = (int)(i1 - i0);
+            const int P = (int)std::max<size_t>(1, std::min<size_t>(16, (i1 - i0) / 4096));
+            std::vector<int> g1(P, 0), g2(P, 0), g3(P, 0);
+            parallel_for(P, 0, [&](int q) {
+                const size_t a = i0 + (i1 - i0) * (size_t)q / (size_t)P, e = i0 + (i1 - i0) * (size_t)(q + 1) / (size_t)P;
+                int m1 = 0, m2 = 0, m3 = 0;
+                for (size_t i = a; i < e; i++) {
+                    m1 = std::max(m1, us[i].gp - us[i].hole_len);
+                    m2 = std::max(m2, us[i].gp);
+                    m3 = std::max(m3, c->gaps[us[i].gap].lmax);
+                }
+                g1[q] = m1; g2[q] = m2; g3[q] = m3;
+            });
+            for (int q = 0; q < P; q++) {
+                nb.gpmax = std::max(nb.gpmax, g1[q]);
+                nb.gp_full = std::max(nb.gp_full, g2[q]);
+                nb.lmax = std::max(nb.lmax, g3[q]);
+            }
             c->bins.push_back(nb);
+            i0 = i1;
         }
-        Bin& bn = c->bins.back();
-        bn.n_units++;
-        bn.gpmax = std::max(bn.gpmax, u.gp - u.hole_len);
-        bn.gp_full = std::max(bn.gp_full, u.gp);
-        bn.lmax = std::max(bn.lmax, c->gaps[u.gap].lmax);
     }
     tr.lap("upload:   unit array");
     mp_out = mp;
@@ -1042,8 +1197,9 @@ int plan_bins(fb_ctx* c, int pwin, size_t& gws_need_out, Trace& tr) {
         int ctas = 2;
         // tuning knob: records per pipeline round (the M-step sets up one record per lane, so at most 32)
         const int pref = getenv("FB_CHUNK") ? std::max(1, std::min(32, atoi(getenv("FB_CHUNK")))) : 16;
+        const bool force_one = getenv("FB_ONE_CTA") && atoi(getenv("FB_ONE_CTA")) != 0;   // experiment knob: size for one CTA per SM
         for (int want : {pref, 8, 4}) {
-            if (want < 1) continue;
+            if (want < 1 || force_one) continue;
             const size_t need = fb_em_smem_bytes(b.nr_stride, b.gp_stride, b.p_stride, want, pwin, false);
             if (need > two_cta) continue;
             // the estimate above leaves 512 B for the kernel's static shared memory; ask the runtime whether two CTAs
@@ -1159,9 +1315,69 @@ int upload_buffers(fb_ctx* c, long long mp, long long co, size_t gws_need, Trace
     }
     if (gws_need) FB_CUDA(c, c->d_gws.ensure(gws_need));
     if (c->host_log || c->rec_mode) FB_CUDA(c, c->h_maxprob.ensure((size_t)mp));
+    // ---- selection map and finalize geometry of the one-call pass
+    c->fused_ok = !c->unit_mode && !c->rec_mode && !c->host_log;
+    c->fused_dirty = false;
+    if (c->fused_ok) {
+        c->h_sel_off.assign(ng + 1, 0);
+        c->h_gmin.assign(ng, 0);
+        for (size_t gi = 0; gi < ng; gi++) {
+            const HostGap& g = c->gaps[gi];
+            c->h_gmin[gi] = g.gmin;
+            c->h_sel_off[gi + 1] = c->h_sel_off[gi] + (g.owned ? g.gmax - g.gmin + 1 : 0);
+        }
+        c->h_sel_unit.assign((size_t)c->h_sel_off[ng], -1);
+        {
+            const size_t n = c->h_units.size();
+            const int S = (int)std::max<size_t>(1, std::min<size_t>(16, n / 8192));
+            parallel_for(S, 0, [&](int sl) {
+                for (size_t i = n * (size_t)sl / (size_t)S; i < n * (size_t)(sl + 1) / (size_t)S; i++) {
+                    const FbUnit& u = c->h_units[i];
+                    c->h_sel_unit[(size_t)c->h_sel_off[u.gap] + (size_t)(u.gp - c->gaps[u.gap].gmin)] = (int)i;
+                }
+            });
+        }
+        c->fin_gaplist.clear();
+        c->fin_counts_off.assign(ng, 0);
+        c->fin_filled_off.assign(ng, 0);
+        c->fin_rows = 0;
+        c->fin_gbmax = 1;
+        c->fin_fill_total = c->fin_counts_total = 0;
+        int max_nrec = 1;
+        for (size_t gi = 0; gi < ng; gi++) {
+            const HostGap& g = c->gaps[gi];
+            if (!g.owned) continue;
+            c->fin_gaplist.push_back((int)gi);
+            c->fin_rows = std::max(c->fin_rows, g.gmax + 2 * g.lmax);
+            c->fin_gbmax = std::max(c->fin_gbmax, g.gmax);
+            max_nrec = std::max(max_nrec, g.nrec);
+            c->fin_filled_off[gi] = (long long)c->fin_fill_total;
+            c->fin_fill_total += (size_t)std::max(g.gmax, 1);
+        }
+        const int per_cta = FB_FIN_THREADS / 32, nfin = std::max<int>(1, (int)c->fin_gaplist.size());
+        c->fin_slices = std::max(1, std::min((4 * c->sm_count + nfin - 1) / nfin, (max_nrec + per_cta - 1) / per_cta));
+        if (c->fin_slices > 1)
+            for (int gi : c->fin_gaplist) {
+                c->fin_counts_off[gi] = (int)c->fin_counts_total;
+                c->fin_counts_total += 5 * (size_t)c->gaps[gi].gmax;
+            }
+        c->fin_smem = sizeof(int) * 5 * (size_t)c->fin_gbmax + (size_t)c->fin_rows + 16;
+        if (c->fin_smem > (size_t)c->max_smem - 8192) c->fused_ok = false;     // the two-call route sizes finalize by the winners
+    }
+    if (c->fused_ok) {
+        FB_CUDA(c, c->d_sel_off.ensure(ng + 1));
+        FB_CUDA(c, c->d_sel_unit.ensure(c->h_sel_unit.size()));
+        FB_CUDA(c, c->d_gmin.ensure(ng));
+        FB_CUDA(c, c->d_best_lik.ensure(ng));
+        FB_CUDA(c, c->d_fin_counts.ensure(c->fin_counts_total));
+        FB_CUDA(c, c->h_best_lik.ensure(ng));
+        FB_CUDA(c, c->h_best_gp.ensure(ng));
+        FB_CUDA(c, c->h_best_off.ensure(ng));
+    }
     long h2d = 0;
     const size_t stage_need = ng * sizeof(FbGapMeta) + c->h_flank.size() + (c->h_codes.size() + c->h_nmask.size()) * sizeof(uint4) +
-                              nr * sizeof(FbRecMeta) + c->h_units.size() * sizeof(FbUnit) + 6 * 256;
+                              nr * sizeof(FbRecMeta) + c->h_units.size() * sizeof(FbUnit) + 12 * 256 +
+                              (c->fused_ok ? (c->h_sel_unit.size() + 4 * ng + 1) * sizeof(int) + ng * sizeof(long long) : 0);
     FB_CUDA(c, c->h_stage.ensure(stage_need));
     size_t stage_off = 0;
     auto up = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
@@ -1178,6 +1394,14 @@ int upload_buffers(fb_ctx* c, long long mp, long long co, size_t gws_need, Trace
     FB_CUDA(c, up(c->d_nmask.p, c->h_nmask.data(), c->h_nmask.size() * sizeof(uint4)));
     FB_CUDA(c, up(c->d_rmeta.p, c->h_rmeta.data(), nr * sizeof(FbRecMeta)));
     FB_CUDA(c, up(c->d_units.p, c->h_units.data(), c->h_units.size() * sizeof(FbUnit)));
+    if (c->fused_ok) {
+        FB_CUDA(c, up(c->d_sel_off.p, c->h_sel_off.data(), (ng + 1) * sizeof(int)));
+        FB_CUDA(c, up(c->d_sel_unit.p, c->h_sel_unit.data(), c->h_sel_unit.size() * sizeof(int)));
+        FB_CUDA(c, up(c->d_gmin.p, c->h_gmin.data(), ng * sizeof(int)));
+        FB_CUDA(c, up(c->d_gaplist.p, c->fin_gaplist.data(), c->fin_gaplist.size() * sizeof(int)));
+        FB_CUDA(c, up(c->d_filled_off.p, c->fin_filled_off.data(), ng * sizeof(long long)));
+        FB_CUDA(c, up(c->d_fin_counts_off.p, c->fin_counts_off.data(), ng * sizeof(int)));
+    }
     c->shard_counts = c->shard_maxprob = 0;
     if (c->rec_mode) {
         // the scan launches see only this rank's block of every gap; its maxima land at the block's place in the
@@ -1477,6 +1701,7 @@ int fb_run_finalize(fb_ctx* c) {
             pin += (bytes + 255) & ~size_t(255);
             return e;
         };
+        c->fused_dirty = true;
         FB_CUDA(c, up(c->d_gaplist.p, gaplist.data(), gaplist.size() * sizeof(int)));
         FB_CUDA(c, up(c->d_bestgp.p, bestgp.data(), ng * sizeof(int)));
         FB_CUDA(c, up(c->d_bestoff.p, cons_off_of_best.data(), ng * sizeof(long long)));
@@ -1813,7 +2038,148 @@ int fb_ipc_close(fb_ctx* c, void* dev_ptr) {
     return FB_OK;
 }
 
+// fillGap for every gap of this context in ONE enqueue: record tables, the EM scan of every size bin, the selection among
+// the estimates, finalize, and the copies home; the host waits once and then hands the results to the gaps.
+static int run_fused(fb_ctx* c) {
+    FB_CUDA(c, cudaSetDevice(c->device));
+    fb_stats& st = c->stats;
+    Trace tr;
+    const size_t ng = c->gaps.size(), nu = c->h_units.size();
+    st.em_launches = st.finalize_launches = 0;
+    st.finalize_likelihoods = 0;
+    if (c->fused_dirty) {
+        FB_CUDA(c, cudaMemcpyAsync(c->d_gaplist.p, c->fin_gaplist.data(), c->fin_gaplist.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        FB_CUDA(c, cudaMemcpyAsync(c->d_filled_off.p, c->fin_filled_off.data(), ng * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+        FB_CUDA(c, cudaMemcpyAsync(c->d_fin_counts_off.p, c->fin_counts_off.data(), ng * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        FB_CUDA(c, c->d_fin_counts.ensure(c->fin_counts_total));
+        FB_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->fused_dirty = false;
+    }
+    FB_CUDA(c, cudaEventRecord(c->evs, c->stream));
+    FB_CUDA(c, cudaMemsetAsync(c->d_counters.p, 0, sizeof(int) * (c->bins.size() + 1), c->stream));
+    FB_CUDA(c, cudaMemsetAsync(c->d_tickets.p, 0, sizeof(int) * 2 * ng, c->stream));
+    if (c->fin_counts_total) FB_CUDA(c, cudaMemsetAsync(c->d_fin_counts.p, 0, sizeof(int) * c->fin_counts_total, c->stream));
+    FB_CUDA(c, launch_stage(c, c->stream));
+    st.aux_launches = 1;
+    FB_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    for (size_t bi = 0; bi < c->bins.size(); bi++) {
+        FbEmParams p;
+        fill_bin_params(c, bi, p);
+        if (c->bins.size() == 1) {                       // a single launch needs no stream of its own
+            FB_CUDA(c, launch_bin(c, c->bins[bi], p, c->stream));
+        } else {
+            cudaStream_t bs = c->bin_streams[bi];
+            FB_CUDA(c, cudaStreamWaitEvent(bs, c->ev0, 0));
+            FB_CUDA(c, launch_bin(c, c->bins[bi], p, bs));
+            FB_CUDA(c, cudaEventRecord(c->bin_done[bi], bs));
+            FB_CUDA(c, cudaStreamWaitEvent(c->stream, c->bin_done[bi], 0));
+        }
+        st.em_launches++;
+    }
+    FB_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    long d2h = 0;
+    if (!c->fin_gaplist.empty()) {
+        FbSelParams sp;
+        sp.n_gaps = (int)ng;
+        sp.sel_off = c->d_sel_off.p;
+        sp.sel_unit = c->d_sel_unit.p;
+        sp.gmin = c->d_gmin.p;
+        sp.unit_lik = c->d_unit_lik.p;
+        sp.units = c->d_units.p;
+        sp.best_gp = c->d_bestgp.p;
+        sp.best_cons_off = c->d_bestoff.p;
+        sp.best_lik = c->d_best_lik.p;
+        FB_CUDA(c, fb_launch_select(sp, c->stream));
+        st.aux_launches++;
+        FbFinParams f;
+        memset(&f, 0, sizeof f);
+        f.ild = c->d_ild.p;
+        f.epos = c->d_epos.p;
+        f.match = c->d_match.p;
+        memcpy(f.T, c->T, sizeof f.T);
+        f.thr_min = c->thr_min;
+        f.thr_max = c->thr_max;
+        f.D = c->D;
+        f.gaps = c->d_gapmeta.p;
+        f.flank = c->d_flank.p;
+        f.codes = c->d_codes.p;
+        f.nmask = c->d_nmask.p;
+        f.rmeta = c->d_rmeta.p;
+        f.gap_list = c->d_gaplist.p;
+        f.best_gp = c->d_bestgp.p;
+        f.best_cons_off = c->d_bestoff.p;
+        f.unit_cons = c->d_cons.p;
+        f.gmax_stride = c->fin_rows;
+        f.gb_stride = c->fin_gbmax;
+        f.theta = c->theta;
+        f.fin_counts = c->d_fin_counts.p;
+        f.fin_counts_off = c->d_fin_counts_off.p;
+        f.tickets = c->d_tickets.p;
+        f.discarded = c->d_tickets.p + ng;
+        f.filled = c->d_filled.p;
+        f.filled_off = c->d_filled_off.p;
+        FB_CUDA(c, cudaEventRecord(c->ev2, c->stream));
+        FB_CUDA(c, fb_launch_finalize(f, (int)c->fin_gaplist.size(), c->fin_slices, c->fin_smem, c->stream));
+        FB_CUDA(c, cudaEventRecord(c->ev3, c->stream));
+        st.finalize_launches = 1;
+        FB_CUDA(c, cudaMemcpyAsync(c->h_filled.p, c->d_filled.p, c->fin_fill_total, cudaMemcpyDeviceToHost, c->stream));
+        FB_CUDA(c, cudaMemcpyAsync(c->h_discarded.p, c->d_tickets.p + ng, ng * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        FB_CUDA(c, cudaMemcpyAsync(c->h_best_gp.p, c->d_bestgp.p, ng * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        FB_CUDA(c, cudaMemcpyAsync(c->h_best_off.p, c->d_bestoff.p, ng * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+        FB_CUDA(c, cudaMemcpyAsync(c->h_best_lik.p, c->d_best_lik.p, ng * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        d2h += (long)(c->fin_fill_total + ng * (2 * sizeof(int) + sizeof(long long) + sizeof(double)));
+    }
+    FB_CUDA(c, cudaMemcpyAsync(c->h_unit_lik.p, c->d_unit_lik.p, nu * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    d2h += (long)(nu * sizeof(double));
+    FB_CUDA(c, cudaEventRecord(c->eve, c->stream));
+    tr.lap("run: enqueued");
+    FB_CUDA(c, cudaEventSynchronize(c->eve));
+    tr.lap("run: device");
+    // ---- results to the gaps (figbird.cpp:2382, 2050-2063, 2503)
+    const int D = c->D;
+    std::vector<long> fin_liks(c->fin_gaplist.size(), 0);
+    parallel_for((int)c->fin_gaplist.size(), 4, [&](int k) {
+        const int gi = c->fin_gaplist[k];
+        HostGap& g = c->gaps[gi];
+        const int ne = g.gmax - g.gmin + 1;
+        g.liks.resize(ne);
+        g.cons_off.resize(ne);
+        for (int e = 0; e < ne; e++) {
+            const int u = c->h_sel_unit[(size_t)c->h_sel_off[gi] + e];
+            g.liks[e] = c->h_unit_lik.p[u];
+            g.cons_off[e] = c->h_units[u].cons_off;
+        }
+        g.best_est = c->h_best_gp.p[gi];
+        g.best_lik = c->h_best_lik.p[gi];
+        g.no_winner = c->h_best_off.p[gi] < 0;
+        g.total_reads = g.nrec;
+        g.discarded = c->h_discarded.p[gi];
+        g.filled.assign(c->h_filled.p + c->fin_filled_off[gi], (size_t)g.best_est);
+        g.done = true;
+        for (int r = 0; r < g.nrec; r++) fin_liks[k] += placements(c->h_rmeta[g.rec_off + r], D, g.best_est);
+    });
+    for (long v : fin_liks) st.finalize_likelihoods += v;
+    tr.lap("run: results");
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    st.em_kernel_ms = ms;
+    cudaEventElapsedTime(&ms, c->evs, c->eve);
+    st.step_ms = ms;
+    st.finalize_kernel_ms = 0;
+    if (!c->fin_gaplist.empty()) {
+        cudaEventElapsedTime(&ms, c->ev2, c->ev3);
+        st.finalize_kernel_ms = ms;
+    }
+    st.d2h_bytes = d2h;
+    c->scanned = true;
+    c->ran = true;
+    return FB_OK;
+}
+
 int fb_run_device(fb_ctx* c) {
+    if (!c) return FB_EINVAL;
+    if (!c->uploaded) return c->fail(FB_ESTATE, "fb_run_device before fb_upload");
+    if (c->fused_ok && !(getenv("FB_TWO_CALL") && atoi(getenv("FB_TWO_CALL")))) return run_fused(c);
     int rc = fb_run_scan(c);
     if (rc != FB_OK) return rc;
     return fb_run_finalize(c);

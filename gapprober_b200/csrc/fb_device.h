@@ -133,6 +133,21 @@ struct FbFinParams {
     const long long* filled_off;   // [n_gaps] offset of gap g's sequence in `filled`
 };
 
+// fillGap's selection among the estimates of a gap (figbird.cpp:2479-2490) on the device: thread per gap, estimates in
+// ascending order, 'likelihood >= maxLikelihood' (the last one wins ties; NaN and -inf never win).
+struct FbSelParams {
+    int n_gaps;
+    const int* sel_off;          // [n_gaps + 1] first entry of gap g in sel_unit (no entries: gap not run by this context)
+    const int* sel_unit;         // per (gap, estimate in ascending order): index of the unit in the launch order
+    const int* gmin;             // [n_gaps] first estimate of the scan
+    const double* unit_lik;
+    const FbUnit* units;
+    int* best_gp;                // [n_gaps] out: maxGapEstimate
+    long long* best_cons_off;    // [n_gaps] out: where the winner's consensus lies, -1 when no estimate won
+    double* best_lik;            // [n_gaps] out: maxLikelihood
+};
+cudaError_t fb_launch_select(const FbSelParams& p, cudaStream_t s);
+
 size_t fb_em_smem_bytes(int nr_stride, int gp_stride, int p_stride, int chunk, int pwin, bool global_tables);
 // threads: 512 or 1024; f1: the reference's log-domain mode (argv[2] = 1)
 cudaError_t fb_launch_em(const FbEmParams& p, int grid, int threads, bool global_tables, bool f1, size_t smem, cudaStream_t s);

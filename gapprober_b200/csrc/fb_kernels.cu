@@ -926,6 +926,23 @@ __global__ void fb_flag_wait_kernel(FbFlagParams p) {
     }
 }
 
+__global__ void __launch_bounds__(128) fb_select_kernel(const FbSelParams p) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= p.n_gaps) return;
+    const int e0 = p.sel_off[g], e1 = p.sel_off[g + 1];
+    if (e1 <= e0) return;
+    double best = -1.7976931348623157e308;      // maxLikelihood = -DBL_MAX, figbird.cpp:2458
+    int be = p.gmin[g], bu = -1;
+    for (int e = e0; e < e1; e++) {
+        const int u = p.sel_unit[e];
+        const double l = p.unit_lik[u];
+        if (l >= best) { best = l; be = p.gmin[g] + (e - e0); bu = u; }
+    }
+    p.best_gp[g] = be;
+    p.best_lik[g] = best;
+    p.best_cons_off[g] = bu < 0 ? -1 : p.units[bu].cons_off;
+}
+
 // Test tap: the device's log / pow(10, .) applied element-wise (tests compare the bits with the host libm).
 __global__ void fb_devmath_kernel(const double* __restrict__ in, double* __restrict__ out, long n, int what) {
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
@@ -933,6 +950,12 @@ __global__ void fb_devmath_kernel(const double* __restrict__ in, double* __restr
 }
 
 }  // namespace
+
+cudaError_t fb_launch_select(const FbSelParams& p, cudaStream_t s) {
+    if (p.n_gaps < 1) return cudaSuccess;
+    fb_select_kernel<<<(p.n_gaps + 127) / 128, 128, 0, s>>>(p);
+    return cudaGetLastError();
+}
 
 cudaError_t fb_launch_devmath(const double* in, double* out, long n, int what, cudaStream_t s) {
     fb_devmath_kernel<<<1184, 256, 0, s>>>(in, out, n, what);
