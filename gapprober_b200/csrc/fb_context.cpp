@@ -138,6 +138,7 @@ struct Bin {
     int ctas_per_sm;
     int threads;      // per CTA: 512, or 1024 when only one CTA fits an SM
     int cluster;      // CTAs per unit (thread-block cluster) when the launch has fewer units than the GPU has CTA slots; 1 = one CTA per unit
+    bool one_cta_few; // few units + wide insert window: tables sized for one CTA per SM on purpose (see plan_bins)
     size_t smem;
     int grid;         // CTAs, or clusters when cluster > 1
     size_t gws_off;   // doubles: this bin's slice of the global workspace (bins run concurrently)
@@ -1186,6 +1187,13 @@ int plan_units(fb_ctx* c, Trace& tr, long long& mp_out, long long& co_out) {
 int plan_bins(fb_ctx* c, int pwin, size_t& gws_need_out, Trace& tr) {
     // ---- shared-memory geometry per bin
     size_t gws_need = 0;
+    long total_units = 0;
+    for (const Bin& b : c->bins) total_units += b.n_units;
+    // Few units (a single gap: its estimates are all the independent work there is) and a wide insert window: two CTAs per
+    // SM would leave room for only a few records per round (cfg1: 4), i.e. many short rounds, each ending in a barrier.
+    // With at most one unit per SM anyway, size the tables for ONE CTA per SM — 16 or 32 records per round, 32 warps —
+    // and give every unit as many SMs (a thread-block cluster) as keeps all units co-resident.
+    const bool few_units = total_units <= c->sm_count && !getenv("FB_CLUSTER") && !getenv("FB_ONE_CTA") && !getenv("FB_NO_FEW");
     for (Bin& b : c->bins) {
         b.nr_stride = b.gpmax + 2 * b.lmax - 2;
         b.gp_stride = (b.gpmax + 1) & ~1;
@@ -1197,7 +1205,9 @@ int plan_bins(fb_ctx* c, int pwin, size_t& gws_need_out, Trace& tr) {
         int ctas = 2;
         // tuning knob: records per pipeline round (the M-step sets up one record per lane, so at most 32)
         const int pref = getenv("FB_CHUNK") ? std::max(1, std::min(32, atoi(getenv("FB_CHUNK")))) : 16;
-        const bool force_one = getenv("FB_ONE_CTA") && atoi(getenv("FB_ONE_CTA")) != 0;   // experiment knob: size for one CTA per SM
+        bool force_one = getenv("FB_ONE_CTA") && atoi(getenv("FB_ONE_CTA")) != 0;   // experiment knob: size for one CTA per SM
+        if (few_units && fb_em_smem_bytes(b.nr_stride, b.gp_stride, b.p_stride, 16, pwin, false) > two_cta) force_one = true;
+        b.one_cta_few = few_units && force_one;
         for (int want : {pref, 8, 4}) {
             if (want < 1 || force_one) continue;
             const size_t need = fb_em_smem_bytes(b.nr_stride, b.gp_stride, b.p_stride, want, pwin, false);
@@ -1248,9 +1258,15 @@ int plan_bins(fb_ctx* c, int pwin, size_t& gws_need_out, Trace& tr) {
             while (want < 4 && cta_need * want * 2 <= 2L * c->sm_count) want *= 2;   // 8 measured slower than 4: too few tasks per CTA and round
         for (Bin& b : c->bins) {
             if (b.global_tables) continue;
-            for (int cl = want; cl > 1; cl >>= 1) {
+            int bwant = want;
+            if (b.one_cta_few) {                 // one CTA per SM: clusters of as many SMs as keep every unit resident
+                bwant = 1;
+                while (bwant < 4 && total_units * bwant * 2 <= c->sm_count) bwant *= 2;
+            }
+            if (b.ctas_per_sm == 2 || (getenv("FB_THREADS1") && atoi(getenv("FB_THREADS1")) == 512)) b.threads = FB_THREADS;
+            for (int cl = bwant; cl > 1; cl >>= 1) {
                 int fit = 0;
-                if (fb_em_max_clusters(cl, c->f1, b.smem, &fit) == cudaSuccess && fit > 0) {
+                if (fb_em_max_clusters(cl, b.threads, c->f1, b.smem, &fit) == cudaSuccess && fit > 0) {
                     b.cluster = cl;
                     b.grid = std::min(b.n_units, fit);
                     break;
@@ -1508,7 +1524,7 @@ cudaError_t launch_stage(fb_ctx* c, cudaStream_t s) {
 }
 
 cudaError_t launch_bin(const fb_ctx* c, const Bin& b, const FbEmParams& p, cudaStream_t s) {
-    if (b.cluster > 1) return fb_launch_em_cluster(p, b.grid, b.cluster, c->f1, b.smem, s);
+    if (b.cluster > 1) return fb_launch_em_cluster(p, b.grid, b.cluster, b.threads, c->f1, b.smem, s);
     return fb_launch_em(p, b.grid, b.threads, b.global_tables, c->f1, b.smem, s);
 }
 

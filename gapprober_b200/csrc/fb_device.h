@@ -153,8 +153,8 @@ size_t fb_em_smem_bytes(int nr_stride, int gp_stride, int p_stride, int chunk, i
 cudaError_t fb_launch_em(const FbEmParams& p, int grid, int threads, bool global_tables, bool f1, size_t smem, cudaStream_t s);
 cudaError_t fb_em_ctas_per_sm(int threads, bool global_tables, bool f1, size_t smem, int* n);   // occupancy of the plain variant, static smem included
 // cluster variant: n_clusters thread-block clusters of `cluster` CTAs, each cluster running one unit at a time
-cudaError_t fb_launch_em_cluster(const FbEmParams& p, int n_clusters, int cluster, bool f1, size_t smem, cudaStream_t s);
-cudaError_t fb_em_max_clusters(int cluster, bool f1, size_t smem, int* n);     // co-resident clusters of that size on this device
+cudaError_t fb_launch_em_cluster(const FbEmParams& p, int n_clusters, int cluster, int threads, bool f1, size_t smem, cudaStream_t s);
+cudaError_t fb_em_max_clusters(int cluster, int threads, bool f1, size_t smem, int* n);     // co-resident clusters of that size on this device
 // n gaps x `slices` CTAs per gap (a CTA takes every slices-th group of 8 records)
 cudaError_t fb_launch_finalize(const FbFinParams& p, int n, int slices, size_t smem, cudaStream_t s);
 // Flags of the record-sharded scan's device-side barrier (one 64-bit word per rank, in every rank's exchange memory).

@@ -980,6 +980,7 @@ size_t fb_em_smem_bytes(int nr_stride, int gp_stride, int p_stride, int chunk, i
 // 512 or 1024 threads per CTA (NT), linear or log-domain scores (F1).
 using EmKernel = void (*)(const FbEmParams);
 static EmKernel em_variant(bool gt, bool clu, int threads, bool f1) {
+    if (clu && threads == 1024) return f1 ? fb_em_kernel<false, true, 1024, true> : fb_em_kernel<false, true, 1024, false>;
     if (clu) return f1 ? fb_em_kernel<false, true, 512, true> : fb_em_kernel<false, true, 512, false>;
     if (threads == 1024) {
         if (gt) return f1 ? fb_em_kernel<true, false, 1024, true> : fb_em_kernel<true, false, 1024, false>;
@@ -998,9 +999,9 @@ cudaError_t fb_kernels_init(int* max_smem_optin, int* sm_count) {
     e = cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
     for (int f1 = 0; f1 < 2; f1++) {
-        for (int v = 0; v < 5; v++) {
-            const bool gt = v == 3 || v == 4, clu = v == 2;
-            const int threads = (v == 1 || v == 4) ? 1024 : 512;
+        for (int v = 0; v < 6; v++) {
+            const bool gt = v == 3 || v == 4, clu = v == 2 || v == 5;
+            const int threads = (v == 1 || v == 4 || v == 5) ? 1024 : 512;
             e = cudaFuncSetAttribute(em_variant(gt, clu, threads, f1 != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, *max_smem_optin - 1024);
             if (e != cudaSuccess) return e;
         }
@@ -1019,10 +1020,10 @@ cudaError_t fb_launch_em(const FbEmParams& p, int grid, int threads, bool global
     return cudaGetLastError();
 }
 
-static void cluster_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, int grid, int cluster, size_t smem, cudaStream_t s) {
+static void cluster_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, int grid, int cluster, int threads, size_t smem, cudaStream_t s) {
     *cfg = cudaLaunchConfig_t{};
     cfg->gridDim = dim3((unsigned)grid, 1, 1);
-    cfg->blockDim = dim3(FB_THREADS, 1, 1);
+    cfg->blockDim = dim3(threads == 1024 ? 1024 : FB_THREADS, 1, 1);
     cfg->dynamicSmemBytes = smem;
     cfg->stream = s;
     attr->id = cudaLaunchAttributeClusterDimension;
@@ -1033,18 +1034,18 @@ static void cluster_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, i
     cfg->numAttrs = 1;
 }
 
-cudaError_t fb_em_max_clusters(int cluster, bool f1, size_t smem, int* n) {
+cudaError_t fb_em_max_clusters(int cluster, int threads, bool f1, size_t smem, int* n) {
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr;
-    cluster_config(&cfg, &attr, cluster, cluster, smem, nullptr);
-    return cudaOccupancyMaxActiveClusters(n, em_variant(false, true, 512, f1), &cfg);
+    cluster_config(&cfg, &attr, cluster, cluster, threads, smem, nullptr);
+    return cudaOccupancyMaxActiveClusters(n, em_variant(false, true, threads, f1), &cfg);
 }
 
-cudaError_t fb_launch_em_cluster(const FbEmParams& p, int n_clusters, int cluster, bool f1, size_t smem, cudaStream_t s) {
+cudaError_t fb_launch_em_cluster(const FbEmParams& p, int n_clusters, int cluster, int threads, bool f1, size_t smem, cudaStream_t s) {
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr;
-    cluster_config(&cfg, &attr, n_clusters * cluster, cluster, smem, s);
-    return cudaLaunchKernelEx(&cfg, em_variant(false, true, 512, f1), p);
+    cluster_config(&cfg, &attr, n_clusters * cluster, cluster, threads, smem, s);
+    return cudaLaunchKernelEx(&cfg, em_variant(false, true, threads, f1), p);
 }
 
 cudaError_t fb_launch_finalize(const FbFinParams& p, int n, int slices, size_t smem, cudaStream_t s) {
