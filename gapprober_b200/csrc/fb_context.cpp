@@ -204,9 +204,19 @@ struct fb_ctx {
     DevBuf<int> d_counters;
     DevBuf<double> d_maxprob, d_gws, d_dump;
     DevBuf<char> d_cons;
-    DevBuf<int> d_gaplist, d_bestgp;
-    DevBuf<long long> d_bestoff, d_filled_off;
-    DevBuf<double> d_unit_lik, d_best_lik;
+    DevBuf<int> d_gaplist;
+    DevBuf<long long> d_filled_off;
+    DevBuf<double> d_unit_lik;
+    // per-gap outputs of selection and finalize, one allocation (one copy home): best_lik f64 | best_off i64 | best_gp i32 |
+    // discarded i32 | tickets i32, each [n_gaps]
+    DevBuf<unsigned char> d_gapout;
+    PinBuf<unsigned char> h_gapout;
+    size_t gapout_n = 0;
+    double* go_lik(unsigned char* b) const { return reinterpret_cast<double*>(b); }
+    long long* go_off(unsigned char* b) const { return reinterpret_cast<long long*>(b + 8 * gapout_n); }
+    int* go_gp(unsigned char* b) const { return reinterpret_cast<int*>(b + 16 * gapout_n); }
+    int* go_disc(unsigned char* b) const { return reinterpret_cast<int*>(b + 20 * gapout_n); }
+    int* go_tick(unsigned char* b) const { return reinterpret_cast<int*>(b + 24 * gapout_n); }
     DevBuf<int> d_sel_off, d_sel_unit, d_gmin;
     std::vector<int> h_sel_off, h_sel_unit, h_gmin;
     // one-call pass (fb_run_device without a partition that needs a host exchange): everything is enqueued at once —
@@ -218,13 +228,9 @@ struct fb_ctx {
     std::vector<long long> fin_filled_off;
     int fin_slices = 1, fin_rows = 0, fin_gbmax = 1;
     size_t fin_smem = 0, fin_counts_total = 0, fin_fill_total = 0;
-    PinBuf<double> h_best_lik;
-    PinBuf<int> h_best_gp;
-    PinBuf<long long> h_best_off;
-    DevBuf<int> d_fin_counts, d_fin_counts_off, d_tickets, d_discarded;
+    DevBuf<int> d_fin_counts, d_fin_counts_off;
     DevBuf<char> d_filled;
     PinBuf<double> h_maxprob, h_unit_lik;
-    PinBuf<int> h_discarded;
     PinBuf<char> h_filled;
     PinBuf<unsigned char> h_stage;   // pinned staging for the host->device copies
 
@@ -391,16 +397,14 @@ void fb_destroy(fb_ctx* c) {
     c->d_ild.release(); c->d_epos.release(); c->d_match.release();
     c->d_gapmeta.release(); c->d_flank.release(); c->d_codes.release(); c->d_nmask.release(); c->d_rmeta.release();
     c->d_units.release(); c->d_counters.release(); c->d_maxprob.release(); c->d_gws.release();
-    c->d_dump.release(); c->d_cons.release(); c->d_gaplist.release(); c->d_bestgp.release();
-    c->d_bestoff.release();
+    c->d_dump.release(); c->d_cons.release(); c->d_gaplist.release(); c->d_gapout.release(); c->h_gapout.release();
     c->d_st_mask.release(); c->d_st_cls4.release(); c->d_st_jl.release(); c->d_st_cum.release();
     c->d_units_scan.release(); c->d_gapmeta_scan.release(); c->d_parts[0].release(); c->d_parts[1].release();
     c->d_sumcounts.release(); c->d_maxmerge.release(); c->d_unit_nrec.release(); c->d_shard_err.release(); c->d_flags.release();
     c->h_maxprob.release(); c->h_stage.release();
     c->d_ild_em.release(); c->d_filled_off.release(); c->d_unit_lik.release(); c->d_fin_counts.release(); c->d_fin_counts_off.release();
-    c->d_best_lik.release(); c->d_sel_off.release(); c->d_sel_unit.release(); c->d_gmin.release();
-    c->h_best_lik.release(); c->h_best_gp.release(); c->h_best_off.release();
-    c->d_tickets.release(); c->d_discarded.release(); c->d_filled.release(); c->h_unit_lik.release(); c->h_discarded.release(); c->h_filled.release();
+    c->d_sel_off.release(); c->d_sel_unit.release(); c->d_gmin.release();
+    c->d_filled.release(); c->h_unit_lik.release(); c->h_filled.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev2) cudaEventDestroy(c->ev2);
@@ -1315,12 +1319,11 @@ int upload_buffers(fb_ctx* c, long long mp, long long co, size_t gws_need, Trace
     FB_CUDA(c, c->d_maxprob.ensure((size_t)mp));
     FB_CUDA(c, c->d_cons.ensure((size_t)co));
     FB_CUDA(c, c->d_gaplist.ensure(ng));
-    FB_CUDA(c, c->d_bestgp.ensure(ng));
-    FB_CUDA(c, c->d_bestoff.ensure(ng));
+    c->gapout_n = std::max<size_t>(ng, 1);
+    FB_CUDA(c, c->d_gapout.ensure(28 * c->gapout_n));
+    FB_CUDA(c, c->h_gapout.ensure(28 * c->gapout_n));
     FB_CUDA(c, c->d_filled_off.ensure(ng));
     FB_CUDA(c, c->d_fin_counts_off.ensure(ng));
-    FB_CUDA(c, c->d_tickets.ensure(2 * ng));          // tickets[ng] + discarded[ng], zeroed together
-    FB_CUDA(c, c->h_discarded.ensure(ng));
     FB_CUDA(c, c->d_unit_lik.ensure(c->h_units.size()));
     FB_CUDA(c, c->h_unit_lik.ensure(c->h_units.size()));
     {
@@ -1384,11 +1387,7 @@ int upload_buffers(fb_ctx* c, long long mp, long long co, size_t gws_need, Trace
         FB_CUDA(c, c->d_sel_off.ensure(ng + 1));
         FB_CUDA(c, c->d_sel_unit.ensure(c->h_sel_unit.size()));
         FB_CUDA(c, c->d_gmin.ensure(ng));
-        FB_CUDA(c, c->d_best_lik.ensure(ng));
         FB_CUDA(c, c->d_fin_counts.ensure(c->fin_counts_total));
-        FB_CUDA(c, c->h_best_lik.ensure(ng));
-        FB_CUDA(c, c->h_best_gp.ensure(ng));
-        FB_CUDA(c, c->h_best_off.ensure(ng));
     }
     long h2d = 0;
     const size_t stage_need = ng * sizeof(FbGapMeta) + c->h_flank.size() + (c->h_codes.size() + c->h_nmask.size()) * sizeof(uint4) +
@@ -1719,11 +1718,11 @@ int fb_run_finalize(fb_ctx* c) {
         };
         c->fused_dirty = true;
         FB_CUDA(c, up(c->d_gaplist.p, gaplist.data(), gaplist.size() * sizeof(int)));
-        FB_CUDA(c, up(c->d_bestgp.p, bestgp.data(), ng * sizeof(int)));
-        FB_CUDA(c, up(c->d_bestoff.p, cons_off_of_best.data(), ng * sizeof(long long)));
+        FB_CUDA(c, up(c->go_gp(c->d_gapout.p), bestgp.data(), ng * sizeof(int)));
+        FB_CUDA(c, up(c->go_off(c->d_gapout.p), cons_off_of_best.data(), ng * sizeof(long long)));
         FB_CUDA(c, up(c->d_filled_off.p, filled_off.data(), ng * sizeof(long long)));
         FB_CUDA(c, up(c->d_fin_counts_off.p, counts_off.data(), ng * sizeof(int)));
-        FB_CUDA(c, cudaMemsetAsync(c->d_tickets.p, 0, sizeof(int) * 2 * ng, c->stream));
+        FB_CUDA(c, cudaMemsetAsync(c->go_disc(c->d_gapout.p), 0, sizeof(int) * 2 * c->gapout_n, c->stream));   // discarded + tickets
         if (counts_total) FB_CUDA(c, cudaMemsetAsync(c->d_fin_counts.p, 0, sizeof(int) * counts_total, c->stream));
         FbFinParams f;
         memset(&f, 0, sizeof f);
@@ -1740,16 +1739,16 @@ int fb_run_finalize(fb_ctx* c) {
         f.nmask = c->d_nmask.p;
         f.rmeta = c->d_rmeta.p;
         f.gap_list = c->d_gaplist.p;
-        f.best_gp = c->d_bestgp.p;
-        f.best_cons_off = c->d_bestoff.p;
+        f.best_gp = c->go_gp(c->d_gapout.p);
+        f.best_cons_off = c->go_off(c->d_gapout.p);
         f.unit_cons = c->d_cons.p;
         f.gmax_stride = rows;
         f.gb_stride = gbmax;
         f.theta = c->theta;
         f.fin_counts = c->d_fin_counts.p;
         f.fin_counts_off = c->d_fin_counts_off.p;
-        f.tickets = c->d_tickets.p;
-        f.discarded = c->d_tickets.p + ng;
+        f.tickets = c->go_tick(c->d_gapout.p);
+        f.discarded = c->go_disc(c->d_gapout.p);
         f.filled = c->d_filled.p;
         f.filled_off = c->d_filled_off.p;
         FB_CUDA(c, cudaEventRecord(c->ev2, c->stream));
@@ -1757,7 +1756,7 @@ int fb_run_finalize(fb_ctx* c) {
         FB_CUDA(c, cudaEventRecord(c->ev3, c->stream));
         st.finalize_launches = 1;
         FB_CUDA(c, cudaMemcpyAsync(c->h_filled.p, c->d_filled.p, fill_total, cudaMemcpyDeviceToHost, c->stream));
-        FB_CUDA(c, cudaMemcpyAsync(c->h_discarded.p, c->d_tickets.p + ng, ng * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        FB_CUDA(c, cudaMemcpyAsync(c->go_disc(c->h_gapout.p), c->go_disc(c->d_gapout.p), ng * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         d2h += (long)(fill_total + ng * sizeof(int));
         FB_CUDA(c, cudaEventRecord(c->eve, c->stream));
         FB_CUDA(c, cudaEventSynchronize(c->eve));
@@ -1770,7 +1769,7 @@ int fb_run_finalize(fb_ctx* c) {
     for (int gi : gaplist) {
         HostGap& g = c->gaps[gi];
         g.total_reads = g.nrec;
-        g.discarded = c->h_discarded.p[gi];
+        g.discarded = c->go_disc(c->h_gapout.p)[gi];
         g.filled.assign(c->h_filled.p + filled_off[gi], (size_t)g.best_est);
         g.done = true;
         for (int r = 0; r < g.nrec; r++) st.finalize_likelihoods += placements(c->h_rmeta[g.rec_off + r], D, g.best_est);
@@ -2073,7 +2072,7 @@ static int run_fused(fb_ctx* c) {
     }
     FB_CUDA(c, cudaEventRecord(c->evs, c->stream));
     FB_CUDA(c, cudaMemsetAsync(c->d_counters.p, 0, sizeof(int) * (c->bins.size() + 1), c->stream));
-    FB_CUDA(c, cudaMemsetAsync(c->d_tickets.p, 0, sizeof(int) * 2 * ng, c->stream));
+    FB_CUDA(c, cudaMemsetAsync(c->go_disc(c->d_gapout.p), 0, sizeof(int) * 2 * c->gapout_n, c->stream));   // discarded + tickets
     if (c->fin_counts_total) FB_CUDA(c, cudaMemsetAsync(c->d_fin_counts.p, 0, sizeof(int) * c->fin_counts_total, c->stream));
     FB_CUDA(c, launch_stage(c, c->stream));
     st.aux_launches = 1;
@@ -2102,9 +2101,9 @@ static int run_fused(fb_ctx* c) {
         sp.gmin = c->d_gmin.p;
         sp.unit_lik = c->d_unit_lik.p;
         sp.units = c->d_units.p;
-        sp.best_gp = c->d_bestgp.p;
-        sp.best_cons_off = c->d_bestoff.p;
-        sp.best_lik = c->d_best_lik.p;
+        sp.best_gp = c->go_gp(c->d_gapout.p);
+        sp.best_cons_off = c->go_off(c->d_gapout.p);
+        sp.best_lik = c->go_lik(c->d_gapout.p);
         FB_CUDA(c, fb_launch_select(sp, c->stream));
         st.aux_launches++;
         FbFinParams f;
@@ -2122,16 +2121,16 @@ static int run_fused(fb_ctx* c) {
         f.nmask = c->d_nmask.p;
         f.rmeta = c->d_rmeta.p;
         f.gap_list = c->d_gaplist.p;
-        f.best_gp = c->d_bestgp.p;
-        f.best_cons_off = c->d_bestoff.p;
+        f.best_gp = c->go_gp(c->d_gapout.p);
+        f.best_cons_off = c->go_off(c->d_gapout.p);
         f.unit_cons = c->d_cons.p;
         f.gmax_stride = c->fin_rows;
         f.gb_stride = c->fin_gbmax;
         f.theta = c->theta;
         f.fin_counts = c->d_fin_counts.p;
         f.fin_counts_off = c->d_fin_counts_off.p;
-        f.tickets = c->d_tickets.p;
-        f.discarded = c->d_tickets.p + ng;
+        f.tickets = c->go_tick(c->d_gapout.p);
+        f.discarded = c->go_disc(c->d_gapout.p);
         f.filled = c->d_filled.p;
         f.filled_off = c->d_filled_off.p;
         FB_CUDA(c, cudaEventRecord(c->ev2, c->stream));
@@ -2139,11 +2138,8 @@ static int run_fused(fb_ctx* c) {
         FB_CUDA(c, cudaEventRecord(c->ev3, c->stream));
         st.finalize_launches = 1;
         FB_CUDA(c, cudaMemcpyAsync(c->h_filled.p, c->d_filled.p, c->fin_fill_total, cudaMemcpyDeviceToHost, c->stream));
-        FB_CUDA(c, cudaMemcpyAsync(c->h_discarded.p, c->d_tickets.p + ng, ng * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        FB_CUDA(c, cudaMemcpyAsync(c->h_best_gp.p, c->d_bestgp.p, ng * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        FB_CUDA(c, cudaMemcpyAsync(c->h_best_off.p, c->d_bestoff.p, ng * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
-        FB_CUDA(c, cudaMemcpyAsync(c->h_best_lik.p, c->d_best_lik.p, ng * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        d2h += (long)(c->fin_fill_total + ng * (2 * sizeof(int) + sizeof(long long) + sizeof(double)));
+        FB_CUDA(c, cudaMemcpyAsync(c->h_gapout.p, c->d_gapout.p, 24 * c->gapout_n, cudaMemcpyDeviceToHost, c->stream));   // all but the tickets
+        d2h += (long)(c->fin_fill_total + 24 * c->gapout_n);
     }
     FB_CUDA(c, cudaMemcpyAsync(c->h_unit_lik.p, c->d_unit_lik.p, nu * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     d2h += (long)(nu * sizeof(double));
@@ -2165,11 +2161,11 @@ static int run_fused(fb_ctx* c) {
             g.liks[e] = c->h_unit_lik.p[u];
             g.cons_off[e] = c->h_units[u].cons_off;
         }
-        g.best_est = c->h_best_gp.p[gi];
-        g.best_lik = c->h_best_lik.p[gi];
-        g.no_winner = c->h_best_off.p[gi] < 0;
+        g.best_est = c->go_gp(c->h_gapout.p)[gi];
+        g.best_lik = c->go_lik(c->h_gapout.p)[gi];
+        g.no_winner = c->go_off(c->h_gapout.p)[gi] < 0;
         g.total_reads = g.nrec;
-        g.discarded = c->h_discarded.p[gi];
+        g.discarded = c->go_disc(c->h_gapout.p)[gi];
         g.filled.assign(c->h_filled.p + c->fin_filled_off[gi], (size_t)g.best_est);
         g.done = true;
         for (int r = 0; r < g.nrec; r++) fin_liks[k] += placements(c->h_rmeta[g.rec_off + r], D, g.best_est);
