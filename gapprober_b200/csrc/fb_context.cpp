@@ -1193,10 +1193,10 @@ int plan_bins(fb_ctx* c, int pwin, size_t& gws_need_out, Trace& tr) {
     size_t gws_need = 0;
     long total_units = 0;
     for (const Bin& b : c->bins) total_units += b.n_units;
-    // Few units (a single gap: its estimates are all the independent work there is) and a wide insert window: two CTAs per
-    // SM would leave room for only a few records per round (cfg1: 4), i.e. many short rounds, each ending in a barrier.
-    // With at most one unit per SM anyway, size the tables for ONE CTA per SM — 16 or 32 records per round, 32 warps —
-    // and give every unit as many SMs (a thread-block cluster) as keeps all units co-resident.
+    // Few units (a single gap: its estimates are all the independent work there is): with at most one unit per SM anyway,
+    // size the tables for ONE CTA per SM — 16 or 32 records per round (two CTAs per SM leave room for 4 with a wide insert
+    // window: many short rounds, each ending in a barrier), 32 warps — and give every unit as many SMs (a thread-block
+    // cluster) as keeps all units co-resident.  cfg1: 0.88 -> 0.53 ms per scan.
     const bool few_units = total_units <= c->sm_count && !getenv("FB_CLUSTER") && !getenv("FB_ONE_CTA") && !getenv("FB_NO_FEW");
     for (Bin& b : c->bins) {
         b.nr_stride = b.gpmax + 2 * b.lmax - 2;
@@ -1210,7 +1210,7 @@ int plan_bins(fb_ctx* c, int pwin, size_t& gws_need_out, Trace& tr) {
         // tuning knob: records per pipeline round (the M-step sets up one record per lane, so at most 32)
         const int pref = getenv("FB_CHUNK") ? std::max(1, std::min(32, atoi(getenv("FB_CHUNK")))) : 16;
         bool force_one = getenv("FB_ONE_CTA") && atoi(getenv("FB_ONE_CTA")) != 0;   // experiment knob: size for one CTA per SM
-        if (few_units && fb_em_smem_bytes(b.nr_stride, b.gp_stride, b.p_stride, 16, pwin, false) > two_cta) force_one = true;
+        if (few_units) force_one = true;
         b.one_cta_few = few_units && force_one;
         for (int want : {pref, 8, 4}) {
             if (want < 1 || force_one) continue;

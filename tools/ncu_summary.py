@@ -1,7 +1,8 @@
 """Per-launch extract of an `ncu --set full` report: the columns profiles/r1_ncu_full_summary.csv keeps, plus the DRAM
 traffic of the EM launches as JSON (feeds bench.py's roofline.traffic).
     ncu -i report.ncu-rep --page raw --csv > raw.csv
-    python tools/ncu_summary.py raw.csv profiles/r1_ncu_full_summary.csv profiles/r1_traffic.json
+    python tools/ncu_summary.py raw.csv profiles/r2_ncu_full_summary.csv profiles/r2_traffic.json cfg4_chr14
+The JSON is keyed by workload; bench.py uses an entry only for that workload and only while its launch count still matches.
 """
 import csv
 import json
@@ -23,7 +24,7 @@ def to_bytes(v, unit):
     return float(v.replace(",", "")) * mult
 
 
-def main(raw, out_csv, out_json):
+def main(raw, out_csv, out_json, workload="cfg4_chr14"):
     rows = list(csv.reader(open(raw)))
     hdr = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
     names, units = rows[hdr], rows[hdr + 1]
@@ -42,10 +43,13 @@ def main(raw, out_csv, out_json):
             rd += to_bytes(r[ri], units[ri])
             wr += to_bytes(r[wi], units[wi])
             n += 1
-    json.dump({"source": f"{out_csv} (ncu --set full, bench.py --steps 1 --warmup 3 --no-cpu, cfg2_rhodobacter seed 2)",
-               "kernel": "fb_em_kernel", "launches_per_step": n, "dram_bytes_read_per_step": rd, "dram_bytes_write_per_step": wr,
-               "dram_bytes_per_launch": (rd + wr) / max(n, 1)}, open(out_json, "w"), indent=1)
+    import os
+    doc = json.load(open(out_json)) if os.path.exists(out_json) else {}
+    doc[workload] = {"source": f"{out_csv} (ncu --set full over the fb_* launches of one timed step of bench.py --config {workload} --steps 1 --warmup 3)",
+                     "kernel": "fb_em_kernel", "launches_per_step": n, "dram_bytes_read_per_step": rd, "dram_bytes_write_per_step": wr,
+                     "dram_bytes_per_launch": (rd + wr) / max(n, 1)}
+    json.dump(doc, open(out_json, "w"), indent=1)
 
 
 if __name__ == "__main__":
-    main(*sys.argv[1:4])
+    main(*sys.argv[1:5])
