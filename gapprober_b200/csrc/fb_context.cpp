@@ -153,7 +153,7 @@ struct fb_ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     std::vector<cudaStream_t> bin_streams;            // one per EM launch (size bin)
     std::vector<cudaEvent_t> bin_done, bin_copied;   // per EM launch: kernel finished / its results are on the host
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, evs = nullptr, eve = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, evs = nullptr, eve = nullptr, ev_fork = nullptr;
     int max_smem = 0, sm_count = 0;
     std::string err;
 
@@ -217,7 +217,9 @@ struct fb_ctx {
     int* go_gp(unsigned char* b) const { return reinterpret_cast<int*>(b + 16 * gapout_n); }
     int* go_disc(unsigned char* b) const { return reinterpret_cast<int*>(b + 20 * gapout_n); }
     int* go_tick(unsigned char* b) const { return reinterpret_cast<int*>(b + 24 * gapout_n); }
-    DevBuf<int> d_sel_off, d_sel_unit, d_gmin;
+    DevBuf<int> d_sel_off, d_sel_unit, d_gmin, d_bin_first;
+    DevBuf<FbUnit> d_win_units;
+    bool two_pass = false;       // many units per CTA slot: first pass without the last M-step, winners run again (see run_fused)
     std::vector<int> h_sel_off, h_sel_unit, h_gmin;
     // one-call pass (fb_run_device without a partition that needs a host exchange): everything is enqueued at once —
     // scan, selection, finalize, copies — and the host waits once.  The finalize geometry is fixed at upload from the
@@ -348,6 +350,7 @@ int fb_create(const fb_model* m, int device, fb_ctx** out) {
     cudaEventCreate(&c->ev3);
     cudaEventCreate(&c->evs);
     cudaEventCreate(&c->eve);
+    cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
     c->max_read_len = m->max_read_len;
     c->thr_min = m->thr_min;
     c->thr_max = m->thr_max;
@@ -403,7 +406,7 @@ void fb_destroy(fb_ctx* c) {
     c->d_sumcounts.release(); c->d_maxmerge.release(); c->d_unit_nrec.release(); c->d_shard_err.release(); c->d_flags.release();
     c->h_maxprob.release(); c->h_stage.release();
     c->d_ild_em.release(); c->d_filled_off.release(); c->d_unit_lik.release(); c->d_fin_counts.release(); c->d_fin_counts_off.release();
-    c->d_sel_off.release(); c->d_sel_unit.release(); c->d_gmin.release();
+    c->d_sel_off.release(); c->d_sel_unit.release(); c->d_gmin.release(); c->d_bin_first.release(); c->d_win_units.release();
     c->d_filled.release(); c->h_unit_lik.release(); c->h_filled.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -411,6 +414,7 @@ void fb_destroy(fb_ctx* c) {
     if (c->ev3) cudaEventDestroy(c->ev3);
     if (c->evs) cudaEventDestroy(c->evs);
     if (c->eve) cudaEventDestroy(c->eve);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (cudaStream_t t : c->bin_streams) cudaStreamDestroy(t);
     for (cudaEvent_t e : c->bin_done) cudaEventDestroy(e);
     for (cudaEvent_t e : c->bin_copied) cudaEventDestroy(e);
@@ -1383,7 +1387,14 @@ int upload_buffers(fb_ctx* c, long long mp, long long co, size_t gws_need, Trace
         c->fin_smem = sizeof(int) * 5 * (size_t)c->fin_gbmax + (size_t)c->fin_rows + 16;
         if (c->fin_smem > (size_t)c->max_smem - 8192) c->fused_ok = false;     // the two-call route sizes finalize by the winners
     }
+    // the last iteration's M-step only matters for the estimate that wins its gap: with many units per CTA slot it pays to
+    // leave it out and run the winners (one unit per gap) a second time; with few units the second run would add a whole
+    // unit's latency instead
+    c->two_pass = c->fused_ok && !getenv("FB_ONE_PASS") && (long)c->h_units.size() >= 16L * c->sm_count && c->h_units.size() >= 8 * ng;
     if (c->fused_ok) {
+        FB_CUDA(c, c->d_bin_first.ensure(c->bins.size() + 1));
+        if (c->two_pass) FB_CUDA(c, c->d_win_units.ensure(c->h_units.size()));
+        FB_CUDA(c, c->d_counters.ensure(3 * c->bins.size() + 3));    // work counters of pass 1, of pass 2, winners per bin
         FB_CUDA(c, c->d_sel_off.ensure(ng + 1));
         FB_CUDA(c, c->d_sel_unit.ensure(c->h_sel_unit.size()));
         FB_CUDA(c, c->d_gmin.ensure(ng));
@@ -1416,6 +1427,10 @@ int upload_buffers(fb_ctx* c, long long mp, long long co, size_t gws_need, Trace
         FB_CUDA(c, up(c->d_gaplist.p, c->fin_gaplist.data(), c->fin_gaplist.size() * sizeof(int)));
         FB_CUDA(c, up(c->d_filled_off.p, c->fin_filled_off.data(), ng * sizeof(long long)));
         FB_CUDA(c, up(c->d_fin_counts_off.p, c->fin_counts_off.data(), ng * sizeof(int)));
+        std::vector<int> bin_first;
+        for (const Bin& b : c->bins) bin_first.push_back(b.first_unit);
+        bin_first.push_back((int)c->h_units.size());
+        FB_CUDA(c, up(c->d_bin_first.p, bin_first.data(), bin_first.size() * sizeof(int)));
     }
     c->shard_counts = c->shard_maxprob = 0;
     if (c->rec_mode) {
@@ -2071,30 +2086,47 @@ static int run_fused(fb_ctx* c) {
         c->fused_dirty = false;
     }
     FB_CUDA(c, cudaEventRecord(c->evs, c->stream));
-    FB_CUDA(c, cudaMemsetAsync(c->d_counters.p, 0, sizeof(int) * (c->bins.size() + 1), c->stream));
+    const size_t nb = c->bins.size();
+    FB_CUDA(c, cudaMemsetAsync(c->d_counters.p, 0, sizeof(int) * (3 * nb + 3), c->stream));
     FB_CUDA(c, cudaMemsetAsync(c->go_disc(c->d_gapout.p), 0, sizeof(int) * 2 * c->gapout_n, c->stream));   // discarded + tickets
     if (c->fin_counts_total) FB_CUDA(c, cudaMemsetAsync(c->d_fin_counts.p, 0, sizeof(int) * c->fin_counts_total, c->stream));
     FB_CUDA(c, launch_stage(c, c->stream));
     st.aux_launches = 1;
     FB_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-    for (size_t bi = 0; bi < c->bins.size(); bi++) {
-        FbEmParams p;
-        fill_bin_params(c, bi, p);
-        if (c->bins.size() == 1) {                       // a single launch needs no stream of its own
-            FB_CUDA(c, launch_bin(c, c->bins[bi], p, c->stream));
-        } else {
-            cudaStream_t bs = c->bin_streams[bi];
-            FB_CUDA(c, cudaStreamWaitEvent(bs, c->ev0, 0));
-            FB_CUDA(c, launch_bin(c, c->bins[bi], p, bs));
-            FB_CUDA(c, cudaEventRecord(c->bin_done[bi], bs));
-            FB_CUDA(c, cudaStreamWaitEvent(c->stream, c->bin_done[bi], 0));
+    // pass: 0 the scan of every unit (without the last M-step when a second pass follows), 1 the winners again in full
+    auto scan_pass = [&](int pass) -> int {
+        if (nb > 1) FB_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));      // every bin's stream forks from here ...
+        for (size_t bi = 0; bi < nb; bi++) {
+            FbEmParams p;
+            fill_bin_params(c, bi, p);
+            if (pass == 0) {
+                p.skip_last_m = c->two_pass ? 1 : 0;
+            } else {
+                p.units = c->d_win_units.p + c->bins[bi].first_unit;
+                p.n_units_ptr = c->d_counters.p + 2 * nb + 2 + bi;
+                p.work_counter = c->d_counters.p + nb + 1 + bi;
+                p.unit_lik = nullptr;                        // pass 1 has written them, by the units' places in the full list
+            }
+            if (nb == 1) {                                   // a single launch needs no stream of its own
+                FB_CUDA(c, launch_bin(c, c->bins[bi], p, c->stream));
+            } else {
+                cudaStream_t bs = c->bin_streams[bi];
+                FB_CUDA(c, cudaStreamWaitEvent(bs, c->ev_fork, 0));
+                FB_CUDA(c, launch_bin(c, c->bins[bi], p, bs));
+                FB_CUDA(c, cudaEventRecord(c->bin_done[bi], bs));
+            }
+            st.em_launches++;
         }
-        st.em_launches++;
-    }
-    FB_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+        if (nb > 1)                                                          // ... and joins the main stream here
+            for (size_t bi = 0; bi < nb; bi++) FB_CUDA(c, cudaStreamWaitEvent(c->stream, c->bin_done[bi], 0));
+        return FB_OK;
+    };
+    int rc = scan_pass(0);
+    if (rc != FB_OK) return rc;
     long d2h = 0;
+    FbSelParams sp;
+    memset(&sp, 0, sizeof sp);
     if (!c->fin_gaplist.empty()) {
-        FbSelParams sp;
         sp.n_gaps = (int)ng;
         sp.sel_off = c->d_sel_off.p;
         sp.sel_unit = c->d_sel_unit.p;
@@ -2104,8 +2136,21 @@ static int run_fused(fb_ctx* c) {
         sp.best_gp = c->go_gp(c->d_gapout.p);
         sp.best_cons_off = c->go_off(c->d_gapout.p);
         sp.best_lik = c->go_lik(c->d_gapout.p);
+        if (c->two_pass) {
+            sp.win_units = c->d_win_units.p;
+            sp.win_count = c->d_counters.p + 2 * nb + 2;
+            sp.bin_first = c->d_bin_first.p;
+            sp.n_bins = (int)nb;
+        }
         FB_CUDA(c, fb_launch_select(sp, c->stream));
         st.aux_launches++;
+        if (c->two_pass) {
+            rc = scan_pass(1);
+            if (rc != FB_OK) return rc;
+        }
+    }
+    FB_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    if (!c->fin_gaplist.empty()) {
         FbFinParams f;
         memset(&f, 0, sizeof f);
         f.ild = c->d_ild.p;

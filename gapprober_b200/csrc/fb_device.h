@@ -79,6 +79,10 @@ struct FbEmParams {
     int n_parts;                             // 0: first iteration, start from initialize()
     double* part_out;                        // this rank's partial counts of this iteration (nullptr: not sharded)
     const int* abort;                        // record-sharded scan: non-zero once a barrier has failed -> the launch does nothing
+    // two-pass scan (one-call pass over many units): pass 1 leaves the M-step of the last iteration and the consensus out,
+    // pass 2 runs the winners of the selection again in full; its unit count is only known on the device
+    int skip_last_m;
+    const int* n_units_ptr;                  // non-null: units to run = min(n_units, *n_units_ptr)
 };
 
 struct FbStageParams {
@@ -145,6 +149,11 @@ struct FbSelParams {
     int* best_gp;                // [n_gaps] out: maxGapEstimate
     long long* best_cons_off;    // [n_gaps] out: where the winner's consensus lies, -1 when no estimate won
     double* best_lik;            // [n_gaps] out: maxLikelihood
+    // two-pass scan: the winners, appended to the work list of their size bin (nullptr: single pass)
+    FbUnit* win_units;           // laid out like `units`: bin b's winners from bin_first[b] on
+    int* win_count;              // [n_bins] zeroed before the launch
+    const int* bin_first;        // [n_bins] first unit of every bin in the launch order
+    int n_bins;
 };
 cudaError_t fb_launch_select(const FbSelParams& p, cudaStream_t s);
 

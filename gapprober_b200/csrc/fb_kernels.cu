@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
         }
         sync_all();
         const int ui = s_unit;
-        if (ui >= p.n_units) break;
+        if (ui >= (p.n_units_ptr ? min(p.n_units, *p.n_units_ptr) : p.n_units)) break;
         const FbUnit unit = p.units[ui];
         const FbGapMeta gm = p.gaps[unit.gap];
         const int gp = unit.gp, nrec = gm.nrec, lmax = gm.lmax;
@@ -489,6 +489,10 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
         int round = 0;                                // global round counter: selects the queue slot
         for (int it = 0; it < p.num_iter; it++) {
             const bool last = it == p.num_iter - 1;
+            // Two-pass scan: the counts of the last iteration only serve computeSequence(0), which matters for the estimate
+            // that wins the gap (figbird.cpp:2479-2490) — the first pass leaves the last M-step out, the winners are run
+            // again in full once the likelihoods have picked them.
+            const bool skip_m = last && p.skip_last_m;
             // rounds of the pipeline: stage chunk r+1 | E-step chunk r | M-step chunk r-1   (r = -1 stages chunk 0)
             for (int r = ((it == 0 || !keep_staged) ? -1 : 0); r <= nchunks; r++, round++) {
                 const int cl = r + 1, ce = r, cm = r - 1;
@@ -522,7 +526,7 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
                     }
                     if (tid < n_l) SL.rmax[tid] = key_init<F1>();   // new iteration (or new chunk), new maximum
                 }
-                const int tM = n_m ? nrb_q * 5 : 0, tE = ne_q * nblk;
+                const int tM = (n_m && !skip_m) ? nrb_q * 5 : 0, tE = ne_q * nblk;
                 const int ntask = tM + tE;
                 int* queue = &s_queue[round & 1];
                 for (;;) {
@@ -656,7 +660,7 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
             // chunk 0 of a kept staging gets its per-record maxima reset here, a barrier ahead of the next iteration's E tasks
             if (keep_staged && !last && tid < min(CH, nrec)) stage_at(s, 0).rmax[tid] = key_init<F1>();
             // ---- computeProbsGap + computeErrorProbsGap on the gap rows (flank rows never change)
-            for (int xg = tid; xg < gpc; xg += NT) {
+            for (int xg = tid; xg < (skip_m ? 0 : gpc); xg += NT) {
                 if (CLU && (unsigned)(xg >> 5) % csize != crank) continue;   // the counts of this row live in another CTA
                 const int xa = xg + (D + xg >= hl ? hn : 0);                  // gap row in the reference's numbering
                 double c[5];
@@ -694,7 +698,7 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
                     for (int k = 0; k < 5; k++) s.cnt[k * gps + xg] = 0.0;   // placeReads zeroes the gap rows, :1708-1714
                 }
             }
-            if (last && (!CLU || crank == 0)) {
+            if (last && !skip_m && (!CLU || crank == 0)) {
                 // rows no placement touches keep all-zero counts: computeSequence(0) gives index 0 there
                 for (int i = tid; i < hn; i += NT) p.unit_cons[unit.cons_off + (hl - D) + i] = 'A';
             }
@@ -941,6 +945,12 @@ __global__ void __launch_bounds__(128) fb_select_kernel(const FbSelParams p) {
     p.best_gp[g] = be;
     p.best_lik[g] = best;
     p.best_cons_off[g] = bu < 0 ? -1 : p.units[bu].cons_off;
+    if (p.win_units && bu >= 0) {
+        // second pass of a two-pass scan: the winner joins the work list of its size bin (any order: units are independent)
+        int b = 0;
+        while (b + 1 < p.n_bins && bu >= p.bin_first[b + 1]) b++;
+        p.win_units[p.bin_first[b] + atomicAdd(&p.win_count[b], 1)] = p.units[bu];
+    }
 }
 
 // Test tap: the device's log / pow(10, .) applied element-wise (tests compare the bits with the host libm).
