@@ -225,6 +225,9 @@ struct fb_ctx {
     // scan, selection, finalize, copies — and the host waits once.  The finalize geometry is fixed at upload from the
     // largest estimates, not from the winners.
     bool fused_ok = false;
+    cudaGraphExec_t graph_exec = nullptr;   // the one-call pass of the current upload, captured
+    bool graph_failed = false;
+    int runs_since_upload = 0;
     bool fused_dirty = false;    // fb_run_finalize has overwritten the gap list / offsets the one-call pass keeps on the device
     std::vector<int> fin_gaplist, fin_counts_off;
     std::vector<long long> fin_filled_off;
@@ -397,6 +400,8 @@ int fb_create(const fb_model* m, int device, fb_ctx** out) {
 void fb_destroy(fb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    c->graph_exec = nullptr;
     c->d_ild.release(); c->d_epos.release(); c->d_match.release();
     c->d_gapmeta.release(); c->d_flank.release(); c->d_codes.release(); c->d_nmask.release(); c->d_rmeta.release();
     c->d_units.release(); c->d_counters.release(); c->d_maxprob.release(); c->d_gws.release();
@@ -1294,6 +1299,11 @@ int plan_bins(fb_ctx* c, int pwin, size_t& gws_need_out, Trace& tr) {
     return FB_OK;
 }
 
+void drop_graph(fb_ctx* c) {
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    c->graph_exec = nullptr;
+}
+
 // fb_upload, step 3 — streams and events per bin, device buffers, host -> device copies.
 int upload_buffers(fb_ctx* c, long long mp, long long co, size_t gws_need, Trace& tr) {
     fb_stats& st = c->stats;
@@ -1341,6 +1351,8 @@ int upload_buffers(fb_ctx* c, long long mp, long long co, size_t gws_need, Trace
     // ---- selection map and finalize geometry of the one-call pass
     c->fused_ok = !c->unit_mode && !c->rec_mode && !c->host_log;
     c->fused_dirty = false;
+    c->runs_since_upload = 0;
+    drop_graph(c);
     if (c->fused_ok) {
         c->h_sel_off.assign(ng + 1, 0);
         c->h_gmin.assign(ng, 0);
@@ -2085,112 +2097,144 @@ static int run_fused(fb_ctx* c) {
         FB_CUDA(c, cudaStreamSynchronize(c->stream));
         c->fused_dirty = false;
     }
-    FB_CUDA(c, cudaEventRecord(c->evs, c->stream));
     const size_t nb = c->bins.size();
-    FB_CUDA(c, cudaMemsetAsync(c->d_counters.p, 0, sizeof(int) * (3 * nb + 3), c->stream));
-    FB_CUDA(c, cudaMemsetAsync(c->go_disc(c->d_gapout.p), 0, sizeof(int) * 2 * c->gapout_n, c->stream));   // discarded + tickets
-    if (c->fin_counts_total) FB_CUDA(c, cudaMemsetAsync(c->d_fin_counts.p, 0, sizeof(int) * c->fin_counts_total, c->stream));
-    FB_CUDA(c, launch_stage(c, c->stream));
-    st.aux_launches = 1;
-    FB_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-    // pass: 0 the scan of every unit (without the last M-step when a second pass follows), 1 the winners again in full
-    auto scan_pass = [&](int pass) -> int {
-        if (nb > 1) FB_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));      // every bin's stream forks from here ...
-        for (size_t bi = 0; bi < nb; bi++) {
-            FbEmParams p;
-            fill_bin_params(c, bi, p);
-            if (pass == 0) {
-                p.skip_last_m = c->two_pass ? 1 : 0;
-            } else {
-                p.units = c->d_win_units.p + c->bins[bi].first_unit;
-                p.n_units_ptr = c->d_counters.p + 2 * nb + 2 + bi;
-                p.work_counter = c->d_counters.p + nb + 1 + bi;
-                p.unit_lik = nullptr;                        // pass 1 has written them, by the units' places in the full list
+    const bool fin = !c->fin_gaplist.empty();
+    st.aux_launches = 1 + (fin ? 1 : 0);
+    st.em_launches = (int)nb * ((c->two_pass && fin) ? 2 : 1);
+    st.finalize_launches = fin ? 1 : 0;
+    const long d2h = (long)(nu * sizeof(double)) + (fin ? (long)(c->fin_fill_total + 24 * c->gapout_n) : 0);
+    // The whole pass as a stream of operations.  `capturing`: the timing events become event-record nodes of a CUDA graph.
+    auto enqueue = [&](bool capturing) -> int {
+        auto rec = [&](cudaEvent_t ev) {
+            return capturing ? cudaEventRecordWithFlags(ev, c->stream, cudaEventRecordExternal) : cudaEventRecord(ev, c->stream);
+        };
+        FB_CUDA(c, rec(c->evs));
+        FB_CUDA(c, cudaMemsetAsync(c->d_counters.p, 0, sizeof(int) * (3 * nb + 3), c->stream));
+        FB_CUDA(c, cudaMemsetAsync(c->go_disc(c->d_gapout.p), 0, sizeof(int) * 2 * c->gapout_n, c->stream));   // discarded + tickets
+        if (c->fin_counts_total) FB_CUDA(c, cudaMemsetAsync(c->d_fin_counts.p, 0, sizeof(int) * c->fin_counts_total, c->stream));
+        FB_CUDA(c, launch_stage(c, c->stream));
+        FB_CUDA(c, rec(c->ev0));
+        // pass: 0 the scan of every unit (without the last M-step when a second pass follows), 1 the winners again in full
+        auto scan_pass = [&](int pass) -> int {
+            if (nb > 1) FB_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));      // every bin's stream forks from here ...
+            for (size_t bi = 0; bi < nb; bi++) {
+                FbEmParams p;
+                fill_bin_params(c, bi, p);
+                if (pass == 0) {
+                    p.skip_last_m = c->two_pass ? 1 : 0;
+                } else {
+                    p.units = c->d_win_units.p + c->bins[bi].first_unit;
+                    p.n_units_ptr = c->d_counters.p + 2 * nb + 2 + bi;
+                    p.work_counter = c->d_counters.p + nb + 1 + bi;
+                    p.unit_lik = nullptr;                        // pass 1 has written them, by the units' places in the full list
+                }
+                if (nb == 1) {                                   // a single launch needs no stream of its own
+                    FB_CUDA(c, launch_bin(c, c->bins[bi], p, c->stream));
+                } else {
+                    cudaStream_t bs = c->bin_streams[bi];
+                    FB_CUDA(c, cudaStreamWaitEvent(bs, c->ev_fork, 0));
+                    FB_CUDA(c, launch_bin(c, c->bins[bi], p, bs));
+                    FB_CUDA(c, cudaEventRecord(c->bin_done[bi], bs));
+                }
             }
-            if (nb == 1) {                                   // a single launch needs no stream of its own
-                FB_CUDA(c, launch_bin(c, c->bins[bi], p, c->stream));
-            } else {
-                cudaStream_t bs = c->bin_streams[bi];
-                FB_CUDA(c, cudaStreamWaitEvent(bs, c->ev_fork, 0));
-                FB_CUDA(c, launch_bin(c, c->bins[bi], p, bs));
-                FB_CUDA(c, cudaEventRecord(c->bin_done[bi], bs));
+            if (nb > 1)                                                          // ... and joins the main stream here
+                for (size_t bi = 0; bi < nb; bi++) FB_CUDA(c, cudaStreamWaitEvent(c->stream, c->bin_done[bi], 0));
+            return FB_OK;
+        };
+        int rc = scan_pass(0);
+        if (rc != FB_OK) return rc;
+        FbSelParams sp;
+        memset(&sp, 0, sizeof sp);
+        if (!c->fin_gaplist.empty()) {
+            sp.n_gaps = (int)ng;
+            sp.sel_off = c->d_sel_off.p;
+            sp.sel_unit = c->d_sel_unit.p;
+            sp.gmin = c->d_gmin.p;
+            sp.unit_lik = c->d_unit_lik.p;
+            sp.units = c->d_units.p;
+            sp.best_gp = c->go_gp(c->d_gapout.p);
+            sp.best_cons_off = c->go_off(c->d_gapout.p);
+            sp.best_lik = c->go_lik(c->d_gapout.p);
+            if (c->two_pass) {
+                sp.win_units = c->d_win_units.p;
+                sp.win_count = c->d_counters.p + 2 * nb + 2;
+                sp.bin_first = c->d_bin_first.p;
+                sp.n_bins = (int)nb;
             }
-            st.em_launches++;
+            FB_CUDA(c, fb_launch_select(sp, c->stream));
+            if (c->two_pass) {
+                rc = scan_pass(1);
+                if (rc != FB_OK) return rc;
+            }
         }
-        if (nb > 1)                                                          // ... and joins the main stream here
-            for (size_t bi = 0; bi < nb; bi++) FB_CUDA(c, cudaStreamWaitEvent(c->stream, c->bin_done[bi], 0));
+        FB_CUDA(c, rec(c->ev1));
+        if (!c->fin_gaplist.empty()) {
+            FbFinParams f;
+            memset(&f, 0, sizeof f);
+            f.ild = c->d_ild.p;
+            f.epos = c->d_epos.p;
+            f.match = c->d_match.p;
+            memcpy(f.T, c->T, sizeof f.T);
+            f.thr_min = c->thr_min;
+            f.thr_max = c->thr_max;
+            f.D = c->D;
+            f.gaps = c->d_gapmeta.p;
+            f.flank = c->d_flank.p;
+            f.codes = c->d_codes.p;
+            f.nmask = c->d_nmask.p;
+            f.rmeta = c->d_rmeta.p;
+            f.gap_list = c->d_gaplist.p;
+            f.best_gp = c->go_gp(c->d_gapout.p);
+            f.best_cons_off = c->go_off(c->d_gapout.p);
+            f.unit_cons = c->d_cons.p;
+            f.gmax_stride = c->fin_rows;
+            f.gb_stride = c->fin_gbmax;
+            f.theta = c->theta;
+            f.fin_counts = c->d_fin_counts.p;
+            f.fin_counts_off = c->d_fin_counts_off.p;
+            f.tickets = c->go_tick(c->d_gapout.p);
+            f.discarded = c->go_disc(c->d_gapout.p);
+            f.filled = c->d_filled.p;
+            f.filled_off = c->d_filled_off.p;
+            FB_CUDA(c, rec(c->ev2));
+            FB_CUDA(c, fb_launch_finalize(f, (int)c->fin_gaplist.size(), c->fin_slices, c->fin_smem, c->stream));
+            FB_CUDA(c, rec(c->ev3));
+            FB_CUDA(c, cudaMemcpyAsync(c->h_filled.p, c->d_filled.p, c->fin_fill_total, cudaMemcpyDeviceToHost, c->stream));
+            FB_CUDA(c, cudaMemcpyAsync(c->h_gapout.p, c->d_gapout.p, 24 * c->gapout_n, cudaMemcpyDeviceToHost, c->stream));   // all but the tickets
+        }
+        FB_CUDA(c, cudaMemcpyAsync(c->h_unit_lik.p, c->d_unit_lik.p, nu * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        FB_CUDA(c, rec(c->eve));
         return FB_OK;
     };
-    int rc = scan_pass(0);
-    if (rc != FB_OK) return rc;
-    long d2h = 0;
-    FbSelParams sp;
-    memset(&sp, 0, sizeof sp);
-    if (!c->fin_gaplist.empty()) {
-        sp.n_gaps = (int)ng;
-        sp.sel_off = c->d_sel_off.p;
-        sp.sel_unit = c->d_sel_unit.p;
-        sp.gmin = c->d_gmin.p;
-        sp.unit_lik = c->d_unit_lik.p;
-        sp.units = c->d_units.p;
-        sp.best_gp = c->go_gp(c->d_gapout.p);
-        sp.best_cons_off = c->go_off(c->d_gapout.p);
-        sp.best_lik = c->go_lik(c->d_gapout.p);
-        if (c->two_pass) {
-            sp.win_units = c->d_win_units.p;
-            sp.win_count = c->d_counters.p + 2 * nb + 2;
-            sp.bin_first = c->d_bin_first.p;
-            sp.n_bins = (int)nb;
+    // Passes with little device time (single gaps) are launch-bound: the sequence is captured once per upload into a CUDA
+    // graph and replayed (FB_NO_GRAPH=1 enqueues it operation by operation every time).
+    // The first pass after an upload goes out directly (a gap set that is filled once does not pay for the capture).
+    c->runs_since_upload++;
+    const bool want_graph = c->runs_since_upload > 1 && !c->graph_failed && !(getenv("FB_NO_GRAPH") && atoi(getenv("FB_NO_GRAPH")));
+    if (want_graph && !c->graph_exec) {
+        cudaGraph_t g = nullptr;
+        int rc = FB_ECUDA;
+        if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            rc = enqueue(true);
+            cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+            if (rc == FB_OK && e == cudaSuccess && g && cudaGraphInstantiate(&c->graph_exec, g, 0) == cudaSuccess) rc = FB_OK;
+            else rc = FB_ECUDA;
+            if (g) cudaGraphDestroy(g);
         }
-        FB_CUDA(c, fb_launch_select(sp, c->stream));
-        st.aux_launches++;
-        if (c->two_pass) {
-            rc = scan_pass(1);
-            if (rc != FB_OK) return rc;
+        if (rc != FB_OK) {
+            cudaGetLastError();
+            c->graph_exec = nullptr;
+            c->graph_failed = true;          // this context enqueues directly from now on
         }
     }
-    FB_CUDA(c, cudaEventRecord(c->ev1, c->stream));
-    if (!c->fin_gaplist.empty()) {
-        FbFinParams f;
-        memset(&f, 0, sizeof f);
-        f.ild = c->d_ild.p;
-        f.epos = c->d_epos.p;
-        f.match = c->d_match.p;
-        memcpy(f.T, c->T, sizeof f.T);
-        f.thr_min = c->thr_min;
-        f.thr_max = c->thr_max;
-        f.D = c->D;
-        f.gaps = c->d_gapmeta.p;
-        f.flank = c->d_flank.p;
-        f.codes = c->d_codes.p;
-        f.nmask = c->d_nmask.p;
-        f.rmeta = c->d_rmeta.p;
-        f.gap_list = c->d_gaplist.p;
-        f.best_gp = c->go_gp(c->d_gapout.p);
-        f.best_cons_off = c->go_off(c->d_gapout.p);
-        f.unit_cons = c->d_cons.p;
-        f.gmax_stride = c->fin_rows;
-        f.gb_stride = c->fin_gbmax;
-        f.theta = c->theta;
-        f.fin_counts = c->d_fin_counts.p;
-        f.fin_counts_off = c->d_fin_counts_off.p;
-        f.tickets = c->go_tick(c->d_gapout.p);
-        f.discarded = c->go_disc(c->d_gapout.p);
-        f.filled = c->d_filled.p;
-        f.filled_off = c->d_filled_off.p;
-        FB_CUDA(c, cudaEventRecord(c->ev2, c->stream));
-        FB_CUDA(c, fb_launch_finalize(f, (int)c->fin_gaplist.size(), c->fin_slices, c->fin_smem, c->stream));
-        FB_CUDA(c, cudaEventRecord(c->ev3, c->stream));
-        st.finalize_launches = 1;
-        FB_CUDA(c, cudaMemcpyAsync(c->h_filled.p, c->d_filled.p, c->fin_fill_total, cudaMemcpyDeviceToHost, c->stream));
-        FB_CUDA(c, cudaMemcpyAsync(c->h_gapout.p, c->d_gapout.p, 24 * c->gapout_n, cudaMemcpyDeviceToHost, c->stream));   // all but the tickets
-        d2h += (long)(c->fin_fill_total + 24 * c->gapout_n);
+    if (want_graph && c->graph_exec) {
+        FB_CUDA(c, cudaGraphLaunch(c->graph_exec, c->stream));
+    } else {
+        int rc = enqueue(false);
+        if (rc != FB_OK) return rc;
     }
-    FB_CUDA(c, cudaMemcpyAsync(c->h_unit_lik.p, c->d_unit_lik.p, nu * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    d2h += (long)(nu * sizeof(double));
-    FB_CUDA(c, cudaEventRecord(c->eve, c->stream));
     tr.lap("run: enqueued");
-    FB_CUDA(c, cudaEventSynchronize(c->eve));
+    FB_CUDA(c, cudaStreamSynchronize(c->stream));     // (not the last event: a graph's record node has not marked it pending yet)
     tr.lap("run: device");
     // ---- results to the gaps (figbird.cpp:2382, 2050-2063, 2503)
     const int D = c->D;
