@@ -6,7 +6,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 WORK = sys.argv[1].split(",") if len(sys.argv) > 1 else ["cfg1_single_gap", "cfg5_stress_g100_c30_k1", "cfg5_stress_g500_c300_k1", "cfg5_stress_g500_c30_k1", "cfg5_stress_g1000_c30_k1"]
-KNOBS = [{}, {"FB_NO_FEW": "1"}, {"FB_TWO_CALL": "1"}, {"FB_THREADS1": "512"}, {"FB_ONE_CTA": "1", "FB_CLUSTER": "2"}, {"FB_ONE_CTA": "1", "FB_CLUSTER": "1"}]
+KNOBS = [{}, {"FB_NO_GRAPH": "1"}, {"FB_TWO_CALL": "1"}, {"FB_NO_FEW": "1"}]
 for w in WORK:
     for k in KNOBS:
         env = dict(os.environ, **k)
