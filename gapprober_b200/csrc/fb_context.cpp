@@ -194,6 +194,9 @@ struct fb_ctx {
     DevBuf<FbRecMeta> d_rmeta;
     DevBuf<uint32_t> d_st_mask, d_st_cls4;           // per-record tables built on the device by fb_stage_kernel
     DevBuf<uint8_t> d_st_jl, d_st_cum;
+    DevBuf<double> d_pre;                            // left-flank prefix table (fb_prefix_kernel), 32 doubles per chain
+    size_t pre_chains = 0;                           // 0: no table (nothing to tabulate, FB_NO_PREFIX, or more chains than the flags can index)
+    int pre_slices = 1;
     DevBuf<FbUnit> d_units, d_units_scan;          // _scan: the units / gap metadata a record-sharded scan launches with
     DevBuf<FbGapMeta> d_gapmeta_scan;
     DevBuf<double> d_parts[2], d_sumcounts, d_maxmerge;
@@ -406,7 +409,7 @@ void fb_destroy(fb_ctx* c) {
     c->d_gapmeta.release(); c->d_flank.release(); c->d_codes.release(); c->d_nmask.release(); c->d_rmeta.release();
     c->d_units.release(); c->d_counters.release(); c->d_maxprob.release(); c->d_gws.release();
     c->d_dump.release(); c->d_cons.release(); c->d_gaplist.release(); c->d_gapout.release(); c->h_gapout.release();
-    c->d_st_mask.release(); c->d_st_cls4.release(); c->d_st_jl.release(); c->d_st_cum.release();
+    c->d_st_mask.release(); c->d_st_cls4.release(); c->d_st_jl.release(); c->d_st_cum.release(); c->d_pre.release();
     c->d_units_scan.release(); c->d_gapmeta_scan.release(); c->d_parts[0].release(); c->d_parts[1].release();
     c->d_sumcounts.release(); c->d_maxmerge.release(); c->d_unit_nrec.release(); c->d_shard_err.release(); c->d_flags.release();
     c->h_maxprob.release(); c->h_stage.release();
@@ -1412,6 +1415,35 @@ int upload_buffers(fb_ctx* c, long long mp, long long co, size_t gws_need, Trace
         FB_CUDA(c, c->d_gmin.ensure(ng));
         FB_CUDA(c, c->d_fin_counts.ensure(c->fin_counts_total));
     }
+    // ---- left-flank prefix table (FbPrefixParams): a record's chains with at least four left-flank terms in every lane
+    {
+        const bool want = !getenv("FB_NO_PREFIX");
+        const int D = c->D;
+        size_t chains = 0;
+        bool fits = true;
+        int max_nrec = 1;
+        for (const HostGap& g : c->gaps) max_nrec = std::max(max_nrec, g.nrec);
+        for (FbRecMeta& m : c->h_rmeta) {
+            m.flags &= (1 << FB_PRE_SHIFT) - 1;
+            if (!want || !fits) continue;
+            const int L2 = m.flags & 0xff;
+            const long lo = std::max<long>(m.a_lo, D - L2 + 1);
+            if (m.a_hi < lo) continue;
+            const long n = std::min<long>((D - lo - 3) / 32, ((long)m.a_hi - lo + 32) / 32);
+            if (n <= 0) continue;
+            if (chains + (size_t)n >= FB_PRE_MAX_CHAINS) { fits = false; continue; }
+            m.flags |= (int)((unsigned)chains << FB_PRE_SHIFT);
+            chains += (size_t)n;
+        }
+        if (!fits) {
+            for (FbRecMeta& m : c->h_rmeta) m.flags &= (1 << FB_PRE_SHIFT) - 1;
+            chains = 0;
+        }
+        c->pre_chains = chains;
+        if (chains) FB_CUDA(c, c->d_pre.ensure(chains * 32));
+        const int per_cta = 8, ngp = std::max<int>(1, (int)ng);
+        c->pre_slices = std::max(1, std::min((4 * c->sm_count + ngp - 1) / ngp, (max_nrec + per_cta - 1) / per_cta));
+    }
     long h2d = 0;
     const size_t stage_need = ng * sizeof(FbGapMeta) + c->h_flank.size() + (c->h_codes.size() + c->h_nmask.size()) * sizeof(uint4) +
                               nr * sizeof(FbRecMeta) + c->h_units.size() * sizeof(FbUnit) + 12 * 256 +
@@ -1529,6 +1561,7 @@ void fill_em_params(fb_ctx* c, FbEmParams& p) {
     p.st_cls4 = c->d_st_cls4.p;
     p.st_jl = c->d_st_jl.p;
     p.st_cum = c->d_st_cum.p;
+    p.pre = c->pre_chains ? c->d_pre.p : nullptr;
     p.unit_maxprob = c->d_maxprob.p;
     p.unit_cons = c->d_cons.p;
     p.dump_unit = -1;
@@ -1546,7 +1579,21 @@ cudaError_t launch_stage(fb_ctx* c, cudaStream_t s) {
     sp.st_cls4 = c->d_st_cls4.p;
     sp.st_jl = c->d_st_jl.p;
     sp.st_cum = c->d_st_cum.p;
-    return fb_launch_stage(sp, s);
+    cudaError_t e = fb_launch_stage(sp, s);
+    if (e != cudaSuccess || !c->pre_chains) return e;
+    FbPrefixParams pp;
+    memcpy(pp.eo_tab, c->h_eo.data(), sizeof pp.eo_tab);
+    memcpy(pp.T, c->T, sizeof pp.T);
+    pp.ild = c->d_ild_em.p;
+    pp.thr_min = c->thr_min;
+    pp.D = c->D;
+    pp.gaps = c->d_gapmeta.p;
+    pp.n_gaps = (int)c->h_gapmeta.size();
+    pp.flank = c->d_flank.p;
+    pp.rmeta = c->d_rmeta.p;
+    pp.st_cls4 = c->d_st_cls4.p;
+    pp.pre = c->d_pre.p;
+    return fb_launch_prefix(pp, c->pre_slices, c->f1, s);
 }
 
 cudaError_t launch_bin(const fb_ctx* c, const Bin& b, const FbEmParams& p, cudaStream_t s) {
@@ -1593,7 +1640,7 @@ int fb_run_scan(fb_ctx* c) {
     FB_CUDA(c, cudaEventRecord(c->evs, c->stream));
     FB_CUDA(c, cudaMemsetAsync(c->d_counters.p, 0, sizeof(int) * (c->bins.size() + 1), c->stream));
     FB_CUDA(c, launch_stage(c, c->stream));
-    st.aux_launches = 1;
+    st.aux_launches = 1 + (c->pre_chains ? 1 : 0);
     FB_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     for (size_t bi = 0; bi < c->bins.size(); bi++) {
         const Bin& b = c->bins[bi];
@@ -1851,7 +1898,7 @@ int shard_enqueue_iter(fb_ctx* c, int it, const double* const* peer_counts, doub
         // records scanned elsewhere keep 0 in this rank's maxima, so the ranks' buffers merge with max
         FB_CUDA(c, cudaMemsetAsync(c->d_maxprob.p, 0, sizeof(double) * c->shard_maxprob, c->stream));
         FB_CUDA(c, launch_stage(c, c->stream));
-        st.aux_launches = 1;
+        st.aux_launches = 1 + (c->pre_chains ? 1 : 0);
     }
     FB_CUDA(c, cudaMemsetAsync(c->d_counters.p, 0, sizeof(int) * (c->bins.size() + 1), c->stream));
     FB_CUDA(c, cudaEventRecord(c->ev0, c->stream));
@@ -2099,7 +2146,7 @@ static int run_fused(fb_ctx* c) {
     }
     const size_t nb = c->bins.size();
     const bool fin = !c->fin_gaplist.empty();
-    st.aux_launches = 1 + (fin ? 1 : 0);
+    st.aux_launches = 1 + (c->pre_chains ? 1 : 0) + (fin ? 1 : 0);
     st.em_launches = (int)nb * ((c->two_pass && fin) ? 2 : 1);
     st.finalize_launches = fin ? 1 : 0;
     const long d2h = (long)(nu * sizeof(double)) + (fin ? (long)(c->fin_fill_total + 24 * c->gapout_n) : 0);

@@ -18,8 +18,11 @@
 struct FbRecMeta {
     int a_lo, a_hi;
     int tb;
-    int flags;   // bits 0-7 mate length, bit 8 isReverse (anchor forward), bit 9 anchor left of gap
+    int flags;   // bits 0-7 mate length, bit 8 isReverse (anchor forward), bit 9 anchor left of gap,
+                 // bits 10-31: first chain of this record in the left-flank prefix table (set at upload; see FbPrefixParams)
 };
+#define FB_PRE_SHIFT 10
+#define FB_PRE_MAX_CHAINS (1u << 22)
 
 struct FbGapMeta {
     int rec_off, nrec;
@@ -54,6 +57,7 @@ struct FbEmParams {
     const uint32_t* st_cls4;   // [n_records][16]
     const uint8_t* st_jl;      // [n_records][FB_MAX_READ + 16]
     const uint8_t* st_cum;     // [n_records][32]
+    const double* pre;         // left-flank prefix table (fb_prefix_kernel); nullptr: every chain starts at ILD[t]
     // work list
     const FbUnit* units;
     int n_units;
@@ -95,6 +99,30 @@ struct FbStageParams {
     uint8_t* st_jl;
     uint8_t* st_cum;
 };
+
+// Left-flank prefixes.  A placement u < D multiplies its first D - u terms against rows of the left flank, and those
+// rows never change: not between the iterations, not between the estimates of a gap (figbird.cpp:1657-1664 writes them
+// once, placeReads only zeroes and refills the gap rows, :1708-1714).  The insert size of a placement does not depend on
+// the estimate either (pack_gap).  So the running score of placement u after its first flank terms is the same number in
+// every E-step of every unit of the gap.  A record's placements are dealt to lanes in chains of 32 (slot k = u - lo,
+// lo = max(a_lo, D - L2 + 1)); for chain c every lane has at least js = D - (lo + 32c + 31) flank terms.  When js >= 4 the
+// table holds, per lane, the score after the first (js & ~3) terms — computed by the same operations in the same order
+// (ILD[t], then one rounded term and one rounded product per base) — and the E-step starts the chain from there.
+// A record owns n = min((D - lo - 3) / 32, chains of [lo, a_hi]) consecutive chains of 32 doubles from the chain index
+// in its flags; slots past a_hi hold 0.
+struct FbPrefixParams {
+    double2 eo_tab[FB_MAX_READ];
+    double T[25];
+    const double* ild;         // the E-step's start values (ILD[t], or log(ILD[t]) in f=1 mode), [thr_min .. thr_max]
+    int thr_min, D;
+    const FbGapMeta* gaps;
+    int n_gaps;
+    const uint8_t* flank;
+    const FbRecMeta* rmeta;
+    const uint32_t* st_cls4;   // built by fb_stage_kernel earlier in the stream
+    double* pre;
+};
+cudaError_t fb_launch_prefix(const FbPrefixParams& p, int slices, bool f1, cudaStream_t s);   // CTAs per gap = slices
 
 // Closing step of a record-sharded scan: rank-ordered sum of the partial counts -> computeSequence(0); per-record
 // maxima merged over the ranks.

@@ -242,12 +242,14 @@ __device__ __forceinline__ double score_step(double s, double term) {
     return F1 ? dadd(s, fbm_log(term)) : dmul(s, term);
 }
 
+// [jb, je): the bases to multiply in; jb is a multiple of 4 (a chain with a left-flank prefix starts past its first terms).
 template <bool REV, bool TWO, bool F1>
 __device__ __forceinline__ void score_pair(const unsigned char* pa, const uint32_t* __restrict__ cls4, unsigned cstride, const FbEmParams& p,
-                                           int L2, double& sa, double& sb) {
-    int k = REV ? L2 - 1 : 0;    // read-position index of base j (figbird.cpp:1845-1852)
-    int j0 = 0;
-    for (; j0 + 4 <= L2; j0 += 4) {
+                                           int L2, int jb, int je, double& sa, double& sb) {
+    int k = REV ? L2 - 1 - jb : jb;    // read-position index of base j (figbird.cpp:1845-1852)
+    int j0 = jb;
+    pa += jb * 16;
+    for (; j0 + 4 <= je; j0 += 4) {
         const uint32_t cw = cls4[j0 >> 3] >> ((j0 & 4) * 4);                // four base classes, 4 bits each
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -263,7 +265,7 @@ __device__ __forceinline__ void score_pair(const unsigned char* pa, const uint32
         pa += 64;
         k += REV ? -4 : 4;
     }
-    for (; j0 < L2; j0++) {
+    for (; j0 < je; j0++) {
         const unsigned c = (cls4[j0 >> 3] >> ((j0 & 7) * 4)) & 7u;
         const unsigned char* a = pa + c * cstride;
         const double2 va = *reinterpret_cast<const double2*>(a);
@@ -349,6 +351,61 @@ __global__ void __launch_bounds__(256) fb_stage_kernel(const FbStageParams p) {
             }
         }
         start = (start + n3 + n2 + n1 + n0 + 3) & ~3;     // next class starts on a 32-bit boundary
+    }
+}
+
+// Left-flank prefixes (FbPrefixParams in fb_device.h): warp per record, lanes over the 32 placements of a chain.  The
+// operations are the E-step's own — start value, then per base one rounded term and one rounded product (or log and
+// sum in f=1) in read order — against the one-hot rows initialize() gives the flank, so the E-step may start from the
+// stored value and produce the same bits as if it had started at base 0.
+template <bool F1>
+__global__ void __launch_bounds__(256) fb_prefix_kernel(const __grid_constant__ FbPrefixParams p) {
+    __shared__ double sT[25];
+    __shared__ double2 sRow[5][5];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    if (tid < 25) sT[tid] = p.T[tid];
+    __syncthreads();
+    if (tid < 5) {
+        double c[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) c[k] = (k == tid) ? 1.0 : 0.0;
+        double P[4], Q[5];
+        profile_row(c, sT, P, Q);
+#pragma unroll
+        for (int k = 0; k < 4; k++) sRow[tid][k] = make_double2(P[k], Q[k]);
+        sRow[tid][4] = make_double2(0.0, Q[4]);
+    }
+    __syncthreads();
+    const int D = p.D;
+    for (int g = blockIdx.x; g < p.n_gaps; g += gridDim.x) {
+        const FbGapMeta gm = p.gaps[g];
+        const uint8_t* fl = p.flank + (size_t)g * 2 * D;
+        for (int r = blockIdx.y * nwarp + warp; r < gm.nrec; r += gridDim.y * nwarp) {
+            const size_t rec = (size_t)gm.rec_off + r;
+            const FbRecMeta rm = p.rmeta[rec];
+            const int L2 = rm.flags & 0xff;
+            const bool rev = (rm.flags >> 8) & 1, left = (rm.flags >> 9) & 1;
+            const int lo = max(rm.a_lo, D - L2 + 1);
+            if (rm.a_hi < lo) continue;
+            const int npc = min((D - lo - 3) / 32, (rm.a_hi - lo + 32) / 32);
+            const uint32_t* cls4 = p.st_cls4 + rec * 16;
+            double* out = p.pre + ((size_t)((unsigned)rm.flags >> FB_PRE_SHIFT)) * 32 + lane;
+            for (int c = 0; c < npc; c++) {
+                const int u = lo + 32 * c + lane;
+                const int skip = (D - (lo + 32 * c + 31)) & ~3;
+                double s = 0.0;
+                if (u <= rm.a_hi) {
+                    s = p.ild[(left ? u + rm.tb : rm.tb - u) - p.thr_min];
+                    for (int j = 0; j < skip; j++) {
+                        const unsigned cl = (cls4[j >> 3] >> ((j & 7) * 4)) & 7u;
+                        const double2 v = sRow[fl[u + j]][cl];
+                        const double2 e = p.eo_tab[rev ? L2 - 1 - j : j];
+                        s = score_step<F1>(s, dadd(dmul(v.x, e.x), dmul(e.y, v.y)));
+                    }
+                }
+                out[(size_t)c * 32] = s;
+            }
+        }
     }
 }
 
@@ -619,12 +676,35 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
                         const uint32_t* cls4 = SE.cls4 + rl * 16;
                         const unsigned cstride = (unsigned)nrs * 16u;
                         const bool two = lo + 64 * blk + 32 <= hi;           // any lane with a second placement?
+                        // Left-flank prefixes (FbPrefixParams): every lane of chain A has at least jsA terms against left-flank
+                        // rows, chain B 32 fewer; where that is 4 or more the chain starts from the tabulated running score.
+                        int skA = 0, skB = 0;
+                        if (p.pre) {
+                            const int jsA = D - (lo + 64 * blk + 31);
+                            if (jsA >= 4) {
+                                const double* pr = p.pre + ((size_t)((unsigned)fl2 >> FB_PRE_SHIFT) + 2 * (size_t)blk) * 32 + lane;
+                                skA = jsA & ~3;
+                                sa = __ldg(pr);
+                                if (two && jsA >= 36) {
+                                    skB = skA - 32;
+                                    sb = __ldg(pr + 32);
+                                }
+                            }
+                        }
+                        if (!two || skB < skA) {
+                            // one chain alone: the whole of a one-chain task, or chain B's terms before chain A's first
+                            const bool headB = two;
+                            double s1 = headB ? sb : sa, s2 = 0.0;
+                            const unsigned char* p1 = headB ? pa + 32 * 16 : pa;
+                            const int jb = headB ? skB : skA, je = headB ? skA : L2;
+                            if (rev) score_pair<true, false, F1>(p1, cls4, cstride, p, L2, jb, je, s1, s2);
+                            else score_pair<false, false, F1>(p1, cls4, cstride, p, L2, jb, je, s1, s2);
+                            if (headB) sb = s1;
+                            else sa = s1;
+                        }
                         if (two) {
-                            if (rev) score_pair<true, true, F1>(pa, cls4, cstride, p, L2, sa, sb);
-                            else score_pair<false, true, F1>(pa, cls4, cstride, p, L2, sa, sb);
-                        } else {
-                            if (rev) score_pair<true, false, F1>(pa, cls4, cstride, p, L2, sa, sb);
-                            else score_pair<false, false, F1>(pa, cls4, cstride, p, L2, sa, sb);
+                            if (rev) score_pair<true, true, F1>(pa, cls4, cstride, p, L2, skA, L2, sa, sb);
+                            else score_pair<false, true, F1>(pa, cls4, cstride, p, L2, skA, L2, sa, sb);
                         }
                         // what the M-step adds to the counts: the score itself, pow(10, score) in f=1 (figbird.cpp:1878, 1879)
                         double wa = sa, wb = sb;
@@ -1066,6 +1146,14 @@ cudaError_t fb_launch_finalize(const FbFinParams& p, int n, int slices, size_t s
 cudaError_t fb_launch_shard_finish(const FbShardFinParams& p, cudaStream_t s) {
     if (p.n_units < 1) return cudaSuccess;
     fb_shard_finish_kernel<<<p.n_units < 4096 ? p.n_units : 4096, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t fb_launch_prefix(const FbPrefixParams& p, int slices, bool f1, cudaStream_t s) {
+    if (p.n_gaps < 1) return cudaSuccess;
+    const dim3 grid((unsigned)(p.n_gaps < 65535 ? p.n_gaps : 65535), (unsigned)(slices < 1 ? 1 : slices), 1);   // CTA (gap, slice): every slices-th group of 8 records
+    if (f1) fb_prefix_kernel<true><<<grid, 256, 0, s>>>(p);
+    else fb_prefix_kernel<false><<<grid, 256, 0, s>>>(p);
     return cudaGetLastError();
 }
 
