@@ -351,9 +351,11 @@ def run_ours(a):
     from gapprober_b200 import GapBatch
     batch = GapBatch([(gaps[i][0], gaps[i][1], gaps[i][2], gap_files[i], seqs[gaps[i][0]]) for i in mine])
 
+    fillers = [None]                           # the GapFiller objects of the last registration, in the order of `mine`
+
     def register():
         fb.clearGaps()
-        fb.add_gap_files(batch)                # the library reads, parses and packs the gap files (host threads)
+        fillers[0] = fb.add_gap_files(batch)   # the library reads, parses and packs the gap files (host threads)
         if by_estimate:
             fb.setPartitionUnits(rank, world)
 
@@ -380,6 +382,12 @@ def run_ours(a):
             fb.runDevice()
 
     def run_e2e():
+        if not (by_record or by_estimate):
+            # the reference-facing call: gap files in, filled sequences out (fb_fill_gap_files: the gap set goes to the
+            # device in two batches so that parsing/packing/planning of the second overlaps the scan of the first)
+            fb.clearGaps()
+            fillers[0] = fb.fill_gap_files(batch)
+            return
         register()
         if by_record:
             open_session()                  # partition + upload + mapping of the peers' exchange buffers
@@ -389,8 +397,6 @@ def run_ours(a):
             fb.upload()
             fb.runScan()
             exchange_and_finalize()
-        else:
-            fb.fillGaps()
 
     def allmax(x):
         if world == 1:
@@ -470,9 +476,9 @@ def run_ours(a):
     # digest must not depend on N or on the partition (compare the lines of the 1/2/4/8-GPU runs).
     from gapprober_b200.multigpu import gather_results
     local_fill = {}
-    for k, gi in enumerate(mine):
-        if fb.hasResult(k):
-            local_fill[(rank if weak else 0, gi)] = fb._gaps[k].result()["filled"]
+    for gf, gi in zip(fillers[0], mine):
+        if fb.hasResult(gf.index):
+            local_fill[(rank if weak else 0, gi)] = gf.result()["filled"]
     fills = gather_results(local_fill)
     filled_total = sum(len(v) for v in fills.values())
     digest = sha_of_fills({f"{k[0]}/{k[1]}": v for k, v in fills.items()})

@@ -165,6 +165,7 @@ struct fb_ctx {
     double T[25];
     std::vector<double> epos, match;
     std::vector<double2> h_eo;   // {1 - e[k], e[k]}, copied into every EM launch's parameters
+    std::vector<double> h_t0;    // FbEmParams::t0_tab, computed on the device at fb_create
     // model (device)
     DevBuf<double> d_ild, d_epos, d_match;
     DevBuf<double> d_ild_em;   // what the E-step starts a score from: ILD[t], or log(ILD[t]) from the host libm in f=1 mode
@@ -241,6 +242,13 @@ struct fb_ctx {
     PinBuf<double> h_maxprob, h_unit_lik;
     PinBuf<char> h_filled;
     PinBuf<unsigned char> h_stage;   // pinned staging for the host->device copies
+
+    // fb_fill_gap_files: the model as fb_create received it (a second context is created from it on first use), the
+    // context that runs the first batch, and whether the gaps of the last fill are spread over both
+    std::vector<double> m_error_pos, m_in_pos, m_del_pos, m_ild;
+    fb_model m_model;
+    fb_ctx* child = nullptr;
+    bool piped = false;
 
     fb_stats stats;
     double t_parse_ms = 0, t_pack_ms = 0;   // FB_TRACE: time spent in fb_add_gap_file since the last upload
@@ -375,6 +383,12 @@ int fb_create(const fb_model* m, int device, fb_ctx** out) {
         c->epos[k] = m->error_pos[k];
         c->match[k] = 1 - m->error_pos[k] - m->in_pos[k] - m->del_pos[k];           // figbird.cpp:2272
     }
+    c->m_error_pos.assign(m->error_pos, m->error_pos + m->max_read_len);
+    c->m_in_pos.assign(m->in_pos, m->in_pos + m->max_read_len);
+    c->m_del_pos.assign(m->del_pos, m->del_pos + m->max_read_len);
+    c->m_ild.assign(m->ild, m->ild + m->ild_len);
+    c->m_model = *m;
+    c->m_model.error_pos = c->m_model.in_pos = c->m_model.del_pos = c->m_model.ild = nullptr;   // set when a copy is handed out
     c->f1 = m->f_mode == 1;
     c->host_log = getenv("FB_HOST_LOG") && atoi(getenv("FB_HOST_LOG")) != 0;
     if (!cutoff_threshold(m->gap_prob_cutoff, &c->theta)) {
@@ -395,6 +409,19 @@ int fb_create(const fb_model* m, int device, fb_ctx** out) {
     }
     cudaMemcpy(c->d_epos.p, c->epos.data(), sizeof(double) * FB_MAX_READ, cudaMemcpyHostToDevice);
     cudaMemcpy(c->d_match.p, c->match.data(), sizeof(double) * FB_MAX_READ, cudaMemcpyHostToDevice);
+    {
+        // the first iteration's gap-row terms (FbEmParams::t0_tab): by the device's own operations, then kept on the host
+        DevBuf<double2> d_eo;
+        DevBuf<double> d_T, d_t0;
+        c->h_t0.assign(5 * FB_MAX_READ, 0.0);
+        if (d_eo.ensure(FB_MAX_READ) || d_T.ensure(25) || d_t0.ensure(5 * FB_MAX_READ)) return bail(FB_ECUDA);
+        cudaMemcpy(d_eo.p, eo.data(), sizeof(double2) * FB_MAX_READ, cudaMemcpyHostToDevice);
+        cudaMemcpy(d_T.p, c->T, sizeof c->T, cudaMemcpyHostToDevice);
+        cudaError_t e = fb_launch_t0(d_eo.p, d_T.p, d_t0.p, c->f1, nullptr);
+        if (e == cudaSuccess) e = cudaMemcpy(c->h_t0.data(), d_t0.p, sizeof(double) * 5 * FB_MAX_READ, cudaMemcpyDeviceToHost);
+        d_eo.release(); d_T.release(); d_t0.release();
+        if (e != cudaSuccess) return bail(FB_ECUDA);
+    }
     if (cudaDeviceSynchronize() != cudaSuccess) return bail(FB_ECUDA);
     *out = c;
     return FB_OK;
@@ -402,6 +429,8 @@ int fb_create(const fb_model* m, int device, fb_ctx** out) {
 
 void fb_destroy(fb_ctx* c) {
     if (!c) return;
+    if (c->child) fb_destroy(c->child);
+    c->child = nullptr;
     cudaSetDevice(c->device);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     c->graph_exec = nullptr;
@@ -433,6 +462,8 @@ void fb_destroy(fb_ctx* c) {
 
 int fb_clear_gaps(fb_ctx* c) {
     if (!c) return FB_EINVAL;
+    if (c->child) fb_clear_gaps(c->child);
+    c->piped = false;
     c->gaps.clear(); c->h_gapmeta.clear(); c->h_flank.clear(); c->h_codes.clear(); c->h_nmask.clear();
     c->h_rmeta.clear(); c->h_bytes.clear(); c->h_units.clear(); c->unit_nrec.clear(); c->bins.clear();
     c->uploaded = c->ran = c->scanned = false;
@@ -768,6 +799,7 @@ extern "C" {
 int fb_add_gap(fb_ctx* c, int contig_no, long gap_start, int orig_gap, const char* contig, long contig_len,
                const fb_record* recs, int nrec) {
     if (!c || !contig || nrec < 0 || (nrec > 0 && !recs)) return FB_EINVAL;
+    if (c && c->piped) return c->fail(FB_ESTATE, "the gaps of fb_fill_gap_files can only be read or run again (fb_run_device); fb_clear_gaps starts over");
     PackedGap pk;
     pack_gap(consts_of(c), contig_no, gap_start, orig_gap, contig, contig_len, recs, nrec, pk);
     return append_gap(c, pk);
@@ -775,6 +807,7 @@ int fb_add_gap(fb_ctx* c, int contig_no, long gap_start, int orig_gap, const cha
 
 int fb_add_gap_file(fb_ctx* c, int contig_no, long gap_start, int orig_gap, const char* contig, long contig_len, const char* gap_file) {
     if (!c || !gap_file || !contig) return FB_EINVAL;
+    if (c && c->piped) return c->fail(FB_ESTATE, "the gaps of fb_fill_gap_files can only be read or run again (fb_run_device); fb_clear_gaps starts over");
     PackedGap pk;
     parse_and_pack(consts_of(c), contig_no, gap_start, orig_gap, contig, contig_len, gap_file, pk);
     return append_gap(c, pk);
@@ -782,6 +815,7 @@ int fb_add_gap_file(fb_ctx* c, int contig_no, long gap_start, int orig_gap, cons
 
 int fb_add_gap_files(fb_ctx* c, const fb_gap_desc* descs, int n, int* handles, int threads) {
     if (!c || n < 0 || (n > 0 && (!descs || !handles))) return FB_EINVAL;
+    if (c && c->piped) return c->fail(FB_ESTATE, "the gaps of fb_fill_gap_files can only be read or run again (fb_run_device); fb_clear_gaps starts over");
     const PackConsts k = consts_of(c);
     std::vector<PackedGap> packed((size_t)n);
     const auto t0 = std::chrono::steady_clock::now();
@@ -894,6 +928,7 @@ double fb_gap_cost(fb_ctx* c, int gap) {
 }
 
 int fb_set_partition(fb_ctx* c, int rank, int world) {
+    if (c && c->piped) return c->fail(FB_ESTATE, "the gaps of fb_fill_gap_files can only be read or run again (fb_run_device); fb_clear_gaps starts over");
     if (!c || world < 1 || rank < 0 || rank >= world) return FB_EINVAL;
     c->part_rank = rank;
     c->part_world = world;
@@ -917,6 +952,7 @@ int fb_set_partition(fb_ctx* c, int rank, int world) {
 }
 
 int fb_set_partition_units(fb_ctx* c, int rank, int world) {
+    if (c && c->piped) return c->fail(FB_ESTATE, "the gaps of fb_fill_gap_files can only be read or run again (fb_run_device); fb_clear_gaps starts over");
     if (!c || world < 1 || rank < 0 || rank >= world) return FB_EINVAL;
     c->part_rank = rank;
     c->part_world = world;
@@ -949,6 +985,7 @@ int fb_set_partition_units(fb_ctx* c, int rank, int world) {
 }
 
 int fb_set_partition_records(fb_ctx* c, int rank, int world) {
+    if (c && c->piped) return c->fail(FB_ESTATE, "the gaps of fb_fill_gap_files can only be read or run again (fb_run_device); fb_clear_gaps starts over");
     if (!c || world < 1 || world > FB_MAX_SHARDS || rank < 0 || rank >= world) return FB_EINVAL;
     if (c->f1) return c->fail(FB_EUNSUPPORTED, "the record-sharded scan runs f=0 only (gap and estimate partitions run both modes)");
     c->part_rank = rank;
@@ -968,6 +1005,7 @@ int fb_set_partition_records(fb_ctx* c, int rank, int world) {
 }
 
 int fb_owns_gap(fb_ctx* c, int gap) {
+    if (c && c->piped && c->child && gap >= (int)c->gaps.size()) return fb_owns_gap(c->child, gap - (int)c->gaps.size());
     if (!c || gap < 0 || gap >= (int)c->gaps.size()) return 0;
     if (c->rec_mode) return gap % c->part_world == c->part_rank ? 1 : 0;   // who finalizes the gap
     return c->gaps[gap].owned ? 1 : 0;
@@ -1525,6 +1563,7 @@ extern "C" {
 
 int fb_upload(fb_ctx* c) {
     if (!c) return FB_EINVAL;
+    if (c && c->piped) return c->fail(FB_ESTATE, "the gaps of fb_fill_gap_files can only be read or run again (fb_run_device); fb_clear_gaps starts over");
     FB_CUDA(c, cudaSetDevice(c->device));
     const int pwin = c->thr_max - c->thr_min + 1;
     Trace tr;
@@ -1562,6 +1601,8 @@ void fill_em_params(fb_ctx* c, FbEmParams& p) {
     p.st_jl = c->d_st_jl.p;
     p.st_cum = c->d_st_cum.p;
     p.pre = c->pre_chains ? c->d_pre.p : nullptr;
+    memcpy(p.t0_tab, c->h_t0.data(), sizeof p.t0_tab);
+    p.use_t0 = getenv("FB_NO_T0") ? 0 : 1;
     p.unit_maxprob = c->d_maxprob.p;
     p.unit_cons = c->d_cons.p;
     p.dump_unit = -1;
@@ -1626,6 +1667,7 @@ extern "C" {
 // FB_HOST_LOG=1 keeps the round-1 route for comparison: per-record maxima to the host, log() and the sum by the host libm.
 int fb_run_scan(fb_ctx* c) {
     if (!c) return FB_EINVAL;
+    if (c && c->piped) return c->fail(FB_ESTATE, "the gaps of fb_fill_gap_files can only be read or run again (fb_run_device); fb_clear_gaps starts over");
     if (!c->uploaded) return c->fail(FB_ESTATE, "fb_run_scan before fb_upload");
     if (c->rec_mode && c->part_world > 1) return c->fail(FB_ESTATE, "record-sharded partition: use fb_shard_scan_iter / fb_shard_scan_finish");
     FB_CUDA(c, cudaSetDevice(c->device));
@@ -1723,6 +1765,7 @@ int fb_run_scan(fb_ctx* c) {
 // sequences and one discard count per gap come home.
 int fb_run_finalize(fb_ctx* c) {
     if (!c) return FB_EINVAL;
+    if (c && c->piped) return c->fail(FB_ESTATE, "the gaps of fb_fill_gap_files can only be read or run again (fb_run_device); fb_clear_gaps starts over");
     if (!c->scanned) return c->fail(FB_ESTATE, "fb_run_finalize before fb_run_scan");
     FB_CUDA(c, cudaSetDevice(c->device));
     fb_stats& st = c->stats;
@@ -2129,7 +2172,8 @@ int fb_ipc_close(fb_ctx* c, void* dev_ptr) {
 
 // fillGap for every gap of this context in ONE enqueue: record tables, the EM scan of every size bin, the selection among
 // the estimates, finalize, and the copies home; the host waits once and then hands the results to the gaps.
-static int run_fused(fb_ctx* c) {
+// run_fused_begin enqueues and returns; run_fused_end waits and collects (fb_fill_gap_files runs host work in between).
+static int run_fused_begin(fb_ctx* c) {
     FB_CUDA(c, cudaSetDevice(c->device));
     fb_stats& st = c->stats;
     Trace tr;
@@ -2149,7 +2193,6 @@ static int run_fused(fb_ctx* c) {
     st.aux_launches = 1 + (c->pre_chains ? 1 : 0) + (fin ? 1 : 0);
     st.em_launches = (int)nb * ((c->two_pass && fin) ? 2 : 1);
     st.finalize_launches = fin ? 1 : 0;
-    const long d2h = (long)(nu * sizeof(double)) + (fin ? (long)(c->fin_fill_total + 24 * c->gapout_n) : 0);
     // The whole pass as a stream of operations.  `capturing`: the timing events become event-record nodes of a CUDA graph.
     auto enqueue = [&](bool capturing) -> int {
         auto rec = [&](cudaEvent_t ev) {
@@ -2281,6 +2324,16 @@ static int run_fused(fb_ctx* c) {
         if (rc != FB_OK) return rc;
     }
     tr.lap("run: enqueued");
+    return FB_OK;
+}
+
+static int run_fused_end(fb_ctx* c) {
+    FB_CUDA(c, cudaSetDevice(c->device));
+    fb_stats& st = c->stats;
+    Trace tr;
+    const size_t nu = c->h_units.size();
+    const bool fin = !c->fin_gaplist.empty();
+    const long d2h = (long)(nu * sizeof(double)) + (fin ? (long)(c->fin_fill_total + 24 * c->gapout_n) : 0);
     FB_CUDA(c, cudaStreamSynchronize(c->stream));     // (not the last event: a graph's record node has not marked it pending yet)
     tr.lap("run: device");
     // ---- results to the gaps (figbird.cpp:2382, 2050-2063, 2503)
@@ -2324,9 +2377,52 @@ static int run_fused(fb_ctx* c) {
     return FB_OK;
 }
 
+static int run_fused(fb_ctx* c) {
+    const int rc = run_fused_begin(c);
+    return rc != FB_OK ? rc : run_fused_end(c);
+}
+
+// The numbers of the last run of both batches as one: kernel times and launches add up, step_ms spans both contexts.
+static void merge_run_stats(fb_ctx* c) {
+    fb_stats& a = c->stats;
+    const fb_stats& b = c->child->stats;
+    a.finalize_likelihoods += b.finalize_likelihoods;
+    a.em_kernel_ms += b.em_kernel_ms; a.finalize_kernel_ms += b.finalize_kernel_ms;
+    a.em_launches += b.em_launches; a.finalize_launches += b.finalize_launches; a.aux_launches += b.aux_launches;
+    a.d2h_bytes += b.d2h_bytes;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->child->evs, c->eve) == cudaSuccess) a.step_ms = ms;
+    else cudaGetLastError();
+}
+
+// Both batches of a fb_fill_gap_files gap set, on the device at the same time (two contexts, two sets of streams).
+static int run_both(fb_ctx* c) {
+    fb_ctx* k = c->child;
+    const bool two_call = getenv("FB_TWO_CALL") && atoi(getenv("FB_TWO_CALL"));
+    const bool kf = k->fused_ok && !two_call, cf = c->fused_ok && !two_call;
+    auto whole = [&](fb_ctx* x) {
+        int rc = fb_run_scan(x);
+        return rc != FB_OK ? rc : fb_run_finalize(x);
+    };
+    int rc = kf ? run_fused_begin(k) : whole(k);
+    if (rc != FB_OK) return c->fail(rc, "first batch: %s", k->err.c_str());
+    rc = cf ? run_fused_begin(c) : whole(c);
+    if (rc == FB_OK && cf) rc = run_fused_end(c);
+    const int rk = kf ? run_fused_end(k) : FB_OK;
+    if (rk != FB_OK) return c->fail(rk, "first batch: %s", k->err.c_str());
+    if (rc == FB_OK) merge_run_stats(c);
+    return rc;
+}
+
 int fb_run_device(fb_ctx* c) {
     if (!c) return FB_EINVAL;
     if (!c->uploaded) return c->fail(FB_ESTATE, "fb_run_device before fb_upload");
+    if (c->piped) {
+        c->piped = false;                    // the two-call route goes through entry points that refuse a piped context
+        const int rc = run_both(c);
+        c->piped = true;
+        return rc;
+    }
     if (c->fused_ok && !(getenv("FB_TWO_CALL") && atoi(getenv("FB_TWO_CALL")))) return run_fused(c);
     int rc = fb_run_scan(c);
     if (rc != FB_OK) return rc;
@@ -2361,7 +2457,83 @@ int fb_run(fb_ctx* c) {
     return fb_run_device(c);
 }
 
+// fillGap for a whole gap set handed over as gap files, in one call.  The set goes to the device in two batches: the
+// first (an eighth of the gaps) is parsed, packed, planned, uploaded and enqueued on a second context; while its EM scan
+// runs, the host does the same for the rest, so all but the first batch's host work is hidden behind device work.
+// Gaps are independent (figbird.cpp:2819-2855 fills them one after the other), so the results are those of
+// fb_add_gap_files + fb_run, bit for bit.  handles[i] indexes the getters (fb_result, fb_estimate_liks, fb_best_string,
+// fb_dump_profile): the second batch's gaps first, then the first batch's.
+int fb_fill_gap_files(fb_ctx* c, const fb_gap_desc* descs, int n, int* handles, int threads) {
+    if (!c || n < 0 || (n > 0 && (!descs || !handles))) return FB_EINVAL;
+    if (c->piped || !c->gaps.empty()) return c->fail(FB_ESTATE, "fb_fill_gap_files needs a context without gaps (fb_clear_gaps)");
+    const char* np = getenv("FB_NO_PIPE");
+    const char* mp = getenv("FB_PIPE_MIN");
+    const int pipe_min = mp ? std::max(2, atoi(mp)) : 128;
+    if (n < pipe_min || (np && atoi(np)) || c->part_world > 1 || c->unit_mode || c->rec_mode) {
+        const int ra = fb_add_gap_files(c, descs, n, handles, threads);
+        if (ra != FB_OK && ra != FB_EDOMAIN) return ra;
+        const int rr = fb_run(c);                 // refused gaps (FB_EDOMAIN) stay out, the others are filled
+        return rr != FB_OK ? rr : ra;
+    }
+    if (!c->child) {
+        fb_model m = c->m_model;
+        m.error_pos = c->m_error_pos.data();
+        m.in_pos = c->m_in_pos.data();
+        m.del_pos = c->m_del_pos.data();
+        m.ild = c->m_ild.data();
+        const int rc = fb_create(&m, c->device, &c->child);
+        if (rc != FB_OK) return c->fail(rc, "second context for the first batch could not be created");
+    }
+    fb_ctx* k = c->child;
+    fb_clear_gaps(k);
+    const int nA = std::max(pipe_min / 4, n / 8);
+    // ---- first batch: on the device before the second is even read
+    int refused = 0;
+    std::string refused_msg;
+    int rc = fb_add_gap_files(k, descs, nA, handles, threads);
+    if (rc == FB_EDOMAIN) { refused++; refused_msg = k->err; rc = FB_OK; }
+    if (rc == FB_OK) rc = fb_upload(k);
+    const bool two_call = getenv("FB_TWO_CALL") && atoi(getenv("FB_TWO_CALL"));
+    const bool kf = k->fused_ok && !two_call;
+    if (rc == FB_OK) rc = kf ? run_fused_begin(k) : fb_run_device(k);
+    if (rc != FB_OK) return c->fail(rc, "first batch: %s", k->err.c_str());
+    // ---- second batch, while the first runs
+    rc = fb_add_gap_files(c, descs + nA, n - nA, handles + nA, threads);
+    if (rc == FB_EDOMAIN) { refused++; refused_msg = c->err; rc = FB_OK; }
+    if (rc == FB_OK) rc = fb_upload(c);
+    if (rc == FB_OK) rc = fb_run_device(c);
+    const int rk = kf ? run_fused_end(k) : FB_OK;       // the first batch is waited for in any case
+    if (rc != FB_OK) return rc;
+    if (rk != FB_OK) return c->fail(rk, "first batch: %s", k->err.c_str());
+    const int nB = (int)c->gaps.size();
+    for (int i = 0; i < nA; i++)
+        if (handles[i] >= 0) handles[i] += nB;
+    c->piped = true;
+    {
+        // one set of numbers for the whole fill
+        fb_stats& a = c->stats;
+        const fb_stats& b = k->stats;
+        a.n_gaps += b.n_gaps; a.n_units += b.n_units; a.n_records += b.n_records;
+        a.likelihoods += b.likelihoods; a.base_terms += b.base_terms;
+        a.algorithmic_bytes += b.algorithmic_bytes;
+        a.h2d_bytes += b.h2d_bytes;
+        merge_run_stats(c);
+    }
+    if (refused) return c->fail(FB_EDOMAIN, "some gaps were refused (see handles); last: %s", refused_msg.c_str());
+    return FB_OK;
+}
+
+// Getters of a context filled by fb_fill_gap_files: indices past its own gaps belong to the first batch's context.
+static fb_ctx* route(fb_ctx* c, int& gap) {
+    if (c && c->piped && c->child && gap >= (int)c->gaps.size()) {
+        gap -= (int)c->gaps.size();
+        return c->child;
+    }
+    return c;
+}
+
 int fb_result(fb_ctx* c, int gap, fb_gap_result* out, char* filled, int cap) {
+    c = route(c, gap);
     if (!c || gap < 0 || gap >= (int)c->gaps.size()) return FB_EINVAL;
     const HostGap& g = c->gaps[gap];
     if (!c->ran || !g.done) return c->fail(FB_ESTATE, "gap %d has no result in this context", gap);
@@ -2384,6 +2556,7 @@ int fb_result(fb_ctx* c, int gap, fb_gap_result* out, char* filled, int cap) {
 }
 
 int fb_estimate_liks(fb_ctx* c, int gap, double* liks, int cap) {
+    c = route(c, gap);
     if (!c || gap < 0 || gap >= (int)c->gaps.size() || !liks) return FB_EINVAL;
     const HostGap& g = c->gaps[gap];
     if (!c->ran || !g.done) return c->fail(FB_ESTATE, "gap %d has no result in this context", gap);
@@ -2393,6 +2566,7 @@ int fb_estimate_liks(fb_ctx* c, int gap, double* liks, int cap) {
 }
 
 int fb_best_string(fb_ctx* c, int gap, char* buf, int cap) {
+    c = route(c, gap);
     if (!c || gap < 0 || gap >= (int)c->gaps.size() || !buf) return FB_EINVAL;
     const HostGap& g = c->gaps[gap];
     if (!c->ran || !g.done) return c->fail(FB_ESTATE, "gap %d has no result in this context", gap);
@@ -2414,6 +2588,7 @@ int fb_best_string(fb_ctx* c, int gap, char* buf, int cap) {
 }
 
 int fb_dump_profile(fb_ctx* c, int gap, int estimate, double* probs, double* counts) {
+    c = route(c, gap);
     if (!c || gap < 0 || gap >= (int)c->gaps.size() || !probs || !counts) return FB_EINVAL;
     if (!c->uploaded) return c->fail(FB_ESTATE, "fb_dump_profile before fb_upload");
     FB_CUDA(c, cudaSetDevice(c->device));

@@ -58,6 +58,13 @@ struct FbEmParams {
     const uint8_t* st_jl;      // [n_records][FB_MAX_READ + 16]
     const uint8_t* st_cum;     // [n_records][32]
     const double* pre;         // left-flank prefix table (fb_prefix_kernel); nullptr: every chain starts at ILD[t]
+    // First-iteration terms.  initialize() gives every gap row the same counts (N = 1, figbird.cpp:1665-1673), so in the
+    // first iteration the term of a base against ANY gap row depends only on its class c and read position k:
+    // t0_tab[c][k] = P*(1-e[k]) + e[k]*Q of that row (its log in f=1 mode), computed once on the device by the E-step's own
+    // operations (fb_t0_kernel).  Where all placements of a task are on gap rows the E-step multiplies by t0_tab[c][k]
+    // — a uniform operand from the constant bank — instead of loading {P,Q} per lane.  use_t0 = 0 switches it off.
+    double t0_tab[5][FB_MAX_READ];
+    int use_t0;
     // work list
     const FbUnit* units;
     int n_units;
@@ -122,6 +129,8 @@ struct FbPrefixParams {
     const uint32_t* st_cls4;   // built by fb_stage_kernel earlier in the stream
     double* pre;
 };
+// t0[c * FB_MAX_READ + k], see FbEmParams::t0_tab; eo/T/out are device pointers
+cudaError_t fb_launch_t0(const double2* eo, const double* T, double* out, bool f1, cudaStream_t s);
 cudaError_t fb_launch_prefix(const FbPrefixParams& p, int slices, bool f1, cudaStream_t s);   // CTAs per gap = slices
 
 // Closing step of a record-sharded scan: rank-ordered sum of the partial counts -> computeSequence(0); per-record

@@ -280,6 +280,25 @@ __device__ __forceinline__ void score_pair(const unsigned char* pa, const uint32
     }
 }
 
+// First iteration, bases [jb, je) (both multiples of 4) of a task whose placements are all on gap rows there: every
+// lane multiplies by the same term (FbEmParams::t0_tab), no table loads.
+template <bool TWO, bool F1>
+__device__ __forceinline__ void score_uniform(const uint32_t* __restrict__ cls4, const FbEmParams& p, int L2, bool rev, int jb, int je,
+                                              double& sa, double& sb) {
+    const int ks = rev ? -1 : 1;
+    int k = rev ? L2 - 1 - jb : jb;
+    for (int j0 = jb; j0 < je; j0 += 4) {
+        const uint32_t cw = cls4[j0 >> 3] >> ((j0 & 4) * 4);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const double t = p.t0_tab[(cw >> (4 * q)) & 7u][k + q * ks];
+            sa = F1 ? dadd(sa, t) : dmul(sa, t);
+            if (TWO) sb = F1 ? dadd(sb, t) : dmul(sb, t);
+        }
+        k += 4 * ks;
+    }
+}
+
 // Per-record running maximum as an unsigned key (atomicMax in shared memory).  f=0: maxProb starts at 0 and only scores
 // above 0 win (figbird.cpp:1815, 1866), so the bit pattern of a positive double orders correctly and 0 means "none".
 // f=1: maxProb starts at -DBL_MAX and log scores are negative (figbird.cpp:1814): the usual order-preserving flip of
@@ -351,6 +370,31 @@ __global__ void __launch_bounds__(256) fb_stage_kernel(const FbStageParams p) {
             }
         }
         start = (start + n3 + n2 + n1 + n0 + 3) & ~3;     // next class starts on a 32-bit boundary
+    }
+}
+
+// FbEmParams::t0_tab — the first iteration's term of a base of class c at read position k against a gap row as
+// initialize() leaves it (counts N = 1): the E-step's own operations on that row's {P,Q}, once per (c, k).
+template <bool F1>
+__global__ void fb_t0_kernel(const double2* __restrict__ eo, const double* __restrict__ T, double* __restrict__ out) {
+    __shared__ double sT[25];
+    __shared__ double2 row[5];
+    const int tid = threadIdx.x;
+    if (tid < 25) sT[tid] = T[tid];
+    __syncthreads();
+    if (tid == 0) {
+        double c[5] = {0.0, 0.0, 0.0, 0.0, 1.0};
+        double P[4], Q[5];
+        profile_row(c, sT, P, Q);
+#pragma unroll
+        for (int k = 0; k < 4; k++) row[k] = make_double2(P[k], Q[k]);
+        row[4] = make_double2(0.0, Q[4]);
+    }
+    __syncthreads();
+    for (int i = tid; i < 5 * FB_MAX_READ; i += blockDim.x) {
+        const double2 v = row[i / FB_MAX_READ], e = eo[i % FB_MAX_READ];
+        const double term = dadd(dmul(v.x, e.x), dmul(e.y, v.y));
+        out[i] = F1 ? fbm_log(term) : term;
     }
 }
 
@@ -550,6 +594,7 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
             // that wins the gap (figbird.cpp:2479-2490) — the first pass leaves the last M-step out, the winners are run
             // again in full once the likelihoods have picked them.
             const bool skip_m = last && p.skip_last_m;
+            const bool uni0 = it == 0 && p.use_t0 && !p.n_parts;   // every gap row still holds initialize()'s counts
             // rounds of the pipeline: stage chunk r+1 | E-step chunk r | M-step chunk r-1   (r = -1 stages chunk 0)
             for (int r = ((it == 0 || !keep_staged) ? -1 : 0); r <= nchunks; r++, round++) {
                 const int cl = r + 1, ce = r, cm = r - 1;
@@ -691,20 +736,43 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
                                 }
                             }
                         }
+                        // First iteration: bases [g0, g1) meet gap rows in every lane of the task — the same initial row everywhere.
+                        int g0 = L2, g1 = L2;
+                        if (uni0) {
+                            const int u0 = lo + 64 * blk;
+                            const int a = max(skA, (D - u0 + 3) & ~3), b = min(L2, D + gp - (two ? 63 : 31) - u0) & ~3;
+                            if (b > a) { g0 = a; g1 = b; }
+                        }
                         if (!two || skB < skA) {
                             // one chain alone: the whole of a one-chain task, or chain B's terms before chain A's first
                             const bool headB = two;
                             double s1 = headB ? sb : sa, s2 = 0.0;
                             const unsigned char* p1 = headB ? pa + 32 * 16 : pa;
-                            const int jb = headB ? skB : skA, je = headB ? skA : L2;
-                            if (rev) score_pair<true, false, F1>(p1, cls4, cstride, p, L2, jb, je, s1, s2);
-                            else score_pair<false, false, F1>(p1, cls4, cstride, p, L2, jb, je, s1, s2);
+                            int jb = headB ? skB : skA, je = headB ? skA : g0;
+                            const int jend = headB ? skA : L2;
+#pragma unroll 1
+                            for (;;) {
+                                if (rev) score_pair<true, false, F1>(p1, cls4, cstride, p, L2, jb, je, s1, s2);
+                                else score_pair<false, false, F1>(p1, cls4, cstride, p, L2, jb, je, s1, s2);
+                                if (je == jend) break;
+                                score_uniform<false, F1>(cls4, p, L2, rev, g0, g1, s1, s2);
+                                jb = g1;
+                                je = L2;
+                            }
                             if (headB) sb = s1;
                             else sa = s1;
                         }
                         if (two) {
-                            if (rev) score_pair<true, true, F1>(pa, cls4, cstride, p, L2, skA, L2, sa, sb);
-                            else score_pair<false, true, F1>(pa, cls4, cstride, p, L2, skA, L2, sa, sb);
+                            int jb = skA, je = g0;
+#pragma unroll 1
+                            for (;;) {
+                                if (rev) score_pair<true, true, F1>(pa, cls4, cstride, p, L2, jb, je, sa, sb);
+                                else score_pair<false, true, F1>(pa, cls4, cstride, p, L2, jb, je, sa, sb);
+                                if (je == L2) break;
+                                score_uniform<true, F1>(cls4, p, L2, rev, g0, g1, sa, sb);
+                                jb = g1;
+                                je = L2;
+                            }
                         }
                         // what the M-step adds to the counts: the score itself, pow(10, score) in f=1 (figbird.cpp:1878, 1879)
                         double wa = sa, wb = sb;
@@ -1146,6 +1214,12 @@ cudaError_t fb_launch_finalize(const FbFinParams& p, int n, int slices, size_t s
 cudaError_t fb_launch_shard_finish(const FbShardFinParams& p, cudaStream_t s) {
     if (p.n_units < 1) return cudaSuccess;
     fb_shard_finish_kernel<<<p.n_units < 4096 ? p.n_units : 4096, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t fb_launch_t0(const double2* eo, const double* T, double* out, bool f1, cudaStream_t s) {
+    if (f1) fb_t0_kernel<true><<<1, 128, 0, s>>>(eo, T, out);
+    else fb_t0_kernel<false><<<1, 128, 0, s>>>(eo, T, out);
     return cudaGetLastError();
 }
 

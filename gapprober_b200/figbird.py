@@ -83,7 +83,7 @@ class FbStats(C.Structure):
 # Every symbol include/figbird_cuda.h declares; tests check the library exports all of them.
 ABI_SYMBOLS = [
     "fb_create", "fb_warmup", "fb_destroy", "fb_add_gap", "fb_add_gap_file", "fb_add_gap_files", "fb_set_partition", "fb_set_partition_units", "fb_run_scan", "fb_run_finalize", "fb_scan_liks", "fb_merge_liks", "fb_owns_gap", "fb_partition_plan", "fb_gap_cost", "fb_run", "fb_upload",
-    "fb_run_device", "fb_result", "fb_estimate_liks", "fb_best_string", "fb_dump_profile", "fb_get_stats",
+    "fb_run_device", "fb_fill_gap_files", "fb_result", "fb_estimate_liks", "fb_best_string", "fb_dump_profile", "fb_get_stats",
     "fb_clear_gaps", "fb_gap_range", "fb_last_error", "fb_status_str", "fb_abi_version",
     "fb_set_partition_records", "fb_shard_sizes", "fb_shard_buffers", "fb_shard_scan_iter", "fb_shard_scan_finish", "fb_shard_scan_all",
     "fb_shard_counts", "fb_shard_reset", "fb_measure_smem_peak", "fb_devmath_eval", "fb_ipc_export", "fb_ipc_open", "fb_ipc_close",
@@ -109,6 +109,7 @@ def load_library():
     L.fb_add_gap.argtypes = [vp, C.c_int, C.c_long, C.c_int, C.c_char_p, C.c_long, C.POINTER(_FbRecord), C.c_int]
     L.fb_add_gap_file.argtypes = [vp, C.c_int, C.c_long, C.c_int, C.c_char_p, C.c_long, C.c_char_p]
     L.fb_add_gap_files.argtypes = [vp, C.POINTER(_FbGapDesc), C.c_int, C.POINTER(C.c_int), C.c_int]
+    L.fb_fill_gap_files.argtypes = [vp, C.POINTER(_FbGapDesc), C.c_int, C.POINTER(C.c_int), C.c_int]
     L.fb_set_partition.argtypes = [vp, C.c_int, C.c_int]
     L.fb_set_partition_units.argtypes = [vp, C.c_int, C.c_int]
     L.fb_run_scan.argtypes = [vp]
@@ -409,15 +410,24 @@ class FigbirdContext:
         """Register many gaps at once: gaps = [(contigNo, gapStart, originalGap, gapFilePath, contig bytes)] or a GapBatch
         prepared from such a list.  The library parses and packs the files on several host threads
         (fb_add_gap_files).  Returns the GapFiller objects."""
+        return self._register(gaps, threads, self._L.fb_add_gap_files)
+
+    def fill_gap_files(self, gaps, threads=0):
+        """The whole gap loop in one call (fb_fill_gap_files): register + fill, with the host's parsing, packing and
+        planning of most of the gap set overlapped with the device's work on the first batch.  Needs a context without
+        gaps (clearGaps).  Same arguments and return value as add_gap_files; the results are ready on return."""
+        return self._register(gaps, threads, self._L.fb_fill_gap_files)
+
+    def _register(self, gaps, threads, call):
         batch = gaps if isinstance(gaps, GapBatch) else GapBatch(gaps)
         n = batch.n
-        rc = self._L.fb_add_gap_files(self._h, batch.descs, n, batch.handles, int(threads))
+        rc = call(self._h, batch.descs, n, batch.handles, int(threads))
         handles = np.frombuffer(batch.handles, dtype=np.int32, count=n)
         cached = batch._fillers
-        if (rc == FB_OK and cached is not None and cached[0] is self and len(self._gaps) == (int(handles[0]) if n else 0)
+        if (rc == FB_OK and cached is not None and cached[0] is self and len(self._gaps) == (int(handles.min()) if n else 0)
                 and np.array_equal(handles, cached[1])):
             out = cached[2]                      # same context, same handles as last time: the objects are still right
-            self._gaps.extend(out)
+            self._gaps.extend(cached[3])         # ... in handle order
             return out
         out = []
         for (c, s, l), h in zip(batch.meta, handles.tolist()):
@@ -430,8 +440,9 @@ class FigbirdContext:
             self._gaps[h] = g
             out.append(g)
         self._check(rc)
-        if n and len(out) == n and np.array_equal(handles, np.arange(handles[0], handles[0] + n)):
-            batch._fillers = (self, handles.copy(), out)
+        if n and len(out) == n and len(self._gaps) == int(handles.min()) + n:   # every handle new and dense: cacheable
+            base = int(handles.min())
+            batch._fillers = (self, handles.copy(), out, self._gaps[base:base + n])
         return out
 
     def add_workdir(self, wd, scaffolds="scaffolds.fa", threads=0):

@@ -199,6 +199,15 @@ double fb_gap_cost(fb_ctx* ctx, int gap);
 int fb_run(fb_ctx* ctx);
 int fb_upload(fb_ctx* ctx);      /* pack + host->device copy of every registered gap */
 int fb_run_device(fb_ctx* ctx);  /* everything after the upload; may be called repeatedly (benchmark steps) */
+/* The gap loop of figbird's main() (figbird.cpp:2819-2855) in one call, gap files in, results out: equivalent to
+ * fb_add_gap_files + fb_run on a context without gaps, but the gap set goes to the device in two batches — the first
+ * eighth is parsed, packed, uploaded and started on a second context of the same model, and the host reads, parses, packs
+ * and plans the rest while that batch's EM scan runs.  Gaps are independent, so every result is the same, bit for bit.
+ * handles[i] indexes the getters below (the second batch's gaps come first); a refused gap (FB_EDOMAIN) gets a negative
+ * handle, the others are still filled and the call returns FB_EDOMAIN.  Afterwards the context can be read, run again
+ * (fb_run_device) or cleared (fb_clear_gaps); adding gaps or changing the partition needs fb_clear_gaps first.
+ * Sets of fewer than 128 gaps (FB_PIPE_MIN) and partitioned contexts take the plain route. */
+int fb_fill_gap_files(fb_ctx* ctx, const fb_gap_desc* descs, int n, int* handles, int threads);
 
 /* GapFiller::getConcensus (figbird.cpp:2050-2063) + the numbers fillGap/finalize print. */
 int fb_result(fb_ctx* ctx, int gap, fb_gap_result* out, char* filled, int filled_cap);

@@ -247,7 +247,8 @@ def test_kernel_variants_agree_bit_for_bit(built):
                     {"FB_HOST_LOG": "1"}, {"FB_HOST_LOG": "1", "FB_CLUSTER": "4"},
                     {"FB_TWO_CALL": "1"},                      # scan and finalize as two calls with the selection on the host
                     {"FB_ONE_CTA": "1", "FB_CLUSTER": "2"}, {"FB_ONE_CTA": "1", "FB_CLUSTER": "1"},
-                    {"FB_NO_PREFIX": "1"}, {"FB_NO_PREFIX": "1", "FB_CLUSTER": "2"}):   # every chain from ILD[t], no left-flank prefix table
+                    {"FB_NO_PREFIX": "1"}, {"FB_NO_PREFIX": "1", "FB_CLUSTER": "2"},    # every chain from ILD[t], no left-flank prefix table
+                    {"FB_NO_T0": "1"}, {"FB_NO_T0": "1", "FB_NO_PREFIX": "1"}):         # first iteration from the tables like the others
             assert _fill_with_env(case, gaps, env) == ref, (name, env)
 
 
@@ -259,5 +260,5 @@ def test_log_mode_variants_agree_bit_for_bit(built):
     for g, r in zip(gaps, ref):
         assert r[0] == g["filled"] and r[1] == g["best_est"] and r[2] == np.asarray(g["liks"]).tobytes()
     for env in ({"FB_CLUSTER": "2"}, {"FB_CLUSTER": "4", "FB_CHUNK": "8"}, {"FB_HOST_LOG": "1"}, {"FB_NO_COMPACT": "1", "FB_CLUSTER": "2"},
-                {"FB_TWO_CALL": "1"}, {"FB_NO_PREFIX": "1"}):
+                {"FB_TWO_CALL": "1"}, {"FB_NO_PREFIX": "1"}, {"FB_NO_T0": "1"}):
         assert _fill_with_env(case, gaps, env) == ref, env
