@@ -435,6 +435,11 @@ def run_ours(a):
         sampler.start()
     barrier()
     em_ms, step_ms = 0.0, 0.0
+    # FB_PROFILE_STEP=1: the timed steps of the device-resident arm are the profiler's capture window
+    # (ncu --profile-from-start off ...); numbers printed by a run under a profiler are not bench values
+    prof = os.environ.get("FB_PROFILE_STEP") == "1"
+    if prof:
+        torch.cuda.cudart().cudaProfilerStart()
     t0 = time.perf_counter()
     for _ in range(a.steps):
         flush.fill_(1)                      # evict L2 between steps
@@ -445,6 +450,8 @@ def run_ours(a):
         em_ms += st["em_kernel_ms"]
         # CUDA-event time of the step; with the likelihood exchange in the middle the events do not span it, use the host clock
         step_ms += st["step_ms"] if not (by_estimate or by_record) else 1e3 * (time.perf_counter() - t_step)
+    if prof:
+        torch.cuda.cudart().cudaProfilerStop()
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None

@@ -1,13 +1,16 @@
-set -x
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_gpu_pipe.py tests/test_gpu_golden.py tests/test_gpu_parity.py tests/test_gpu_edge.py tests/test_gpu_fuzz.py tests/test_gpu_dropin.py -m gpu -x -q > gpurun_out/r2i_pytest.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/r2i_pytest.log
-for cfg in cfg2_rhodobacter cfg4_chr14; do
-for k in "" "FB_NO_PIPE=1" "FB_NO_T0=1"; do
-  sc=strong; [ $cfg = cfg2_rhodobacter ] && sc=weak
-  env $k python bench.py --config $cfg --scaling $sc --no-cpu --no-check --steps 5 > gpurun_out/r2i_${cfg}_$k.json 2> gpurun_out/r2i_${cfg}_$k.err; python - <<PY
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2j_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r2j_pytest.log
+for k in "FB_CHUNK=12" "FB_CHUNK=24"; do
+  env $k python bench.py --config cfg2_rhodobacter --scaling weak --no-cpu --no-check --steps 5 > gpurun_out/r2j_cfg2_$k.json 2> gpurun_out/r2j_cfg2_$k.err; python - <<PY
 import json
-d=json.loads(open("gpurun_out/r2i_${cfg}_$k.json").read().strip().splitlines()[-1])
-print("$cfg [$k] step_ms %.4f em_ms %.4f value %.4e e2e %.4e (%.3f) sha %s" % (d["ms_per_step"], d["roofline"]["kernel_ms_per_step"], d["value"], d["e2e"]["value"], d["e2e"]["value"]/d["value"], d["result"]["filled_sha256"][:12]))
+d=json.loads(open("gpurun_out/r2j_cfg2_$k.json").read().strip().splitlines()[-1])
+print("cfg2 [$k] step_ms %.4f em_ms %.4f value %.4e e2e %.4e (%.3f)" % (d["ms_per_step"], d["roofline"]["kernel_ms_per_step"], d["value"], d["e2e"]["value"], d["e2e"]["value"]/d["value"]))
 PY
 done
-done
+export FB_PROFILE_STEP=1
+CMD="python bench.py --steps 1 --warmup 3 --no-cpu --no-check"
+$CMD > gpurun_out/r2j_plain.log 2>&1 &&
+ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2j_launches.csv $CMD > gpurun_out/r2j_ncu1.log 2>&1
+echo "launch list rc=$?"
+ncu --profile-from-start off --set full --clock-control none --import-source on -o gpurun_out/r2j_full $CMD > gpurun_out/r2j_ncu2.log 2>&1
+echo "full rc=$?"; ls -la gpurun_out/r2j_full.ncu-rep

@@ -21,7 +21,11 @@ KEEP = [
 
 def to_bytes(v, unit):
     mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
-    return float(v.replace(",", "")) * mult
+    try:
+        x = float(v.replace(",", ""))
+    except ValueError:
+        return 0.0
+    return 0.0 if x != x else x * mult          # a launch with no units to run reports n/a
 
 
 def main(raw, out_csv, out_json, workload="cfg4_chr14"):
@@ -45,7 +49,7 @@ def main(raw, out_csv, out_json, workload="cfg4_chr14"):
             n += 1
     import os
     doc = json.load(open(out_json)) if os.path.exists(out_json) else {}
-    doc[workload] = {"source": f"{out_csv} (ncu --set full over the fb_* launches of one timed step of bench.py --config {workload} --steps 1 --warmup 3)",
+    doc[workload] = {"source": f"{out_csv} (ncu --set full --profile-from-start off over the launches of the one timed step of FB_PROFILE_STEP=1 bench.py --config {workload} --steps 1 --warmup 3)",
                      "kernel": "fb_em_kernel", "launches_per_step": n, "dram_bytes_read_per_step": rd, "dram_bytes_write_per_step": wr,
                      "dram_bytes_per_launch": (rd + wr) / max(n, 1)}
     json.dump(doc, open(out_json, "w"), indent=1)
