@@ -1603,6 +1603,7 @@ void fill_em_params(fb_ctx* c, FbEmParams& p) {
     p.pre = c->pre_chains ? c->d_pre.p : nullptr;
     memcpy(p.t0_tab, c->h_t0.data(), sizeof p.t0_tab);
     p.use_t0 = getenv("FB_NO_T0") ? 0 : 1;
+    p.e_rec_major = getenv("FB_E_REC_MAJOR") ? 1 : 0;
     p.unit_maxprob = c->d_maxprob.p;
     p.unit_cons = c->d_cons.p;
     p.dump_unit = -1;
@@ -2205,8 +2206,11 @@ static int run_fused_begin(fb_ctx* c) {
         FB_CUDA(c, launch_stage(c, c->stream));
         FB_CUDA(c, rec(c->ev0));
         // pass: 0 the scan of every unit (without the last M-step when a second pass follows), 1 the winners again in full
+        // FB_SERIAL_BINS=1 (profiling aid): every bin on the main stream, one after the other — ncu collects its metrics
+        // for every launch that way (launches that overlap on side streams come back without counters)
+        const bool serial = nb == 1 || (getenv("FB_SERIAL_BINS") && atoi(getenv("FB_SERIAL_BINS")));
         auto scan_pass = [&](int pass) -> int {
-            if (nb > 1) FB_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));      // every bin's stream forks from here ...
+            if (!serial) FB_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));      // every bin's stream forks from here ...
             for (size_t bi = 0; bi < nb; bi++) {
                 FbEmParams p;
                 fill_bin_params(c, bi, p);
@@ -2218,7 +2222,7 @@ static int run_fused_begin(fb_ctx* c) {
                     p.work_counter = c->d_counters.p + nb + 1 + bi;
                     p.unit_lik = nullptr;                        // pass 1 has written them, by the units' places in the full list
                 }
-                if (nb == 1) {                                   // a single launch needs no stream of its own
+                if (serial) {                                    // a single launch needs no stream of its own
                     FB_CUDA(c, launch_bin(c, c->bins[bi], p, c->stream));
                 } else {
                     cudaStream_t bs = c->bin_streams[bi];
@@ -2227,7 +2231,7 @@ static int run_fused_begin(fb_ctx* c) {
                     FB_CUDA(c, cudaEventRecord(c->bin_done[bi], bs));
                 }
             }
-            if (nb > 1)                                                          // ... and joins the main stream here
+            if (!serial)                                                         // ... and joins the main stream here
                 for (size_t bi = 0; bi < nb; bi++) FB_CUDA(c, cudaStreamWaitEvent(c->stream, c->bin_done[bi], 0));
             return FB_OK;
         };

@@ -65,6 +65,7 @@ struct FbEmParams {
     // — a uniform operand from the constant bank — instead of loading {P,Q} per lane.  use_t0 = 0 switches it off.
     double t0_tab[5][FB_MAX_READ];
     int use_t0;
+    int e_rec_major;           // experiment knob (FB_E_REC_MAJOR=1): E tasks of a round in (record, block) order instead of (block, record)
     // work list
     const FbUnit* units;
     int n_units;

@@ -689,7 +689,9 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
                         // ---- E-step: warp per (record, 64 placements); lanes over placements.  Every slot of the record's score row is
                         // written: the score inside the window, 0.0 outside it (the M-step relies on those zeros).
                         const int te = task - tM;
-                        const int rq = te / nblk, blk = te - rq * nblk;
+                        // block-major: the first 64 placements of every record (full two-chain tasks) go out before the records'
+                        // last blocks (partly filled or empty), so the tasks a round ends on are the short ones
+                        const int blk = p.e_rec_major ? te % nblk : te / ne_q, rq = p.e_rec_major ? te / nblk : te - blk * ne_q;
                         const int rl = CLU ? rq * (int)csize + (int)crank : rq;
                         const FbRecMeta rm = SE.meta[rl];
                         const int fl2 = rm.flags, L2 = fl2 & 0xff, tb = rm.tb;
