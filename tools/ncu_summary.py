@@ -41,17 +41,33 @@ def main(raw, out_csv, out_json, workload="cfg4_chr14"):
             if len(r) == len(names):
                 w.writerow([r[c] for c in cols])
     ki, ri, wi = names.index("Kernel Name"), names.index("dram__bytes_read.sum"), names.index("dram__bytes_write.sum")
-    rd = wr = n = 0
+    ti = names.index("gpu__time_duration.sum")
+    rd = wr = 0.0
+    n = n_ok = 0
+    t_all = t_ok = 0.0
     for r in rows[hdr + 2:]:
         if len(r) == len(names) and "fb_em_kernel" in r[ki]:
-            rd += to_bytes(r[ri], units[ri])
-            wr += to_bytes(r[wi], units[wi])
             n += 1
+            t = float(r[ti].replace(",", ""))
+            t_all += t
+            try:
+                ok = float(r[ri].replace(",", "")) == float(r[ri].replace(",", ""))      # not NaN
+            except ValueError:
+                ok = False
+            if ok:                      # ncu cuts the replay of some long launches short: they come back with their time only
+                rd += to_bytes(r[ri], units[ri])
+                wr += to_bytes(r[wi], units[wi])
+                n_ok += 1
+                t_ok += t
+    scale = t_all / t_ok if t_ok else float("nan")   # the launches without counters are filled in by their share of device time
     import os
     doc = json.load(open(out_json)) if os.path.exists(out_json) else {}
     doc[workload] = {"source": f"{out_csv} (ncu --set full --profile-from-start off over the launches of the one timed step of FB_PROFILE_STEP=1 bench.py --config {workload} --steps 1 --warmup 3)",
-                     "kernel": "fb_em_kernel", "launches_per_step": n, "dram_bytes_read_per_step": rd, "dram_bytes_write_per_step": wr,
-                     "dram_bytes_per_launch": (rd + wr) / max(n, 1)}
+                     "kernel": "fb_em_kernel", "launches_per_step": n, "launches_with_counters": n_ok,
+                     "device_time_share_with_counters": t_ok / t_all if t_all else None,
+                     "dram_bytes_read_measured": rd, "dram_bytes_write_measured": wr,
+                     "dram_bytes_per_step_scaled": (rd + wr) * scale,
+                     "dram_bytes_per_launch": (rd + wr) * scale / max(n, 1)}
     json.dump(doc, open(out_json, "w"), indent=1)
 
 
