@@ -53,6 +53,7 @@ struct Api {
     decltype(&fb_destroy) destroy = nullptr;
     decltype(&fb_add_gap) add_gap = nullptr;
     decltype(&fb_run) run = nullptr;
+    decltype(&fb_fill_gap_files) fill_gap_files = nullptr;   // optional: absent in older builds of the library
     decltype(&fb_set_partition) set_partition = nullptr;
     decltype(&fb_owns_gap) owns_gap = nullptr;
     decltype(&fb_result) result = nullptr;
@@ -99,6 +100,7 @@ bool load_api(Api& a, std::string& why) {
     FB_SYM(status_str, "fb_status_str")
     FB_SYM(abi_version, "fb_abi_version")
 #undef FB_SYM
+    a.fill_gap_files = reinterpret_cast<decltype(a.fill_gap_files)>(dlsym(a.h, "fb_fill_gap_files"));
     if (a.abi_version() != FB_ABI_VERSION) { why = "ABI version mismatch"; return false; }
     return true;
 }
@@ -241,45 +243,85 @@ int main(int argc, char* argv[]) {
         return 1;
     }
     std::vector<int> handle(gaps.size(), -1);
-    for (size_t g = 0; g < gaps.size(); g++) {
-        char name[64];
-        snprintf(name, sizeof name, "Gaps/gaps_%zu.sam", g);
-        std::vector<fbhost::GapRecord> recs;
-        if (split) {
-            recs.swap(split->gaps[g].records);
-        } else if (!fbhost::read_gap_file(name, recs)) {
-            printf("Can't open %s\n", name);
-            return 1;
-        }
-        std::vector<fb_record> rv(recs.size());
-        for (size_t r = 0; r < recs.size(); r++) {
-            rv[r].pos1 = recs[r].pos1;
-            rv[r].len1 = recs[r].len1;
-            rv[r].strand1 = recs[r].strand1;
-            rv[r].seq2 = recs[r].seq2.c_str();
-            rv[r].len2 = (int)recs[r].seq2.size();
-        }
-        const fbhost::GapInfo& gi = gaps[g];
-        if (gi.contig_no < 0 || gi.contig_no >= (int)sc.seqs.size()) continue;
-        const std::string& ctg = sc.seqs[gi.contig_no];
-        for (int k = 0; k < ngpu; k++) {     // every context sees every gap; the partition decides who fills it
-            int h = api.add_gap(ctxs[k], gi.contig_no, gi.start, gi.length, ctg.c_str(), (long)ctg.size(), rv.data(), (int)rv.size());
-            if (h < 0 && k == 0) fprintf(stderr, "figbird: gap %zu left unfilled: %s\n", g, api.last_error(ctxs[k]));
-            handle[g] = h;
-        }
-    }
-    lap("gap files + pack");
     std::vector<int> run_rc(ngpu, FB_OK);
-    if (ngpu == 1) {
-        run_rc[0] = api.run(ctxs[0]);
+    // File route on one GPU: the whole gap loop in one library call — the gap files are read, parsed and packed by the
+    // library's host threads, and all but the first batch of that work overlaps the EM scan (fb_fill_gap_files).
+    const bool one_call = !split && ngpu == 1 && api.fill_gap_files && !getenv("FIGBIRD_NO_PIPE");
+    if (one_call) {
+        std::vector<std::string> names;
+        std::vector<size_t> which;
+        std::vector<fb_gap_desc> descs;
+        names.reserve(gaps.size());
+        for (size_t g = 0; g < gaps.size(); g++) {
+            char name[64];
+            snprintf(name, sizeof name, "Gaps/gaps_%zu.sam", g);
+            if (access(name, R_OK) != 0) {
+                printf("Can't open %s\n", name);
+                return 1;
+            }
+            const fbhost::GapInfo& gi = gaps[g];
+            if (gi.contig_no < 0 || gi.contig_no >= (int)sc.seqs.size()) continue;
+            const std::string& ctg = sc.seqs[gi.contig_no];
+            names.push_back(name);
+            which.push_back(g);
+            fb_gap_desc d;
+            d.contig_no = gi.contig_no;
+            d.gap_start = gi.start;
+            d.orig_gap = gi.length;
+            d.contig = ctg.c_str();
+            d.contig_len = (long)ctg.size();
+            d.gap_file = nullptr;
+            descs.push_back(d);
+        }
+        for (size_t k = 0; k < descs.size(); k++) descs[k].gap_file = names[k].c_str();
+        std::vector<int> h(descs.size(), -1);
+        const int rc1 = descs.empty() ? FB_OK : api.fill_gap_files(ctxs[0], descs.data(), (int)descs.size(), h.data(), 0);
+        run_rc[0] = rc1 == FB_EDOMAIN ? FB_OK : rc1;     // refused gaps stay N-runs (counted below), the others are filled
+        for (size_t k = 0; k < descs.size(); k++) {
+            handle[which[k]] = h[k];
+            if (h[k] < 0) fprintf(stderr, "figbird: gap %zu left unfilled: %s\n", which[k], api.status_str(h[k]));
+        }
+        lap("gap files + EM (one call)");
     } else {
-        std::vector<std::thread> pool;
-        for (int k = 0; k < ngpu; k++)
-            pool.emplace_back([&, k]() {
-                int rc = api.set_partition(ctxs[k], k, ngpu);
-                run_rc[k] = rc == FB_OK ? api.run(ctxs[k]) : rc;
-            });
-        for (auto& t : pool) t.join();
+        for (size_t g = 0; g < gaps.size(); g++) {
+            char name[64];
+            snprintf(name, sizeof name, "Gaps/gaps_%zu.sam", g);
+            std::vector<fbhost::GapRecord> recs;
+            if (split) {
+                recs.swap(split->gaps[g].records);
+            } else if (!fbhost::read_gap_file(name, recs)) {
+                printf("Can't open %s\n", name);
+                return 1;
+            }
+            std::vector<fb_record> rv(recs.size());
+            for (size_t r = 0; r < recs.size(); r++) {
+                rv[r].pos1 = recs[r].pos1;
+                rv[r].len1 = recs[r].len1;
+                rv[r].strand1 = recs[r].strand1;
+                rv[r].seq2 = recs[r].seq2.c_str();
+                rv[r].len2 = (int)recs[r].seq2.size();
+            }
+            const fbhost::GapInfo& gi = gaps[g];
+            if (gi.contig_no < 0 || gi.contig_no >= (int)sc.seqs.size()) continue;
+            const std::string& ctg = sc.seqs[gi.contig_no];
+            for (int k = 0; k < ngpu; k++) {     // every context sees every gap; the partition decides who fills it
+                int h = api.add_gap(ctxs[k], gi.contig_no, gi.start, gi.length, ctg.c_str(), (long)ctg.size(), rv.data(), (int)rv.size());
+                if (h < 0 && k == 0) fprintf(stderr, "figbird: gap %zu left unfilled: %s\n", g, api.last_error(ctxs[k]));
+                handle[g] = h;
+            }
+        }
+        lap("gap files + pack");
+        if (ngpu == 1) {
+            run_rc[0] = api.run(ctxs[0]);
+        } else {
+            std::vector<std::thread> pool;
+            for (int k = 0; k < ngpu; k++)
+                pool.emplace_back([&, k]() {
+                    int rc = api.set_partition(ctxs[k], k, ngpu);
+                    run_rc[k] = rc == FB_OK ? api.run(ctxs[k]) : rc;
+                });
+            for (auto& t : pool) t.join();
+        }
     }
     for (int k = 0; k < ngpu; k++)
         if (run_rc[k] != FB_OK) {

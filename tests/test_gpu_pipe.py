@@ -97,3 +97,45 @@ def test_small_batches_and_log_mode(built, tmp_path):
             os.environ.pop("FB_PIPE_MIN", None)
         else:
             os.environ["FB_PIPE_MIN"] = old
+
+
+def test_refused_gaps_in_either_batch(built, tmp_path):
+    """A gap closer than max_distance to a scaffold end is outside the reference's defined territory (FB_EDOMAIN): its
+    handle is negative, the call says so, and every other gap of both batches is filled as usual."""
+    import ctypes as C
+
+    from gapprober_b200 import FigbirdContext, GapBatch
+    wd, model, seqs, gaps, batch = _make(
+        tmp_path, ["--genome", "300000", "--scaffolds", "3", "--gaps", "24", "--gap-min", "40", "--gap-max", "300", "--cov", "30",
+                   "--err", "0.01", "--ins-mean", "180", "--ins-sd", "20", "--model-pairs", "50000"], 9)
+    with FigbirdContext(model) as fb:
+        plain = _all(fb.fill_gap_files(batch))
+    bad = {1, 17}                                             # one in the first batch (3 gaps), one in the second
+    cut = list(batch)
+    for i in bad:
+        c, s, l, path, contig = cut[i]
+        cut[i] = (c, s, l, path, contig[:s + l + 50])         # the scaffold now ends 50 bp after the gap
+    old = os.environ.get("FB_PIPE_MIN")
+    os.environ["FB_PIPE_MIN"] = "8"
+    try:
+        with FigbirdContext(model) as fb:
+            gb = GapBatch(cut)
+            rc = fb._L.fb_fill_gap_files(fb._h, gb.descs, gb.n, gb.handles, 0)
+            assert rc == -2                                   # FB_EDOMAIN: some gaps were refused, the rest ran
+            handles = list(gb.handles)[:gb.n]
+            assert [h < 0 for h in handles] == [i in bad for i in range(gb.n)]
+            assert sorted(h for h in handles if h >= 0) == list(range(gb.n - len(bad)))
+            from gapprober_b200.figbird import _FbGapResult
+            for i, h in enumerate(handles):
+                if h < 0:
+                    assert h == -2
+                    continue
+                r = _FbGapResult()
+                buf = C.create_string_buffer(4096)
+                assert fb._L.fb_result(fb._h, h, C.byref(r), buf, 4096) == 0
+                assert buf.value == plain[i][0]["filled"] and r.best_estimate == plain[i][0]["best_estimate"]
+    finally:
+        if old is None:
+            os.environ.pop("FB_PIPE_MIN", None)
+        else:
+            os.environ["FB_PIPE_MIN"] = old
