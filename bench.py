@@ -202,7 +202,7 @@ def workload_config(a, n_gaps):
     return {"workload": a.config, "seed": a.seed, "gaps": n_gaps, "scaling": a.scaling,
             "partition": ("rank r fills the gap set of seed+r (replicas of the workload, no data-path collective)" if a.scaling == "weak"
                           else part[a.partition]),
-            "l2": "flushed between steps (256 MiB write)"}
+            "l2": "flushed between steps (256 MiB write)", **({"f_mode": 1} if getattr(a, "f_mode", 0) else {})}
 
 
 def run_reference_arm(a):
@@ -320,6 +320,7 @@ def run_ours(a):
     barrier()
     wd = prepare_workload(a.config, my_seed)
     model = FigbirdModel.load(os.path.join(wd, "fb_model.bin"))
+    model.f_mode = a.f_mode                 # argv[2] of figbird: 0 is what GapProber.py passes and what the metric is quoted on
     _, seqs = read_scaffolds(os.path.join(wd, "scaffolds.fa"))
     gaps = read_gap_info(os.path.join(wd, "gapInfo.txt"))
     gap_files = [os.path.join(wd, "Gaps", f"gaps_{gi}.sam") for gi in range(len(gaps))]
@@ -542,7 +543,7 @@ def run_ours(a):
                      "note": "useful bytes = 16 B per base term of the E-step; lanes without a placement, the M-step's score reads and the "
                              "staging are issued on top of that (profiles/README.md has the wavefront accounting from ncu)"},
         }
-        if world == 1 and not a.no_cpu:
+        if world == 1 and not a.no_cpu and not a.f_mode:
             try:
                 rate, info = cpu_reference_rate(wd, a.cpu_liks, 1, "cb", a.seed) if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "figbird.out")) else (None, None)
             except Exception as e:   # the checker must not take the bench down
@@ -572,6 +573,8 @@ def main():
     ap.add_argument("--cpu-liks", type=float, default=2.0e7, help="likelihoods in the cpu_baseline sample (~15-25 s of one core)")
     ap.add_argument("--ref-liks", type=float, default=4.0e6, help="likelihoods per process per step in the reference arm")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--f-mode", type=int, default=0, choices=[0, 1],
+                    help="figbird's argv[2]: 1 = log-domain scores (secondary mode; own arm only, not the headline)")
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
     ap.add_argument("--no-check", action="store_true", help="skip the multi-GPU self-check that precedes the timed region")
     ap.add_argument("--partition", default="gap", choices=["gap", "estimate", "record"],

@@ -8,15 +8,20 @@
 //       placeReads                    figbird.cpp:1677-1965
 //         E-step  (1826-1872/1889-1938): score = ILD[t] * prod_j (P*(1-e) + e*Q)
 //                                                           -> warp per (record, 64 placements), lanes over
-//                                                              placements (two per lane), j sequential per lane
+//                                                              placements (two per lane), j sequential per lane;
+//                                                              chains that start in the left flank begin from
+//                                                              fb_prefix_kernel's tabulated running score, first-
+//                                                              iteration terms against gap rows are uniform operands
 //         M-step  (1874-1881/1940-1947): counts[row][base] += score
 //                                                           -> ordered gather: lane per gap row, warp per
 //                                                              (32 rows, base class); adds arrive in the
 //                                                              reference's (record, placement) order
+//         return value (1951-1955)                          -> unit_likelihood(): glibc's log restated, record order
 //       computeProbsGap/ErrorProbsGap figbird.cpp:1568-1608  -> fused row update, thread per row
 //     computeSequence(0)              figbird.cpp:1984-2047  -> consensus string per unit
-//   finalize(best)                    figbird.cpp:2087-2393  -> fb_finalize_kernel (scores + arg-max);
-//                                                              log/cut-off/counting stay on the host
+//   selection among the estimates     figbird.cpp:2479-2490  -> fb_select_kernel (thread per gap, last wins ties)
+//   finalize(best)                    figbird.cpp:2087-2393  -> fb_finalize_kernel, all of it (scores, arg-max, cut-off as a
+//                                                              threshold, integer counts, computeSequence(1))
 //
 // Bit-exactness (hard parts 1-2): the CPU evaluates P*(1-e)+e*Q as two rounded products
 // and one rounded sum and multiplies the running score in j order; every FP64 operation below is an
@@ -24,9 +29,10 @@
 // scores to a cell in exactly the order the CPU's scatter loop does.  Likelihood plateaus therefore
 // tie exactly as they do on the CPU.  No tensor cores: the path is not a contraction.
 //
-// Roofs: ~6.5 algorithmic HBM bytes per likelihood (6.5 MB of real DRAM traffic per bench step) vs ~1.6 KB of
-// shared-memory reads and ~400 FP64 instructions per likelihood, so shared-memory bandwidth (then the FP64 pipe)
-// binds; DESIGN.md has the arithmetic, profiles/README.md the measurements.
+// Roofs: ~6.5 algorithmic HBM bytes per likelihood (0.68 GB of real DRAM traffic per pass over the chr14-scale set
+// against 32 GB algorithmic) vs ~1.6 KB of shared-memory reads and ~400 FP64 instructions per likelihood, so
+// shared-memory bandwidth (then issue slots and the FP64 pipe) binds; DESIGN.md has the arithmetic,
+// profiles/README.md the measurements.
 
 #include "fb_device.h"
 #include "fb_glibc_math.h"
