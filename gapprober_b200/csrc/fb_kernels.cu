@@ -204,6 +204,13 @@ __device__ __forceinline__ void fetch_classes(const uint4* __restrict__ codes, c
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// 8-byte load from a shared-memory byte address
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -672,23 +679,25 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
                                 v_lo = lo;
                             }
                         }
-                        const double* wrow0 = wM + kPadW + x0 + lane;
+                        // shared-memory byte addresses by hand (ld.shared with a 32-bit address): per entry one byte extract, one
+                        // multiply-add and the load, instead of an index rebuilt from its parts
+                        const uint32_t wrow0 = smem_u32(wM + kPadW + x0 + lane);
                         for (int rl = 0; rl < n_m; rl++) {
                             const int qs = __shfl_sync(0xffffffffu, v_qs, rl), qe = __shfl_sync(0xffffffffu, v_qe, rl);
                             if (qs >= qe) continue;
                             const int lo = __shfl_sync(0xffffffffu, v_lo, rl);
                             const uint8_t* jl = SM.jl + rl * kListBytes;
-                            const double* wr = wrow0 + rl * WS - lo;              // wr[-j] = score of placement (row - j) of this record
+                            const uint32_t wr = wrow0 + (uint32_t)((rl * WS - lo) * 8);   // score of placement (row - j) of this record at wr - 8 j
                             int q = qs;
-                            for (; q < qe && (q & 3); q++) a0 = dadd(a0, wr[-(int)jl[q]]);        // figbird.cpp:1879
+                            for (; q < qe && (q & 3); q++) a0 = dadd(a0, lds_f64(wr - 8u * jl[q]));        // figbird.cpp:1879
 #pragma unroll 2
                             for (; q + 4 <= qe; q += 4) {
                                 const uint32_t j4 = *reinterpret_cast<const uint32_t*>(jl + q);
-                                const double w0 = wr[-(int)(j4 & 0xffu)], w1 = wr[-(int)((j4 >> 8) & 0xffu)];
-                                const double w2 = wr[-(int)((j4 >> 16) & 0xffu)], w3 = wr[-(int)(j4 >> 24)];
+                                const double w0 = lds_f64(wr - 8u * __byte_perm(j4, 0, 0x4440)), w1 = lds_f64(wr - 8u * __byte_perm(j4, 0, 0x4441));
+                                const double w2 = lds_f64(wr - 8u * __byte_perm(j4, 0, 0x4442)), w3 = lds_f64(wr - 8u * __byte_perm(j4, 0, 0x4443));
                                 a0 = dadd(dadd(dadd(dadd(a0, w0), w1), w2), w3);
                             }
-                            for (; q < qe; q++) a0 = dadd(a0, wr[-(int)jl[q]]);
+                            for (; q < qe; q++) a0 = dadd(a0, lds_f64(wr - 8u * jl[q]));
                         }
                         if (ok0) cr[0] = a0;
                     } else {
