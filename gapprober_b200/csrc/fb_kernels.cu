@@ -262,8 +262,8 @@ __device__ __forceinline__ void score_pair(const unsigned char* pa, const uint32
     int k = REV ? L2 - 1 - jb : jb;    // read-position index of base j (figbird.cpp:1845-1852)
     int j0 = jb;
     pa += jb * 16;
-    for (; j0 + 4 <= je; j0 += 4) {
-        const uint32_t cw = cls4[j0 >> 3] >> ((j0 & 4) * 4);                // four base classes, 4 bits each
+    // four bases: their classes are the low 16 bits of cw (4 bits each)
+    auto four = [&](const uint32_t cw) {
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const unsigned char* a = pa + ((cw >> (4 * q)) & 7u) * cstride + q * 16;   // class table of this base, row of this placement
@@ -277,6 +277,19 @@ __device__ __forceinline__ void score_pair(const unsigned char* pa, const uint32
         }
         pa += 64;
         k += REV ? -4 : 4;
+    };
+    if ((j0 & 4) && j0 + 4 <= je) {          // up to an 8-base boundary of the packed classes
+        four(cls4[j0 >> 3] >> 16);
+        j0 += 4;
+    }
+    for (; j0 + 8 <= je; j0 += 8) {          // one 32-bit word of classes per trip
+        const uint32_t cw = cls4[j0 >> 3];
+        four(cw);
+        four(cw >> 16);
+    }
+    if (j0 + 4 <= je) {
+        four(cls4[j0 >> 3]);
+        j0 += 4;
     }
     for (; j0 < je; j0++) {
         const unsigned c = (cls4[j0 >> 3] >> ((j0 & 7) * 4)) & 7u;
@@ -656,7 +669,9 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
                         // zero-filled tail), so a row that is not inside the window for some entry adds +0.0 — exact: the
                         // accumulators are sums of non-negative scores (or NaN), never -0.0 — and the loop needs no predicates:
                         // per entry one LDS.64 + DADD, list positions fetched four at a time.
-                        const int c = task / nrb_q, rb = CLU ? (task - c * nrb_q) * (int)csize + (int)crank : task - c * nrb_q;
+                        int c = 0, rbq = task;                                   // class-major: five classes, counted off
+                        while (rbq >= nrb_q) { rbq -= nrb_q; c++; }
+                        const int rb = CLU ? rbq * (int)csize + (int)crank : rbq;
                         const int xg = rb * 32 + lane, x0 = D + rb * 32 + (D + rb * 32 >= hl ? hn : 0);   // table row, profile row of lane 0
                         const bool ok0 = xg < gpc;
                         double* cr = s.cnt + c * gps + xg;
@@ -706,7 +721,14 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
                         const int te = task - tM;
                         // block-major: the first 64 placements of every record (full two-chain tasks) go out before the records'
                         // last blocks (partly filled or empty), so the tasks a round ends on are the short ones
-                        const int blk = p.e_rec_major ? te % nblk : te / ne_q, rq = p.e_rec_major ? te / nblk : te - blk * ne_q;
+                        // (a record has a handful of blocks: counting them off is cheaper than an integer division)
+                        int blk = 0, rq = te;
+                        if (p.e_rec_major) {
+                            rq = te / nblk;
+                            blk = te - rq * nblk;
+                        } else {
+                            while (rq >= ne_q) { rq -= ne_q; blk++; }
+                        }
                         const int rl = CLU ? rq * (int)csize + (int)crank : rq;
                         const FbRecMeta rm = SE.meta[rl];
                         const int fl2 = rm.flags, L2 = fl2 & 0xff, tb = rm.tb;
@@ -809,9 +831,12 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
                         }
                         // tempProb > maxProb with maxProb starting at 0 (-DBL_MAX in f=1): NaN and scores not above it never win;
                         // the maximum is over the scores as the reference compares them (log scores in f=1)
-                        unsigned long long ba = score_key<F1>(sa, va_ok), bb = score_key<F1>(sb, vb_ok);
-                        ba = warp_max_u64(ba > bb ? ba : bb);
-                        if (lane == 0 && ba > key_init<F1>()) atomicMax(&SE.rmax[rl], ba);
+                        // maxProb only feeds placeReads' return value, and only the last iteration's is ever used (figbird.cpp:2472-2478)
+                        if (last) {
+                            unsigned long long ba = score_key<F1>(sa, va_ok), bb = score_key<F1>(sb, vb_ok);
+                            ba = warp_max_u64(ba > bb ? ba : bb);
+                            if (lane == 0 && ba > key_init<F1>()) atomicMax(&SE.rmax[rl], ba);
+                        }
                     }
                 }
                 if (tid == 0) s_queue[(round + 1) & 1] = 0;   // nobody touches the other slot during this round
