@@ -211,6 +211,17 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
     return v;
 }
 
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -515,6 +526,7 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
     __shared__ int s_unit;
     __shared__ int s_queue[2];
     __shared__ __align__(8) uint64_t s_bar[3];   // one per stage buffer: completion of the bulk copies that fill it
+    __shared__ Stage s_stage[3];                 // the three stage buffers' sections: fixed for the launch, carved once
     uint32_t bar_phase = 0;                      // bit k: parity the next wait on s_bar[k] has to see (same in every thread)
     __shared__ double sT[25];
     __shared__ double2 sRow[5][5];   // {P,Q} per base class of a row whose counts are one-hot in base b (flanks, and b=4: untouched gap rows)
@@ -524,6 +536,7 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
 
     for (int i = tid; i < pwin; i += NT) s.ild[i] = p.ild[i];
     if (tid < 25) sT[tid] = p.T[tid];
+    if (tid < 3) s_stage[tid] = stage_at(s, tid);
     if (tid == 0) {
         for (int k = 0; k < 3; k++) mbar_init(&s_bar[k], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -628,7 +641,7 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
                 const int n_l = cl < nchunks ? min(CH, nrec - cl * CH) : 0;
                 const int n_e = (ce >= 0 && ce < nchunks) ? min(CH, nrec - ce * CH) : 0;
                 const int n_m = (cm >= 0 && cm < nchunks) ? min(CH, nrec - cm * CH) : 0;
-                const Stage SL = stage_at(s, cl % 3), SE = stage_at(s, (ce + 3) % 3), SM = stage_at(s, (cm + 3) % 3);
+                const Stage &SL = s_stage[cl % 3], &SE = s_stage[(ce + 3) % 3], &SM = s_stage[(cm + 3) % 3];
                 double* wE = s.w0 + ((ce + 2) & 1) * s.w_stride;
                 const double* wM = s.w0 + ((cm + 2) & 1) * s.w_stride;
                 if (last && tid < n_m) {   // per-record maximum of the last iteration (feeds figbird.cpp:1951-1955 on the host)
@@ -696,23 +709,24 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
                         }
                         // shared-memory byte addresses by hand (ld.shared with a 32-bit address): per entry one byte extract, one
                         // multiply-add and the load, instead of an index rebuilt from its parts
-                        const uint32_t wrow0 = smem_u32(wM + kPadW + x0 + lane);
+                        const uint32_t wrow0 = smem_u32(wM + kPadW + x0 + lane), jl0 = smem_u32(SM.jl);
                         for (int rl = 0; rl < n_m; rl++) {
                             const int qs = __shfl_sync(0xffffffffu, v_qs, rl), qe = __shfl_sync(0xffffffffu, v_qe, rl);
                             if (qs >= qe) continue;
                             const int lo = __shfl_sync(0xffffffffu, v_lo, rl);
-                            const uint8_t* jl = SM.jl + rl * kListBytes;
+                            const uint32_t jl = jl0 + (uint32_t)(rl * kListBytes);       // this record's class-sorted position list
                             const uint32_t wr = wrow0 + (uint32_t)((rl * WS - lo) * 8);   // score of placement (row - j) of this record at wr - 8 j
-                            int q = qs;
-                            for (; q < qe && (q & 3); q++) a0 = dadd(a0, lds_f64(wr - 8u * jl[q]));        // figbird.cpp:1879
+                            uint32_t q = jl + (uint32_t)qs;
+                            const uint32_t qend = jl + (uint32_t)qe;
+                            for (; q < qend && (q & 3u); q++) a0 = dadd(a0, lds_f64(wr - 8u * lds_u8(q)));        // figbird.cpp:1879
 #pragma unroll 2
-                            for (; q + 4 <= qe; q += 4) {
-                                const uint32_t j4 = *reinterpret_cast<const uint32_t*>(jl + q);
+                            for (; q + 4 <= qend; q += 4) {
+                                const uint32_t j4 = lds_u32(q);
                                 const double w0 = lds_f64(wr - 8u * __byte_perm(j4, 0, 0x4440)), w1 = lds_f64(wr - 8u * __byte_perm(j4, 0, 0x4441));
                                 const double w2 = lds_f64(wr - 8u * __byte_perm(j4, 0, 0x4442)), w3 = lds_f64(wr - 8u * __byte_perm(j4, 0, 0x4443));
                                 a0 = dadd(dadd(dadd(dadd(a0, w0), w1), w2), w3);
                             }
-                            for (; q < qe; q++) a0 = dadd(a0, lds_f64(wr - 8u * jl[q]));
+                            for (; q < qend; q++) a0 = dadd(a0, lds_f64(wr - 8u * lds_u8(q)));
                         }
                         if (ok0) cr[0] = a0;
                     } else {
@@ -848,7 +862,7 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
             }
 
             // chunk 0 of a kept staging gets its per-record maxima reset here, a barrier ahead of the next iteration's E tasks
-            if (keep_staged && !last && tid < min(CH, nrec)) stage_at(s, 0).rmax[tid] = key_init<F1>();
+            if (keep_staged && !last && tid < min(CH, nrec)) s_stage[0].rmax[tid] = key_init<F1>();
             // ---- computeProbsGap + computeErrorProbsGap on the gap rows (flank rows never change)
             for (int xg = tid; xg < (skip_m ? 0 : gpc); xg += NT) {
                 if (CLU && (unsigned)(xg >> 5) % csize != crank) continue;   // the counts of this row live in another CTA
