@@ -270,8 +270,9 @@ __device__ __forceinline__ double score_step(double s, double term) {
 }
 
 // [jb, je): the bases to multiply in; jb is a multiple of 4 (a chain with a left-flank prefix starts past its first terms).
+// cls: 32-bit shared-memory address of the record's packed classes (a generic load cost six more instructions per trip).
 template <bool REV, bool TWO, bool F1>
-__device__ __forceinline__ void score_pair(const unsigned char* pa, const uint32_t* __restrict__ cls4, unsigned cstride, const FbEmParams& p,
+__device__ __forceinline__ void score_pair(const unsigned char* pa, uint32_t cls, unsigned cstride, const FbEmParams& p,
                                            int L2, int jb, int je, double& sa, double& sb) {
     int k = REV ? L2 - 1 - jb : jb;    // read-position index of base j (figbird.cpp:1845-1852)
     int j0 = jb;
@@ -293,20 +294,20 @@ __device__ __forceinline__ void score_pair(const unsigned char* pa, const uint32
         k += REV ? -4 : 4;
     };
     if ((j0 & 4) && j0 + 4 <= je) {          // up to an 8-base boundary of the packed classes
-        four(cls4[j0 >> 3] >> 16);
+        four(lds_u32(cls + 4u * (unsigned)(j0 >> 3)) >> 16);
         j0 += 4;
     }
     for (; j0 + 8 <= je; j0 += 8) {          // one 32-bit word of classes per trip
-        const uint32_t cw = cls4[j0 >> 3];
+        const uint32_t cw = lds_u32(cls + 4u * (unsigned)(j0 >> 3));
         four(cw);
         four(cw >> 16);
     }
     if (j0 + 4 <= je) {
-        four(cls4[j0 >> 3]);
+        four(lds_u32(cls + 4u * (unsigned)(j0 >> 3)));
         j0 += 4;
     }
     for (; j0 < je; j0++) {
-        const unsigned c = (cls4[j0 >> 3] >> ((j0 & 7) * 4)) & 7u;
+        const unsigned c = (lds_u32(cls + 4u * (unsigned)(j0 >> 3)) >> ((j0 & 7) * 4)) & 7u;
         const unsigned char* a = pa + c * cstride;
         const double2 va = *reinterpret_cast<const double2*>(a);
         const double2 e = p.eo_tab[k];
@@ -337,6 +338,45 @@ __device__ __forceinline__ void score_uniform(const uint32_t* __restrict__ cls4,
         }
         k += 4 * ks;
     }
+}
+
+// One chain of a tail task (plan_tails): every lane has its own record, i.e. its own packed class words (cls: 32-bit
+// shared-memory address of the record's cls4) and table rows; mate length and orientation are the same in all lanes.
+template <bool REV, bool F1>
+__device__ __forceinline__ double score_tail(const unsigned char* pa, uint32_t cls, unsigned cstride, const FbEmParams& p, int L2, double sa) {
+    int k = REV ? L2 - 1 : 0;
+    auto four = [&](const uint32_t cw) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const double2 va = *reinterpret_cast<const double2*>(pa + ((cw >> (4 * q)) & 7u) * cstride + q * 16);
+            const double2 e = p.eo_tab[REV ? k - q : k + q];
+            sa = score_step<F1>(sa, dadd(dmul(va.x, e.x), dmul(e.y, va.y)));   // figbird.cpp:1855 / 1862
+        }
+        pa += 64;
+        k += REV ? -4 : 4;
+    };
+    int j0 = 0;
+    for (; j0 + 8 <= L2; j0 += 8, cls += 4) {      // one 32-bit word of classes per trip
+        const uint32_t cw = lds_u32(cls);
+        four(cw);
+        four(cw >> 16);
+    }
+    if (j0 < L2) {
+        uint32_t cw = lds_u32(cls);
+        if (j0 + 4 <= L2) {
+            four(cw);
+            cw >>= 16;
+            j0 += 4;
+        }
+        for (; j0 < L2; j0++, cw >>= 4) {
+            const double2 va = *reinterpret_cast<const double2*>(pa + (cw & 7u) * cstride);
+            const double2 e = p.eo_tab[k];
+            sa = score_step<F1>(sa, dadd(dmul(va.x, e.x), dmul(e.y, va.y)));
+            pa += 16;
+            k += REV ? -1 : 1;
+        }
+    }
+    return sa;
 }
 
 // Per-record running maximum as an unsigned key (atomicMax in shared memory).  f=0: maxProb starts at 0 and only scores
@@ -719,19 +759,20 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
                     }
                     if (tid < n_l) SL.rmax[tid] = key_init<F1>();   // new iteration (or new chunk), new maximum
                 }
-                // the queue of a round: [tail plan of chunk cl] [M tasks of chunk cm] [tail tasks of chunk ce] [E tasks of chunk ce]
+                // the queue of a round: [tail plan of chunk cl] [E tasks of chunk ce] [tail tasks of chunk ce] [M tasks of chunk cm]
                 const int tP = (pack && n_l && full_stage) ? 1 : 0;
                 const int ntt = (pack && n_e) ? (int)SE.tpk[CH] : 0;
                 const int tM = (n_m && !skip_m) ? nrb_q * 5 : 0, tE = ne_q * nblk;
                 const int ntask = tP + tM + ntt + tE;
-                // order of the segments (experiment knob FB_TASK_ORDER: bit 0 = M tasks last, bit 1 = tail tasks after the E tasks)
+                // the small M tasks last: they fill the end of the round behind the long E tasks (cfg4 EM 363 -> 360 ms)
+                // (experiment knob FB_TASK_ORDER: bit 0 = M tasks first, bit 1 = tail tasks before the E tasks)
                 int oM, oT, oE;
                 {
                     int base = tP;
-                    if (!(p.task_order & 1)) { oM = base; base += tM; }
-                    if (!(p.task_order & 2)) { oT = base; base += ntt; oE = base; base += tE; }
+                    if (p.task_order & 1) { oM = base; base += tM; }
+                    if (p.task_order & 2) { oT = base; base += ntt; oE = base; base += tE; }
                     else { oE = base; base += tE; oT = base; base += ntt; }
-                    if (p.task_order & 1) oM = base;
+                    if (!(p.task_order & 1)) oM = base;
                 }
                 const unsigned cstride = (unsigned)nrs * 16u;              // bytes between the class tables
                 int* queue = &s_queue[round & 1];
@@ -825,11 +866,10 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
                             const int lo = max(rm.a_lo, D - L2 + 1), hi = min(rm.a_hi, D + gp - 1);
                             const int kt = ((hi - lo + 1) & ~31) + ti;               // slot of this lane's placement in its record's score row
                             const int u = lo + kt;
-                            double sa = s.ild[(left ? u + rm.tb : rm.tb - u) - p.thr_min], sx = 0.0;
+                            double sa = s.ild[(left ? u + rm.tb : rm.tb - u) - p.thr_min];
                             const unsigned char* pa = reinterpret_cast<const unsigned char*>(s.pq + (u - R0 - (lo >= hl ? hn : 0)));
-                            const uint32_t* cls4 = SE.cls4 + rl * 16;
-                            if (rev) score_pair<true, false, F1>(pa, cls4, cstride, p, L2, 0, L2, sa, sx);
-                            else score_pair<false, false, F1>(pa, cls4, cstride, p, L2, 0, L2, sa, sx);
+                            const uint32_t cls = smem_u32(SE.cls4) + (uint32_t)rl * 64u;
+                            sa = rev ? score_tail<true, F1>(pa, cls, cstride, p, L2, sa) : score_tail<false, F1>(pa, cls, cstride, p, L2, sa);
                             if (ok) {
                                 wE[kPadW + rl * WS + kt] = F1 ? fbm_pow10(sa) : sa;
                                 if (last) {
@@ -889,6 +929,7 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
                         double sa = s.ild[ta - p.thr_min], sb = s.ild[tbb - p.thr_min];   // f=1: the table holds log(ILD[t]) (host libm)
                         const unsigned char* pa = reinterpret_cast<const unsigned char*>(s.pq + (uc - R0 - (lo >= hl ? hn : 0)));
                         const uint32_t* cls4 = SE.cls4 + rl * 16;
+                        const uint32_t cls = smem_u32(cls4);
                         const bool two = lo + 64 * blk + 32 <= hi;           // any lane with a second placement?
                         // Left-flank prefixes (FbPrefixParams): every lane of chain A has at least jsA terms against left-flank
                         // rows, chain B 32 fewer; where that is 4 or more the chain starts from the tabulated running score.
@@ -921,8 +962,8 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
                             const int jend = headB ? skA : L2;
 #pragma unroll 1
                             for (;;) {
-                                if (rev) score_pair<true, false, F1>(p1, cls4, cstride, p, L2, jb, je, s1, s2);
-                                else score_pair<false, false, F1>(p1, cls4, cstride, p, L2, jb, je, s1, s2);
+                                if (rev) score_pair<true, false, F1>(p1, cls, cstride, p, L2, jb, je, s1, s2);
+                                else score_pair<false, false, F1>(p1, cls, cstride, p, L2, jb, je, s1, s2);
                                 if (je == jend) break;
                                 score_uniform<false, F1>(cls4, p, L2, rev, g0, g1, s1, s2);
                                 jb = g1;
@@ -935,8 +976,8 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
                             int jb = skA, je = g0;
 #pragma unroll 1
                             for (;;) {
-                                if (rev) score_pair<true, true, F1>(pa, cls4, cstride, p, L2, jb, je, sa, sb);
-                                else score_pair<false, true, F1>(pa, cls4, cstride, p, L2, jb, je, sa, sb);
+                                if (rev) score_pair<true, true, F1>(pa, cls, cstride, p, L2, jb, je, sa, sb);
+                                else score_pair<false, true, F1>(pa, cls, cstride, p, L2, jb, je, sa, sb);
                                 if (je == L2) break;
                                 score_uniform<true, F1>(cls4, p, L2, rev, g0, g1, sa, sb);
                                 jb = g1;

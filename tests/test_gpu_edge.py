@@ -253,6 +253,7 @@ def test_kernel_variants_agree_bit_for_bit(built):
                     # tail tasks (partly filled last chains of several records in one warp) off, and on with other chunk sizes
                     {"FB_NO_TAILPACK": "1", "FB_CLUSTER": "1"}, {"FB_NO_TAILPACK": "1", "FB_CLUSTER": "1", "FB_CHUNK": "32"},
                     {"FB_CLUSTER": "1", "FB_CHUNK": "5"}, {"FB_CLUSTER": "1", "FB_CHUNK": "8", "FB_NO_PREFIX": "1"},
+                    {"FB_CLUSTER": "1", "FB_TASK_ORDER": "3"}, {"FB_CLUSTER": "1", "FB_TASK_ORDER": "1", "FB_NO_T0": "1", "FB_CHUNK": "4"},
                     {"FB_CLUSTER": "1", "FB_ONE_CTA": "1", "FB_THREADS1": "512", "FB_CHUNK": "32"}):
             assert _fill_with_env(case, gaps, env) == ref, (name, env)
 
