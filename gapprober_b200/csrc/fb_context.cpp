@@ -1604,8 +1604,6 @@ void fill_em_params(fb_ctx* c, FbEmParams& p) {
     memcpy(p.t0_tab, c->h_t0.data(), sizeof p.t0_tab);
     p.use_t0 = getenv("FB_NO_T0") ? 0 : 1;
     p.e_rec_major = getenv("FB_E_REC_MAJOR") ? 1 : 0;
-    p.tail_pack = getenv("FB_NO_TAILPACK") ? 0 : 1;
-    p.task_order = getenv("FB_TASK_ORDER") ? atoi(getenv("FB_TASK_ORDER")) : 0;
     p.unit_maxprob = c->d_maxprob.p;
     p.unit_cons = c->d_cons.p;
     p.dump_unit = -1;

@@ -66,9 +66,6 @@ struct FbEmParams {
     double t0_tab[5][FB_MAX_READ];
     int use_t0;
     int e_rec_major;           // experiment knob (FB_E_REC_MAJOR=1): E tasks of a round in (record, block) order instead of (block, record)
-    int tail_pack;             // the last, partly filled chains of several records of a chunk share one warp (fb_kernels.cu: plan_tails);
-                               // FB_NO_TAILPACK=1 switches it off
-    int task_order;            // experiment knob (FB_TASK_ORDER): order of a round's task segments, see fb_em_kernel
     // work list
     const FbUnit* units;
     int n_units;

@@ -120,8 +120,6 @@ struct Stage {
     uint8_t* cum;     // [chunk][32]  cum[c*4+w] = index in jl of the first position of class c that lies in mask word <= w
                       //              (i.e. class start + number of class-c positions in words above w); cum[20+c] = class end
     unsigned long long* rmax;   // [chunk] running maximum score of the record in this iteration (bit pattern of a positive double)
-    uint16_t* tpk;    // [chunk + 1] tail packing of this chunk for the unit at hand (plan_tails): per record 0xffff, or
-                      //             lanes [bits 0-4, bits 5-10) of tail task (bits 11-14); [chunk] = number of tail tasks
 };
 constexpr int kStageCopyBytes = 16 + 80 + 64 + kListBytes + 32;   // per record, brought in by the bulk copies (all but rmax)
 
@@ -147,7 +145,6 @@ __device__ __forceinline__ Stage stage_at(const EmSmem& s, int k) {
     t.jl = reinterpret_cast<uint8_t*>(t.cls4 + 16 * s.chunk);
     t.cum = t.jl + kListBytes * s.chunk;
     t.rmax = reinterpret_cast<unsigned long long*>(t.cum + 32 * s.chunk);
-    t.tpk = reinterpret_cast<uint16_t*>(t.rmax + s.chunk);
     return t;
 }
 
@@ -172,8 +169,8 @@ __host__ __device__ inline size_t em_carve(unsigned char* base, EmSmem* s, int n
     a = take(2 * wbytes);
     if (s) { s->w0 = (double*)a; s->w_stride = wbytes / sizeof(double); }
     // one staged chunk: meta[chunk] 16 B | mask[chunk][20] u32 | cls4[chunk][16] u32 | jl[chunk][144] u8 | cum[chunk][32] u8 |
-    //                   rmax[chunk] u64 | tpk[chunk + 1] u16
-    const size_t sbytes = align16((size_t)chunk * (kStageCopyBytes + 8) + 2 * ((size_t)chunk + 1));
+    //                   rmax[chunk] u64
+    const size_t sbytes = align16((size_t)chunk * (kStageCopyBytes + 8));
     a = take(3 * sbytes);
     if (s) { s->st0 = a; s->st_stride = sbytes; s->chunk = chunk; }
     return off;
@@ -270,9 +267,8 @@ __device__ __forceinline__ double score_step(double s, double term) {
 }
 
 // [jb, je): the bases to multiply in; jb is a multiple of 4 (a chain with a left-flank prefix starts past its first terms).
-// cls: 32-bit shared-memory address of the record's packed classes (a generic load cost six more instructions per trip).
 template <bool REV, bool TWO, bool F1>
-__device__ __forceinline__ void score_pair(const unsigned char* pa, uint32_t cls, unsigned cstride, const FbEmParams& p,
+__device__ __forceinline__ void score_pair(const unsigned char* pa, const uint32_t* __restrict__ cls4, unsigned cstride, const FbEmParams& p,
                                            int L2, int jb, int je, double& sa, double& sb) {
     int k = REV ? L2 - 1 - jb : jb;    // read-position index of base j (figbird.cpp:1845-1852)
     int j0 = jb;
@@ -294,20 +290,20 @@ __device__ __forceinline__ void score_pair(const unsigned char* pa, uint32_t cls
         k += REV ? -4 : 4;
     };
     if ((j0 & 4) && j0 + 4 <= je) {          // up to an 8-base boundary of the packed classes
-        four(lds_u32(cls + 4u * (unsigned)(j0 >> 3)) >> 16);
+        four(cls4[j0 >> 3] >> 16);
         j0 += 4;
     }
     for (; j0 + 8 <= je; j0 += 8) {          // one 32-bit word of classes per trip
-        const uint32_t cw = lds_u32(cls + 4u * (unsigned)(j0 >> 3));
+        const uint32_t cw = cls4[j0 >> 3];
         four(cw);
         four(cw >> 16);
     }
     if (j0 + 4 <= je) {
-        four(lds_u32(cls + 4u * (unsigned)(j0 >> 3)));
+        four(cls4[j0 >> 3]);
         j0 += 4;
     }
     for (; j0 < je; j0++) {
-        const unsigned c = (lds_u32(cls + 4u * (unsigned)(j0 >> 3)) >> ((j0 & 7) * 4)) & 7u;
+        const unsigned c = (cls4[j0 >> 3] >> ((j0 & 7) * 4)) & 7u;
         const unsigned char* a = pa + c * cstride;
         const double2 va = *reinterpret_cast<const double2*>(a);
         const double2 e = p.eo_tab[k];
@@ -338,45 +334,6 @@ __device__ __forceinline__ void score_uniform(const uint32_t* __restrict__ cls4,
         }
         k += 4 * ks;
     }
-}
-
-// One chain of a tail task (plan_tails): every lane has its own record, i.e. its own packed class words (cls: 32-bit
-// shared-memory address of the record's cls4) and table rows; mate length and orientation are the same in all lanes.
-template <bool REV, bool F1>
-__device__ __forceinline__ double score_tail(const unsigned char* pa, uint32_t cls, unsigned cstride, const FbEmParams& p, int L2, double sa) {
-    int k = REV ? L2 - 1 : 0;
-    auto four = [&](const uint32_t cw) {
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const double2 va = *reinterpret_cast<const double2*>(pa + ((cw >> (4 * q)) & 7u) * cstride + q * 16);
-            const double2 e = p.eo_tab[REV ? k - q : k + q];
-            sa = score_step<F1>(sa, dadd(dmul(va.x, e.x), dmul(e.y, va.y)));   // figbird.cpp:1855 / 1862
-        }
-        pa += 64;
-        k += REV ? -4 : 4;
-    };
-    int j0 = 0;
-    for (; j0 + 8 <= L2; j0 += 8, cls += 4) {      // one 32-bit word of classes per trip
-        const uint32_t cw = lds_u32(cls);
-        four(cw);
-        four(cw >> 16);
-    }
-    if (j0 < L2) {
-        uint32_t cw = lds_u32(cls);
-        if (j0 + 4 <= L2) {
-            four(cw);
-            cw >>= 16;
-            j0 += 4;
-        }
-        for (; j0 < L2; j0++, cw >>= 4) {
-            const double2 va = *reinterpret_cast<const double2*>(pa + (cw & 7u) * cstride);
-            const double2 e = p.eo_tab[k];
-            sa = score_step<F1>(sa, dadd(dmul(va.x, e.x), dmul(e.y, va.y)));
-            pa += 16;
-            k += REV ? -1 : 1;
-        }
-    }
-    return sa;
 }
 
 // Per-record running maximum as an unsigned key (atomicMax in shared memory).  f=0: maxProb starts at 0 and only scores
@@ -533,54 +490,6 @@ __global__ void __launch_bounds__(256) fb_prefix_kernel(const __grid_constant__ 
     }
 }
 
-// Tail packing.  Lanes of a warp take 32 consecutive placements of a record (a chain), so a window of W placements costs
-// ceil(W / 32) chains of table loads however few lanes the last one fills — and an LDS.128 with five active lanes costs
-// the same four wavefronts as a full one (profiles/r2_smem_probe.txt).  With an insert window of 101 placements that is a
-// fourth chain for five placements: a fifth of the E-step's loads belonged to lanes without a placement.  One warp plans,
-// per staged chunk and unit, "tail tasks": the last, partly filled chains of several records of the same mate length
-// and orientation (the two things the inner loop takes as warp-uniform) share one warp, every lane with its own
-// record's class words and table rows.  First fit in record order; a tail that finds no partner, or whose chain starts
-// from a left-flank prefix, stays with its record's ordinary tasks.  The scores are the same numbers — a lane runs the
-// same operations in the same order whichever warp it sits in.
-// rmeta: the chunk's n <= 32 records in global memory (the chunk's shared-memory copy is still in flight); out: Stage::tpk.
-__device__ __noinline__ void plan_tails(const FbRecMeta* __restrict__ rmeta, int n, int D, int gp, bool has_pre, uint16_t* tpk,
-                                        int chunk) {
-    const int lane = threadIdx.x & 31;
-    int key = -1, nt = 0;
-    if (lane < n) {
-        const FbRecMeta rm = rmeta[lane];
-        const int L2 = rm.flags & 0xff;
-        const int lo = max(rm.a_lo, D - L2 + 1), hi = min(rm.a_hi, D + gp - 1);
-        const int W = hi - lo + 1;
-        if (W > 0 && (W & 31) && !(has_pre && D - (lo + (W & ~31) + 31) >= 4)) {
-            key = rm.flags & 0x1ff;     // mate length, isReverse
-            nt = W & 31;
-        }
-    }
-    // lane t holds the state of task t
-    int t_key = -2, t_fill = 0, t_cnt = 0, ntask = 0;
-    int my_task = -1, my_l0 = 0;
-    for (int r = 0; r < n; r++) {
-        const int k = __shfl_sync(0xffffffffu, key, r);
-        if (k < 0) continue;
-        const int c = __shfl_sync(0xffffffffu, nt, r);
-        const unsigned fit = __ballot_sync(0xffffffffu, lane < ntask && t_key == k && t_fill + c <= 32);
-        const int t = fit ? __ffs(fit) - 1 : ntask;
-        if (!fit) ntask++;
-        const int l0 = __shfl_sync(0xffffffffu, t_fill, t);
-        if (lane == t) { t_key = k; t_fill += c; t_cnt++; }
-        if (lane == r) { my_task = t; my_l0 = l0; }
-    }
-    const unsigned keep = __ballot_sync(0xffffffffu, lane < ntask && t_cnt >= 2);   // a task of one tail packs nothing
-    if (lane < n) {
-        unsigned v = 0xffffu;
-        if (my_task >= 0 && ((keep >> my_task) & 1u))
-            v = (unsigned)my_l0 | ((unsigned)(my_l0 + nt) << 5) | ((unsigned)__popc(keep & ((1u << my_task) - 1u)) << 11);
-        tpk[lane] = (uint16_t)v;
-    }
-    if (lane == 0) tpk[chunk] = (uint16_t)__popc(keep);
-}
-
 // CLU: one unit is run by a thread-block cluster instead of one CTA — for launches with fewer units than the GPU has
 // CTA slots (single gaps, the stress sweep).  Nothing about the arithmetic changes, so results stay bit-exact:
 //   * every CTA keeps a full copy of the P/Q table and of the two score buffers in its own shared memory;
@@ -624,7 +533,6 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int D = p.D, CH = p.chunk, PS = p.p_stride;
-    const bool pack = !CLU && p.tail_pack;       // tail tasks (plan_tails); a cluster deals its E tasks by record instead
 
     for (int i = tid; i < pwin; i += NT) s.ild[i] = p.ild[i];
     if (tid < 25) sT[tid] = p.T[tid];
@@ -759,35 +667,15 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
                     }
                     if (tid < n_l) SL.rmax[tid] = key_init<F1>();   // new iteration (or new chunk), new maximum
                 }
-                // the queue of a round: [tail plan of chunk cl] [E tasks of chunk ce] [tail tasks of chunk ce] [M tasks of chunk cm]
-                const int tP = (pack && n_l && full_stage) ? 1 : 0;
-                const int ntt = (pack && n_e) ? (int)SE.tpk[CH] : 0;
                 const int tM = (n_m && !skip_m) ? nrb_q * 5 : 0, tE = ne_q * nblk;
-                const int ntask = tP + tM + ntt + tE;
-                // the small M tasks last: they fill the end of the round behind the long E tasks (cfg4 EM 363 -> 360 ms)
-                // (experiment knob FB_TASK_ORDER: bit 0 = M tasks first, bit 1 = tail tasks before the E tasks)
-                int oM, oT, oE;
-                {
-                    int base = tP;
-                    if (p.task_order & 1) { oM = base; base += tM; }
-                    if (p.task_order & 2) { oT = base; base += ntt; oE = base; base += tE; }
-                    else { oE = base; base += tE; oT = base; base += ntt; }
-                    if (!(p.task_order & 1)) oM = base;
-                }
-                const unsigned cstride = (unsigned)nrs * 16u;              // bytes between the class tables
+                const int ntask = tM + tE;
                 int* queue = &s_queue[round & 1];
                 for (;;) {
                     int task = 0;
                     if (lane == 0) task = atomicAdd(queue, 1);
                     task = __shfl_sync(0xffffffffu, task, 0);
                     if (task >= ntask) break;
-                    if (task < tP) {
-                        // ---- tail plan of the chunk being staged (its buffer is the one no task of this round reads)
-                        plan_tails(p.rmeta + (size_t)gm.rec_off + (size_t)cl * CH, n_l, D, gp, p.pre != nullptr, SL.tpk, CH);
-                        continue;
-                    }
-                    if (task >= oM && task < oM + tM) {
-                        task -= oM;
+                    if (task < tM) {
                         // ---- M-step: a lane owns one gap row, a warp one (32 rows, base class) cell block.  Within a cell the CPU adds in
                         // (record asc, placement asc) order (figbird.cpp:1718, 1826, 1874): walking a record's class list from high j
                         // to low j visits its placements in ascending order.  Score rows are zero outside the record's window (pads +
@@ -844,42 +732,7 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
                     } else {
                         // ---- E-step: warp per (record, 64 placements); lanes over placements.  Every slot of the record's score row is
                         // written: the score inside the window, 0.0 outside it (the M-step relies on those zeros).
-                        if (task >= oT && task < oT + ntt) {
-                            const int te = task - oT;
-                            // ---- tail task te: the last, partly filled chains of several records in one warp (plan_tails).  Lane ->
-                            // (record, placement) from the records' lane ranges; lanes left over shadow the task's first placement.
-                            unsigned pk = 0xffffu;
-                            if (lane < n_e) pk = SE.tpk[lane];
-                            const unsigned mem = __ballot_sync(0xffffffffu, pk != 0xffffu && (int)(pk >> 11) == te);
-                            const int l_a = pk & 31u, l_e = (pk >> 5) & 63u;
-                            int rl = __ffs(mem) - 1, ti = 0;      // the task's first record starts at lane 0
-                            bool ok = false;
-                            for (unsigned m = mem; m; m &= m - 1) {
-                                const int r = __ffs(m) - 1;
-                                const int a = __shfl_sync(0xffffffffu, l_a, r), e = __shfl_sync(0xffffffffu, l_e, r);
-                                if (lane >= a && lane < e) { rl = r; ti = lane - a; ok = true; }
-                            }
-                            const FbRecMeta rm = SE.meta[rl];
-                            const int fl0 = __shfl_sync(0xffffffffu, rm.flags, 0);   // mate length and orientation: the same in every member
-                            const int L2 = fl0 & 0xff;
-                            const bool rev = (fl0 >> 8) & 1, left = (rm.flags >> 9) & 1;
-                            const int lo = max(rm.a_lo, D - L2 + 1), hi = min(rm.a_hi, D + gp - 1);
-                            const int kt = ((hi - lo + 1) & ~31) + ti;               // slot of this lane's placement in its record's score row
-                            const int u = lo + kt;
-                            double sa = s.ild[(left ? u + rm.tb : rm.tb - u) - p.thr_min];
-                            const unsigned char* pa = reinterpret_cast<const unsigned char*>(s.pq + (u - R0 - (lo >= hl ? hn : 0)));
-                            const uint32_t cls = smem_u32(SE.cls4) + (uint32_t)rl * 64u;
-                            sa = rev ? score_tail<true, F1>(pa, cls, cstride, p, L2, sa) : score_tail<false, F1>(pa, cls, cstride, p, L2, sa);
-                            if (ok) {
-                                wE[kPadW + rl * WS + kt] = F1 ? fbm_pow10(sa) : sa;
-                                if (last) {
-                                    const unsigned long long key = score_key<F1>(sa, true);
-                                    if (key > key_init<F1>()) atomicMax(&SE.rmax[rl], key);
-                                }
-                            }
-                            continue;
-                        }
-                        const int te = task - oE;
+                        const int te = task - tM;
                         // block-major: the first 64 placements of every record (full two-chain tasks) go out before the records'
                         // last blocks (partly filled or empty), so the tasks a round ends on are the short ones
                         // (a record has a handful of blocks: counting them off is cheaper than an integer division)
@@ -894,28 +747,18 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
                         const FbRecMeta rm = SE.meta[rl];
                         const int fl2 = rm.flags, L2 = fl2 & 0xff, tb = rm.tb;
                         // placements i in [gapStart-L2+1, gapStart+gp) (figbird.cpp:1826) -> u in [D-L2+1, D+gp-1]
-                        const int lo = max(rm.a_lo, D - L2 + 1);
-                        int hi = min(rm.a_hi, D + gp - 1);
+                        const int lo = max(rm.a_lo, D - L2 + 1), hi = min(rm.a_hi, D + gp - 1);
                         double* wrow = wE + kPadW + rl * WS;                  // slot k holds placement lo + k
                         const int ka = 64 * blk + lane, kb = ka + 32;
-                        // a record whose last, partly filled chain went into a tail task: those placements are scored, and their
-                        // slots [t_lo, t_hi) written, there; the window of the tasks here ends with the last full chain
-                        int t_lo = PS, t_hi = PS;
-                        if (pack && SE.tpk[rl] != 0xffffu) {
-                            t_hi = hi - lo + 1;
-                            t_lo = t_hi & ~31;
-                            hi = lo + t_lo - 1;
-                        }
-                        const bool wa_mine = ka < PS && (ka < t_lo || ka >= t_hi), wb_mine = kb < PS && (kb < t_lo || kb >= t_hi);
                         if (lo + 64 * blk > hi) {                              // nothing of the window in this block (or no window at all)
                             if (!CLU) {
-                                if (wa_mine) wrow[ka] = 0.0;
-                                if (wb_mine) wrow[kb] = 0.0;
+                                if (ka < PS) wrow[ka] = 0.0;
+                                if (kb < PS) wrow[kb] = 0.0;
                             } else {
                                 for (unsigned k = 0; k < csize; k++) {
                                     double* wr = cg::this_cluster().map_shared_rank(wrow, k);
-                                    if (wa_mine) wr[ka] = 0.0;
-                                    if (wb_mine) wr[kb] = 0.0;
+                                    if (ka < PS) wr[ka] = 0.0;
+                                    if (kb < PS) wr[kb] = 0.0;
                                 }
                             }
                             continue;
@@ -929,7 +772,7 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
                         double sa = s.ild[ta - p.thr_min], sb = s.ild[tbb - p.thr_min];   // f=1: the table holds log(ILD[t]) (host libm)
                         const unsigned char* pa = reinterpret_cast<const unsigned char*>(s.pq + (uc - R0 - (lo >= hl ? hn : 0)));
                         const uint32_t* cls4 = SE.cls4 + rl * 16;
-                        const uint32_t cls = smem_u32(cls4);
+                        const unsigned cstride = (unsigned)nrs * 16u;
                         const bool two = lo + 64 * blk + 32 <= hi;           // any lane with a second placement?
                         // Left-flank prefixes (FbPrefixParams): every lane of chain A has at least jsA terms against left-flank
                         // rows, chain B 32 fewer; where that is 4 or more the chain starts from the tabulated running score.
@@ -962,8 +805,8 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
                             const int jend = headB ? skA : L2;
 #pragma unroll 1
                             for (;;) {
-                                if (rev) score_pair<true, false, F1>(p1, cls, cstride, p, L2, jb, je, s1, s2);
-                                else score_pair<false, false, F1>(p1, cls, cstride, p, L2, jb, je, s1, s2);
+                                if (rev) score_pair<true, false, F1>(p1, cls4, cstride, p, L2, jb, je, s1, s2);
+                                else score_pair<false, false, F1>(p1, cls4, cstride, p, L2, jb, je, s1, s2);
                                 if (je == jend) break;
                                 score_uniform<false, F1>(cls4, p, L2, rev, g0, g1, s1, s2);
                                 jb = g1;
@@ -976,8 +819,8 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
                             int jb = skA, je = g0;
 #pragma unroll 1
                             for (;;) {
-                                if (rev) score_pair<true, true, F1>(pa, cls, cstride, p, L2, jb, je, sa, sb);
-                                else score_pair<false, true, F1>(pa, cls, cstride, p, L2, jb, je, sa, sb);
+                                if (rev) score_pair<true, true, F1>(pa, cls4, cstride, p, L2, jb, je, sa, sb);
+                                else score_pair<false, true, F1>(pa, cls4, cstride, p, L2, jb, je, sa, sb);
                                 if (je == L2) break;
                                 score_uniform<true, F1>(cls4, p, L2, rev, g0, g1, sa, sb);
                                 jb = g1;
@@ -991,13 +834,13 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
                             wb = two ? fbm_pow10(sb) : 0.0;
                         }
                         if (!CLU) {
-                            if (wa_mine) wrow[ka] = va_ok ? wa : 0.0;
-                            if (wb_mine) wrow[kb] = vb_ok ? wb : 0.0;
+                            if (ka < PS) wrow[ka] = va_ok ? wa : 0.0;
+                            if (kb < PS) wrow[kb] = vb_ok ? wb : 0.0;
                         } else {
                             for (unsigned k = 0; k < csize; k++) {   // the M tasks of every CTA read this row from their own copy
                                 double* wr = cg::this_cluster().map_shared_rank(wrow, k);
-                                if (wa_mine) wr[ka] = va_ok ? wa : 0.0;
-                                if (wb_mine) wr[kb] = vb_ok ? wb : 0.0;
+                                if (ka < PS) wr[ka] = va_ok ? wa : 0.0;
+                                if (kb < PS) wr[kb] = vb_ok ? wb : 0.0;
                             }
                         }
                         // tempProb > maxProb with maxProb starting at 0 (-DBL_MAX in f=1): NaN and scores not above it never win;

@@ -231,8 +231,7 @@ def _fill_with_env(case, gaps, env):
 
 
 def test_kernel_variants_agree_bit_for_bit(built):
-    """One CTA per unit, clusters of 2 and 4 CTAs per unit, 512- and 1024-thread CTAs, other chunk sizes, tail tasks on and
-    off: the same bits.
+    """One CTA per unit, clusters of 2 and 4 CTAs per unit, 512- and 1024-thread CTAs, other chunk sizes: the same bits.
     plateau_1000bp scans estimates up to 1 050 rows (one CTA per SM), the other cases fit two CTAs per SM."""
     for name, n in (("multi_gap_err1pct", 3), ("plateau_1000bp", 1), ("lib180_100bp_60x", 1)):
         case = G.Case(name)
@@ -249,12 +248,7 @@ def test_kernel_variants_agree_bit_for_bit(built):
                     {"FB_TWO_CALL": "1"},                      # scan and finalize as two calls with the selection on the host
                     {"FB_ONE_CTA": "1", "FB_CLUSTER": "2"}, {"FB_ONE_CTA": "1", "FB_CLUSTER": "1"},
                     {"FB_NO_PREFIX": "1"}, {"FB_NO_PREFIX": "1", "FB_CLUSTER": "2"},    # every chain from ILD[t], no left-flank prefix table
-                    {"FB_NO_T0": "1"}, {"FB_NO_T0": "1", "FB_NO_PREFIX": "1"},          # first iteration from the tables like the others
-                    # tail tasks (partly filled last chains of several records in one warp) off, and on with other chunk sizes
-                    {"FB_NO_TAILPACK": "1", "FB_CLUSTER": "1"}, {"FB_NO_TAILPACK": "1", "FB_CLUSTER": "1", "FB_CHUNK": "32"},
-                    {"FB_CLUSTER": "1", "FB_CHUNK": "5"}, {"FB_CLUSTER": "1", "FB_CHUNK": "8", "FB_NO_PREFIX": "1"},
-                    {"FB_CLUSTER": "1", "FB_TASK_ORDER": "3"}, {"FB_CLUSTER": "1", "FB_TASK_ORDER": "1", "FB_NO_T0": "1", "FB_CHUNK": "4"},
-                    {"FB_CLUSTER": "1", "FB_ONE_CTA": "1", "FB_THREADS1": "512", "FB_CHUNK": "32"}):
+                    {"FB_NO_T0": "1"}, {"FB_NO_T0": "1", "FB_NO_PREFIX": "1"}):         # first iteration from the tables like the others
             assert _fill_with_env(case, gaps, env) == ref, (name, env)
 
 
@@ -266,6 +260,5 @@ def test_log_mode_variants_agree_bit_for_bit(built):
     for g, r in zip(gaps, ref):
         assert r[0] == g["filled"] and r[1] == g["best_est"] and r[2] == np.asarray(g["liks"]).tobytes()
     for env in ({"FB_CLUSTER": "2"}, {"FB_CLUSTER": "4", "FB_CHUNK": "8"}, {"FB_HOST_LOG": "1"}, {"FB_NO_COMPACT": "1", "FB_CLUSTER": "2"},
-                {"FB_TWO_CALL": "1"}, {"FB_NO_PREFIX": "1"}, {"FB_NO_T0": "1"},
-                {"FB_NO_TAILPACK": "1", "FB_CLUSTER": "1"}, {"FB_CLUSTER": "1", "FB_CHUNK": "8"}):
+                {"FB_TWO_CALL": "1"}, {"FB_NO_PREFIX": "1"}, {"FB_NO_T0": "1"}):
         assert _fill_with_env(case, gaps, env) == ref, env
