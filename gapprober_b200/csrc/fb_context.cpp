@@ -1583,7 +1583,10 @@ namespace {
 
 void fill_em_params(fb_ctx* c, FbEmParams& p) {
     memset(&p, 0, sizeof p);
-    memcpy(p.eo_tab, c->h_eo.data(), sizeof p.eo_tab);
+    for (int k = 0; k < FB_MAX_READ; k++) {
+        p.eo_tab[k] = c->h_eo[k];
+        p.eo_tab[FB_MAX_READ + k] = c->h_eo[FB_MAX_READ - 1 - k];      // backwards, for reverse-complemented mates
+    }
     p.ild = c->d_ild_em.p;
     memcpy(p.T, c->T, sizeof p.T);
     p.thr_min = c->thr_min;

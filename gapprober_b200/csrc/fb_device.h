@@ -41,8 +41,11 @@ struct FbUnit {
 
 struct FbEmParams {
     // model
-    double2 eo_tab[FB_MAX_READ];   // {1 - e[k], e[k]} per read position: lives in the kernel-parameter constant bank, so the
-                                   // E-step fetches it through the constant cache instead of shared-memory bandwidth
+    double2 eo_tab[2 * FB_MAX_READ];   // {1 - e[k], e[k]} per read position: lives in the kernel-parameter constant bank, so
+                                   // the E-step fetches it through the constant cache instead of shared-memory bandwidth.
+                                   // Twice: [k] forwards, and [FB_MAX_READ + i] = entry FB_MAX_READ-1-i, so that a
+                                   // reverse-complemented mate of length L (read position L-1-j for base j) walks the table
+                                   // upwards too, from 2*FB_MAX_READ - L: one E loop for both orientations
     const double* ild;      // insertLengthDistSmoothed[thr_min .. thr_max]
     double T[25];           // errorTypeProbs
     int thr_min, thr_max, D, num_iter, max_read_len;

@@ -257,8 +257,10 @@ __device__ __forceinline__ void load_record_bytes(const uint4* __restrict__ code
 }
 
 // E-step of 64 placements of one record: lane owns placements ua and ua+32 (two independent product chains).
-// The running score is multiplied base by base in read order (figbird.cpp:1840-1864); REV selects the
-// read-position index k = L2-1-j of a reverse-complemented mate (figbird.cpp:1845-1852).
+// The running score is multiplied base by base in read order (figbird.cpp:1840-1864).  The read-position index of base j
+// is j, or L2-1-j for a reverse-complemented mate (figbird.cpp:1845-1852): FbEmParams::eo_tab holds the {1-e, e} table
+// twice, forwards and backwards, so that both orientations walk it upwards from their own start k0 — one copy of the
+// loop instead of two (the task loop's code no longer fits the 32 KB instruction-cache level otherwise).
 // F1 is the reference's log-domain mode (argv[2] = 1): the running score is a SUM of glibc logs of the same terms
 // (figbird.cpp:1856, 1861), started from log(ILD[t]) (figbird.cpp:1835).
 template <bool F1>
@@ -266,11 +268,14 @@ __device__ __forceinline__ double score_step(double s, double term) {
     return F1 ? dadd(s, fbm_log(term)) : dmul(s, term);
 }
 
+// eo_tab index of base 0 of a mate of length L2
+__device__ __forceinline__ int eo_start(bool rev, int L2) { return rev ? 2 * FB_MAX_READ - L2 : 0; }
+
 // [jb, je): the bases to multiply in; jb is a multiple of 4 (a chain with a left-flank prefix starts past its first terms).
-template <bool REV, bool TWO, bool F1>
+template <bool TWO, bool F1>
 __device__ __forceinline__ void score_pair(const unsigned char* pa, const uint32_t* __restrict__ cls4, unsigned cstride, const FbEmParams& p,
-                                           int L2, int jb, int je, double& sa, double& sb) {
-    int k = REV ? L2 - 1 - jb : jb;    // read-position index of base j (figbird.cpp:1845-1852)
+                                           int k0, int jb, int je, double& sa, double& sb) {
+    int k = k0 + jb;                   // eo_tab index of base j
     int j0 = jb;
     pa += jb * 16;
     // four bases: their classes are the low 16 bits of cw (4 bits each)
@@ -279,7 +284,7 @@ __device__ __forceinline__ void score_pair(const unsigned char* pa, const uint32
         for (int q = 0; q < 4; q++) {
             const unsigned char* a = pa + ((cw >> (4 * q)) & 7u) * cstride + q * 16;   // class table of this base, row of this placement
             const double2 va = *reinterpret_cast<const double2*>(a);
-            const double2 e = p.eo_tab[REV ? k - q : k + q];                // {1 - e[k], e[k]} via the constant cache
+            const double2 e = p.eo_tab[k + q];                              // {1 - e[k], e[k]} via the constant cache
             sa = score_step<F1>(sa, dadd(dmul(va.x, e.x), dmul(e.y, va.y)));   // figbird.cpp:1855 / 1862
             if (TWO) {
                 const double2 vb = *reinterpret_cast<const double2*>(a + 32 * 16);
@@ -287,7 +292,7 @@ __device__ __forceinline__ void score_pair(const unsigned char* pa, const uint32
             }
         }
         pa += 64;
-        k += REV ? -4 : 4;
+        k += 4;
     };
     if ((j0 & 4) && j0 + 4 <= je) {          // up to an 8-base boundary of the packed classes
         four(cls4[j0 >> 3] >> 16);
@@ -302,7 +307,8 @@ __device__ __forceinline__ void score_pair(const unsigned char* pa, const uint32
         four(cls4[j0 >> 3]);
         j0 += 4;
     }
-    for (; j0 < je; j0++) {
+#pragma unroll 1
+    for (; j0 < je; j0++) {                  // at most three bases
         const unsigned c = (cls4[j0 >> 3] >> ((j0 & 7) * 4)) & 7u;
         const unsigned char* a = pa + c * cstride;
         const double2 va = *reinterpret_cast<const double2*>(a);
@@ -313,7 +319,7 @@ __device__ __forceinline__ void score_pair(const unsigned char* pa, const uint32
             sb = score_step<F1>(sb, dadd(dmul(vb.x, e.x), dmul(e.y, vb.y)));
         }
         pa += 16;
-        k += REV ? -1 : 1;
+        k++;
     }
 }
 
@@ -774,6 +780,7 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
                         const uint32_t* cls4 = SE.cls4 + rl * 16;
                         const unsigned cstride = (unsigned)nrs * 16u;
                         const bool two = lo + 64 * blk + 32 <= hi;           // any lane with a second placement?
+                        const int k0 = eo_start(rev, L2);
                         // Left-flank prefixes (FbPrefixParams): every lane of chain A has at least jsA terms against left-flank
                         // rows, chain B 32 fewer; where that is 4 or more the chain starts from the tabulated running score.
                         int skA = 0, skB = 0;
@@ -805,8 +812,7 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
                             const int jend = headB ? skA : L2;
 #pragma unroll 1
                             for (;;) {
-                                if (rev) score_pair<true, false, F1>(p1, cls4, cstride, p, L2, jb, je, s1, s2);
-                                else score_pair<false, false, F1>(p1, cls4, cstride, p, L2, jb, je, s1, s2);
+                                score_pair<false, F1>(p1, cls4, cstride, p, k0, jb, je, s1, s2);
                                 if (je == jend) break;
                                 score_uniform<false, F1>(cls4, p, L2, rev, g0, g1, s1, s2);
                                 jb = g1;
@@ -819,8 +825,7 @@ __global__ void __launch_bounds__(NT, (GT || NT > 512) ? 1 : 2) fb_em_kernel(con
                             int jb = skA, je = g0;
 #pragma unroll 1
                             for (;;) {
-                                if (rev) score_pair<true, true, F1>(pa, cls4, cstride, p, L2, jb, je, sa, sb);
-                                else score_pair<false, true, F1>(pa, cls4, cstride, p, L2, jb, je, sa, sb);
+                                score_pair<true, F1>(pa, cls4, cstride, p, k0, jb, je, sa, sb);
                                 if (je == L2) break;
                                 score_uniform<true, F1>(cls4, p, L2, rev, g0, g1, sa, sb);
                                 jb = g1;
