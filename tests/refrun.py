@@ -37,7 +37,7 @@ def run_reference(wd, dump_probs=True, f_mode=0):
     return dict(model=model, dump=dump, gapout=gapout, stdout=out)
 
 
-def run_reference_on_gaps(wd, gap_ids, procs, tmp):
+def run_reference_on_gaps(wd, gap_ids, procs, tmp, f_mode=0):
     """The instrumented reference on a SUBSET of the gaps of wd, spread over `procs` concurrent processes (each gets a
     working directory with its share of the gaps renumbered from 0 and the big inputs symlinked).  Returns
     {gap_id: dict(est={estimate: lik}, best=(estimate, lik, bestString), filled=str)}."""
@@ -60,7 +60,7 @@ def run_reference_on_gaps(wd, gap_ids, procs, tmp):
         dirs.append(d)
     env = dict(os.environ)
     env.pop("FB_DUMP_PROBS", None)
-    ps = [subprocess.Popen([REF_DUMP, "scaffolds.fa", " 0", "250"], cwd=d, env=env, stdout=subprocess.DEVNULL) for d in dirs]
+    ps = [subprocess.Popen([REF_DUMP, "scaffolds.fa", f" {f_mode}", "250"], cwd=d, env=env, stdout=subprocess.DEVNULL) for d in dirs]
     for p in ps:
         if p.wait() != 0:
             raise RuntimeError("reference figbird_dump.out failed")
