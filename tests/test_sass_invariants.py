@@ -128,3 +128,26 @@ def test_task_loop_fits_the_instruction_cache_level(kernels):
     task_loop = min(enclosing)
     assert task_loop * 16 <= 32 * 1024, f"task loop is {task_loop} instructions = {task_loop * 16} bytes"
     assert len(ins) < 5200, f"main EM variant has grown to {len(ins)} instructions"
+
+
+def test_register_and_parameter_budgets():
+    """Two 512-thread CTAs (or one of 1024 threads) per SM need at most 64 registers per thread; the kernel parameters
+    (both copies of the {1-e, e} table and the first-iteration terms travel in them) must stay below the 32 KB limit."""
+    exe = _cuobjdump()
+    if exe is None or not os.path.exists(LIB):
+        pytest.skip("cuobjdump or the library not found")
+    out = subprocess.run([exe, "-res-usage", LIB], stdout=subprocess.PIPE, check=True).stdout.decode().splitlines()
+    seen = 0
+    for i, ln in enumerate(out):
+        m = re.search(r"Function .*fb_em_kernelILb(\d)ELb(\d)ELi(\d+)ELb(\d)E", ln)
+        if not m:
+            continue
+        gt, clu, nt, f1 = (int(x) for x in m.groups())
+        use = dict((k, int(v)) for k, v in re.findall(r"(\w+(?:\[0\])?):(\d+)", out[i + 1]))
+        seen += 1
+        if not gt or nt == 1024:
+            assert use["REG"] <= 64, (gt, clu, nt, f1, use)
+        assert use["STACK"] <= 256, (gt, clu, nt, f1, use)           # a few spilled words outside the hot loops, no more
+        assert use["CONSTANT[0]"] < 32 * 1024, (gt, clu, nt, f1, use)
+        assert use["SHARED"] - 1024 <= 1024, (gt, clu, nt, f1, use)  # static shared memory (the planner's budget assumes < 1 KB)
+    assert seen == 12
